@@ -1,0 +1,171 @@
+/* mrf_b200 -- C-ABI of the B200-native multi-robot-fabrics hot path.
+ *
+ * Drop-in boundary: these entry points are what a binding of the reference's planner call
+ * surface calls instead of evaluating the CasADi functions.  The reference is pure Python; the
+ * binding a maintainer adds is a ctypes stub.  What each entry replaces
+ * (paths relative to the reference repository root):
+ *
+ *   mrf_action_*          planner._funs._function / planner.compute_action(**kwargs)
+ *                         examples/example_pandas_Jointspace.py:417-445,
+ *                         multi_robot_fabrics/fabrics_planner/forward_planner_Cartesian.py:132-191
+ *   mrf_rollout_*         ForwardFabricsPlanner.forward_multi_fabrics_symbolic + get_velocity_rollouts
+ *                         + rollouts_numerical
+ *                         multi_robot_fabrics/fabrics_planner/forward_planner_Jointspace.py:118-296,298-423
+ *                         (with the RF-CV goal estimate of examples/example_pandas_Jointspace.py:346-348 and the
+ *                         end-effector FK of :236-238,328-329 fused in)
+ *   mrf_rollout_cart_*    FabricsRollouts.symbolic_forward_fabrics + rollouts_numerical + get_velocity_rollouts
+ *                         multi_robot_fabrics/fabrics_planner/forward_planner_Cartesian.py:347-489,538-563
+ *   mrf_deadlock_*        deadlockprevention.deadlock_checking
+ *                         multi_robot_fabrics/others_planner/deadlock_prevention.py:50-118
+ *   mrf_kinematics_*      UtilsKinematics.necessary_kinematics fk/jac/jac_dot functions
+ *                         multi_robot_fabrics/utils/utils.py:16-54 (as used at
+ *                         examples/example_pandas_Jointspace.py:324-343)
+ *
+ * Conventions
+ *  - Plain pointers and sizes; no exceptions cross the boundary.  Every function returns 0 on success or a
+ *    negative MRF_E* code; mrf_last_error() gives the message of the calling thread's last failure.
+ *  - "_dev" entries take DEVICE pointers owned by the caller, structure-of-arrays with the scenario index
+ *    fastest (layouts below), and are asynchronous on the given cudaStream_t (passed as void*).
+ *  - "_host" entries take HOST pointers in the reference's natural array-of-records order, copy to the device,
+ *    run the same kernels and copy the results back (synchronous).
+ *  - There is no CPU fallback: without a CUDA device mrf_create fails with MRF_ENODEV.
+ *  - A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef MRF_B200_H
+#define MRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRF_MAX_ROBOTS 4
+#define MRF_DOF 7
+#define MRF_NLINKS 8   /* panda_link1..8, examples/parameters_manipulators.py:25-26 */
+#define MRF_REC 44     /* scalars per robot record */
+#define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
+
+/* Per-robot record = the numeric arguments of one fabric action / of get_velocity_rollouts
+ * (forward_planner_Jointspace.py:303-329), fixed order:
+ *  [0..6] q  [7..13] qdot  [14..16] x_goal_0  [17] weight_goal_0  [18..20] x_goal_1  [21] weight_goal_1
+ *  [22] x_goal_2  [23] weight_goal_2  [24..32] angle_goal_1 (row-major 3x3)  [33..36] constraint_0
+ *  [37..42] radius_body_panda_link3..8  [43] reserved (0) */
+enum { MRF_Q = 0, MRF_QD = 7, MRF_G0 = 14, MRF_W0 = 17, MRF_G1 = 18, MRF_W1 = 21, MRF_G2 = 22, MRF_W2 = 23,
+       MRF_ANG = 24, MRF_CON = 33, MRF_RB = 37 };
+
+enum { MRF_OK = 0, MRF_EINVAL = -1, MRF_ENODEV = -2, MRF_ECUDA = -3, MRF_ENOMEM = -4, MRF_EUNSUPPORTED = -5 };
+
+/* Planner / rollout configuration (what the reference fixes at graph-construction time). */
+typedef struct MrfConfig {
+    int32_t struct_size;          /* sizeof(MrfConfig), ABI check */
+    int32_t n_robots;             /* 1..MRF_MAX_ROBOTS */
+    int32_t mode;                 /* 0 'acc', 1 'vel'  (planner.concretize(mode, time_step)) */
+    int32_t static_or_dyn;        /* STATIC_OR_DYN_FABRICS (forward_planner_Jointspace.py:215-217) */
+    int32_t has_collision_links;  /* 0: grasp planner, collision_links_nr=[] (example_pandas_Jointspace.py:160-166) */
+    int32_t estimate_goal;        /* ESTIMATE_GOAL: 0 off, 1 Jacobian-column-0 "velocity" (example_pandas_Jointspace.py:
+                                     236-238,346-348), 2 J*qdot (example_pandas_cartesian.py:355-357, utils.py:131) */
+    int32_t estimate_robot;       /* robot whose goal is estimated (1 in the reference) */
+    int32_t reserved0;
+    double estimate_horizon;      /* 20 * 0.01 (example_pandas_Jointspace.py:347) */
+    double dt;                    /* planner time_step == rollout dt (parameters_manipulators.py:8) */
+    double eps;                   /* fabrics eps, 1e-6 */
+    double jdot_sign;             /* fabrics DifferentialMap Jdot sign, -1 */
+    double jdot_ref_sign;         /* utils.py:28 Jdot_sign, -1 (published sphere accelerations) */
+    double exec_scale;            /* ExecutionLagrangian = exec_scale * qdot.qdot */
+    double mount[MRF_MAX_ROBOTS][16];              /* row-major 4x4, example_pandas_Jointspace.py:108-118 */
+    double limits[MRF_DOF][2];                     /* example_pandas_Jointspace.py:97-105 */
+    double r_robots[MRF_MAX_ROBOTS][MRF_NLINKS];   /* sphere radii of each robot's links as seen by the others
+                                                      (forward_planner_Jointspace.py:221) */
+    /* deadlock heuristic constants, deadlock_prevention.py:20-27,64,66 */
+    double dl_avg_vel_constant, dl_dist_constant, dl_goal_weight_follower, dl_goal_weight_leader;
+    double dl_nr_goal_scale, dl_dist_endeff, dl_backoff;
+    int32_t dl_time_wait, dl_time_gate;
+} MrfConfig;
+
+typedef struct MrfHandle_* mrf_handle_t;
+
+int mrf_version(void);
+const char* mrf_last_error(void);
+int mrf_config_default(MrfConfig* cfg, int n_robots);       /* the reference's 2/3-Panda set-up */
+int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out);
+int mrf_destroy(mrf_handle_t h);
+int mrf_device_count(void);
+
+/* ------------------------------- device-pointer entries (SoA) ---------------------------------
+ * B = number of scenarios, R = robots in the call, index b fastest:
+ *   rec    [MRF_REC][R][B]
+ *   obst   [S][MRF_OBST][R][B]          obstacle o of robot r in scenario b
+ *   action [MRF_DOF][R][B]
+ *   avg_vel[R][B]   x_ee [R][3][B]   goal_est [3][B]
+ *   qN, qdN [R][N][MRF_DOF][B]          (nullable)
+ */
+int mrf_action_dev_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S, const double* obst,
+                       double* action, int64_t B, void* stream);
+int mrf_action_dev_f32(mrf_handle_t h, int robot_first, int n_rob, const float* rec, int S, const float* obst,
+                       float* action, int64_t B, void* stream);
+
+int mrf_rollout_dev_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee, double* goal_est,
+                        double* qN, double* qdN, int64_t B, void* stream);
+int mrf_rollout_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                        float* qN, float* qdN, int64_t B, void* stream);
+
+/* Cartesian (decoupled) rollout of robot `robot`: obstacles move with constant velocity, xddot = 0.
+ *   rec [MRF_REC][B]  obst [S][MRF_OBST][B] (xddot ignored)  avg_vel [B]  qN,qdN [N][MRF_DOF][B] */
+int mrf_rollout_cart_dev_f64(mrf_handle_t h, int robot, const double* rec, int S, const double* obst, int N,
+                             double* avg_vel, double* qN, double* qdN, int64_t B, void* stream);
+int mrf_rollout_cart_dev_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,
+                             float* avg_vel, float* qN, float* qdN, int64_t B, void* stream);
+
+/* Link kinematics of the 8 collision links: x, v = J qdot, a = jdot_ref_sign * d(J qdot)/dq qdot.
+ *   q, qdot [MRF_DOF][R][B];  x, v, a [MRF_NLINKS][3][R][B] (nullable) */
+int mrf_kinematics_dev_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,
+                           int64_t B, void* stream);
+int mrf_kinematics_dev_f32(mrf_handle_t h, const float* q, const float* qdot, float* x, float* v, float* a,
+                           int64_t B, void* stream);
+
+/* Batched deadlock_checking step.  All arrays index b fastest; state arrays are updated in place.
+ *   x_ee [R][3][B]  goals [R][3][B] (in/out)  weights [R][B] (in/out)  avg_vel [R][B]
+ *   sm_state [R][B] (state-machine codes)  time_step [B]  time_deadlock_out [B] (in/out)
+ *   st_int [4][B]: i_leader, i_follower, i_robots_dead[0], i_robots_dead[1]  (in/out)
+ *   st_goal [3][B]: goal_robot0 (in/out)      flag [B] (out): 1 if `deadlock` was raised this step */
+int mrf_deadlock_dev_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights, const double* avg_vel,
+                         const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                         int32_t* st_int, double* st_goal, int32_t* flag, int64_t B, void* stream);
+int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* goals, float* weights, const float* avg_vel,
+                         const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                         int32_t* st_int, float* st_goal, int32_t* flag, int64_t B, void* stream);
+
+/* ------------------------------- host-pointer entries (AoS) -----------------------------------
+ *   rec [B][R][MRF_REC]   obst [B][R][S][MRF_OBST]   action [B][R][MRF_DOF]
+ *   avg_vel [B][R]  x_ee [B][R][3]  goal_est [B][3]  qN,qdN [B][R][N][MRF_DOF]  (nullable outputs skipped) */
+int mrf_action_host_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S, const double* obst,
+                        double* action, int64_t B);
+int mrf_action_host_f32(mrf_handle_t h, int robot_first, int n_rob, const float* rec, int S, const float* obst,
+                        float* action, int64_t B);
+int mrf_rollout_host_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee, double* goal_est,
+                         double* qN, double* qdN, int64_t B);
+int mrf_rollout_host_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                         float* qN, float* qdN, int64_t B);
+/*   rec [B][MRF_REC]  obst [B][S][MRF_OBST]  avg_vel [B]  qN,qdN [B][N][MRF_DOF] */
+int mrf_rollout_cart_host_f64(mrf_handle_t h, int robot, const double* rec, int S, const double* obst, int N,
+                              double* avg_vel, double* qN, double* qdN, int64_t B);
+int mrf_rollout_cart_host_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,
+                              float* avg_vel, float* qN, float* qdN, int64_t B);
+/*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */
+int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,
+                            int64_t B);
+
+/* Number of kernels this library has launched through handle h since creation (for bench accounting). */
+int64_t mrf_launch_count(mrf_handle_t h);
+/* Device time in ms of the last *_host_* call's kernel(s) (CUDA events on the handle's stream). */
+double mrf_last_kernel_ms(mrf_handle_t h);
+
+/* Measured FMA throughput (TFLOP/s, FMA = 2 flops) of the device's FP32 / FP64 pipes: the roofline denominator of
+ * the compute-bound kernels (8 independent chains per thread, 8 CTAs of 256 threads per SM, best of 5). */
+int mrf_fma_peak(mrf_handle_t h, int is_f64, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRF_B200_H */

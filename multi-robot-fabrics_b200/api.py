@@ -1,0 +1,195 @@
+"""Batched entry points over the C-ABI: numpy (host buffers) and torch (device tensors, hand-off only).
+
+`Fabrics` owns one handle on one GPU.  Host methods take the reference's natural array-of-records order;
+device methods take structure-of-arrays torch tensors (scenario index fastest) and launch on torch's current
+stream.  Nothing here computes: every number comes out of libmrf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DOF, NLINKS, OBST, REC, Handle, MrfError, check, default_config, hptr, lib
+
+_NP = {"f64": np.float64, "f32": np.float32}
+
+
+def _arr(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise MrfError(f"expected array of shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class Fabrics:
+    """One planner configuration (MrfConfig) on one B200."""
+
+    def __init__(self, n_robots: int = 2, device: int = 0, config=None, **overrides):
+        self.cfg = config if config is not None else default_config(n_robots, **overrides)
+        self.n_robots = int(self.cfg.n_robots)
+        self.device = device
+        self.handle = Handle(self.cfg, device)
+
+    def close(self):
+        self.handle.close()
+
+    # ------------------------------------------------------------------ host buffers (AoS)
+    def rollout_host(self, rec, N: int, dtype: str = "f64", trajectories: bool = False, out=None):
+        """rec (B,R,44) -> dict(avg_vel (B,R), x_ee (B,R,3), goal_est (B,3)[, qN, qdN (B,R,N,7)])."""
+        dt = _NP[dtype]
+        R = self.n_robots
+        rec = np.ascontiguousarray(rec, dtype=dt)
+        if rec.ndim == 2:
+            rec = rec[None]
+        if rec.shape[1:] != (R, REC):
+            raise MrfError(f"rec must be (B,{R},{REC}), got {rec.shape}")
+        B = rec.shape[0]
+        o = out if out is not None else {}
+        o.setdefault("avg_vel", np.empty((B, R), dt))
+        o.setdefault("x_ee", np.empty((B, R, 3), dt))
+        o.setdefault("goal_est", np.empty((B, 3), dt))
+        if trajectories:
+            o.setdefault("qN", np.empty((B, R, N, DOF), dt))
+            o.setdefault("qdN", np.empty((B, R, N, DOF), dt))
+        fn = getattr(lib(), f"mrf_rollout_host_{dtype}")
+        check(fn(self.handle.ptr, hptr(rec), N, hptr(o["avg_vel"]), hptr(o["x_ee"]), hptr(o["goal_est"]),
+                 hptr(o.get("qN")), hptr(o.get("qdN")), B), "mrf_rollout_host")
+        return o
+
+    def action_host(self, rec, obst=None, robot_first: int = 0, dtype: str = "f64"):
+        """rec (B,n_rob,44), obst (B,n_rob,S,10) -> action (B,n_rob,7)."""
+        dt = _NP[dtype]
+        rec = np.ascontiguousarray(rec, dtype=dt)
+        if rec.ndim == 2:
+            rec = rec[:, None, :]
+        B, n_rob = rec.shape[0], rec.shape[1]
+        if obst is None:
+            S, obst_a = 0, None
+        else:
+            obst_a = np.ascontiguousarray(obst, dtype=dt).reshape(B, n_rob, -1, OBST)
+            S = obst_a.shape[2]
+            if S == 0:
+                obst_a = None
+        act = np.empty((B, n_rob, DOF), dt)
+        fn = getattr(lib(), f"mrf_action_host_{dtype}")
+        check(fn(self.handle.ptr, robot_first, n_rob, hptr(rec), S, hptr(obst_a), hptr(act), B), "mrf_action_host")
+        return act
+
+    def rollout_cart_host(self, robot: int, rec, obst, N: int, dtype: str = "f64", trajectories: bool = True):
+        """rec (B,44), obst (B,S,10) -> avg_vel (B,), qN, qdN (B,N,7)."""
+        dt = _NP[dtype]
+        rec = np.ascontiguousarray(rec, dtype=dt).reshape(-1, REC)
+        B = rec.shape[0]
+        obst_a = np.ascontiguousarray(obst, dtype=dt).reshape(B, -1, OBST)
+        S = obst_a.shape[1]
+        avg = np.empty((B,), dt)
+        qN = np.empty((B, N, DOF), dt) if trajectories else None
+        qdN = np.empty((B, N, DOF), dt) if trajectories else None
+        fn = getattr(lib(), f"mrf_rollout_cart_host_{dtype}")
+        check(fn(self.handle.ptr, robot, hptr(rec), S, hptr(obst_a if S else None), N, hptr(avg), hptr(qN), hptr(qdN), B),
+              "mrf_rollout_cart_host")
+        return avg, qN, qdN
+
+    def kinematics_host(self, q, qdot):
+        """q, qdot (B,R,7) -> x, v, a (B,R,8,3); a = jdot_ref_sign * d(J qdot)/dq qdot (utils.py:28,37)."""
+        R = self.n_robots
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, R, DOF)
+        qd = np.ascontiguousarray(qdot, dtype=np.float64).reshape(-1, R, DOF)
+        B = q.shape[0]
+        x, v, a = (np.empty((B, R, NLINKS, 3)) for _ in range(3))
+        check(lib().mrf_kinematics_host_f64(self.handle.ptr, hptr(q), hptr(qd), hptr(x), hptr(v), hptr(a), B),
+              "mrf_kinematics_host")
+        return x, v, a
+
+    # ------------------------------------------------------------------ device tensors (SoA)
+    @staticmethod
+    def _tp(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def _prec(t):
+        import torch
+        if t.dtype == torch.float64:
+            return "f64"
+        if t.dtype == torch.float32:
+            return "f32"
+        raise MrfError(f"unsupported dtype {t.dtype}")
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def rollout_dev(self, rec, N: int, avg_vel=None, x_ee=None, goal_est=None, qN=None, qdN=None):
+        """rec: torch (44,R,B) on this device; outputs as in include/mrf_b200.h (allocated if None for avg_vel)."""
+        import torch
+        p = self._prec(rec)
+        _, R, B = rec.shape
+        if R != self.n_robots or rec.shape[0] != REC or not rec.is_contiguous():
+            raise MrfError("rec must be a contiguous (44,R,B) tensor")
+        if avg_vel is None:
+            avg_vel = torch.empty((R, B), dtype=rec.dtype, device=rec.device)
+        fn = getattr(lib(), f"mrf_rollout_dev_{p}")
+        check(fn(self.handle.ptr, self._tp(rec), N, self._tp(avg_vel), self._tp(x_ee), self._tp(goal_est), self._tp(qN),
+                 self._tp(qdN), B, self._stream()), "mrf_rollout_dev")
+        return avg_vel
+
+    def action_dev(self, rec, obst, action=None, robot_first: int = 0):
+        """rec (44,n_rob,B), obst (S,10,n_rob,B) or None -> action (7,n_rob,B)."""
+        import torch
+        p = self._prec(rec)
+        _, n_rob, B = rec.shape
+        S = 0 if obst is None else obst.shape[0]
+        if action is None:
+            action = torch.empty((DOF, n_rob, B), dtype=rec.dtype, device=rec.device)
+        fn = getattr(lib(), f"mrf_action_dev_{p}")
+        check(fn(self.handle.ptr, robot_first, n_rob, self._tp(rec), S, self._tp(obst), self._tp(action), B,
+                 self._stream()), "mrf_action_dev")
+        return action
+
+    def rollout_cart_dev(self, robot: int, rec, obst, N: int, avg_vel=None, qN=None, qdN=None):
+        import torch
+        p = self._prec(rec)
+        B = rec.shape[-1]
+        S = 0 if obst is None else obst.shape[0]
+        if avg_vel is None:
+            avg_vel = torch.empty((B,), dtype=rec.dtype, device=rec.device)
+        fn = getattr(lib(), f"mrf_rollout_cart_dev_{p}")
+        check(fn(self.handle.ptr, robot, self._tp(rec), S, self._tp(obst), N, self._tp(avg_vel), self._tp(qN),
+                 self._tp(qdN), B, self._stream()), "mrf_rollout_cart_dev")
+        return avg_vel
+
+    def kinematics_dev(self, q, qdot, x=None, v=None, a=None):
+        import torch
+        p = self._prec(q)
+        _, R, B = q.shape
+        mk = lambda: torch.empty((NLINKS, 3, R, B), dtype=q.dtype, device=q.device)
+        x = mk() if x is None else x
+        v = mk() if v is None else v
+        a = mk() if a is None else a
+        fn = getattr(lib(), f"mrf_kinematics_dev_{p}")
+        check(fn(self.handle.ptr, self._tp(q), self._tp(qdot), self._tp(x), self._tp(v), self._tp(a), B, self._stream()),
+              "mrf_kinematics_dev")
+        return x, v, a
+
+    def deadlock_dev(self, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
+                     flag=None):
+        """Batched deadlock_checking step; goals/weights/time_deadlock_out/st_* are updated in place."""
+        import torch
+        p = self._prec(x_ee)
+        B = x_ee.shape[-1]
+        if flag is None:
+            flag = torch.empty((B,), dtype=torch.int32, device=x_ee.device)
+        fn = getattr(lib(), f"mrf_deadlock_dev_{p}")
+        check(fn(self.handle.ptr, self._tp(x_ee), self._tp(goals), self._tp(weights), self._tp(avg_vel),
+                 self._tp(sm_state), self._tp(time_step), self._tp(time_deadlock_out), self._tp(st_int),
+                 self._tp(st_goal), self._tp(flag), B, self._stream()), "mrf_deadlock_dev")
+        return flag
+
+
+def to_soa(rec):
+    """(B,R,F) array-of-records -> (F,R,B) structure-of-arrays (numpy or torch)."""
+    if isinstance(rec, np.ndarray):
+        return np.ascontiguousarray(rec.transpose(2, 1, 0))
+    return rec.permute(2, 1, 0).contiguous()

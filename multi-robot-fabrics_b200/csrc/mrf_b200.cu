@@ -1,0 +1,949 @@
+// mrf_b200.cu -- __global__ kernels and the C-ABI (include/mrf_b200.h) of the B200-native
+// multi-robot-fabrics hot path.  Build: see __graft_entry__.build()
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared ...
+//
+// Kernels
+//   rollout_kernel<T>   coupled joint-space Rollout Fabrics (RF / RF-CV), persistent over the horizon.
+//                       CTA = R warps x 32 lanes; warp r = robot r, lane = scenario of the CTA's 32-scenario
+//                       tile.  Every step each thread re-computes its own chain (Phase A), publishes its five
+//                       moving link points through shared memory, and evaluates its fabric action against the
+//                       other robots' points (Phase B).  Reference: ForwardFabricsPlanner
+//                       multi_robot_fabrics/fabrics_planner/forward_planner_Jointspace.py:118-296,298-423.
+//   action_kernel<T>    one fabric action per (scenario, robot) against caller-supplied obstacle spheres.
+//                       Reference: planner.compute_action, examples/example_pandas_Jointspace.py:417-445.
+//   cart_kernel<T>      decoupled rollout with constant-velocity obstacles.  Reference: FabricsRollouts
+//                       multi_robot_fabrics/fabrics_planner/forward_planner_Cartesian.py:347-489.
+//   kinematics_kernel   fk / J qdot / Jdot qdot of the 8 collision links (utils.py:16-54).
+//   deadlock_kernel     deadlockprevention.deadlock_checking (others_planner/deadlock_prevention.py:50-118).
+//   transpose kernels   AoS <-> SoA staging for the host-pointer entries.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mrf_b200.h"
+#include "mrf_device.cuh"
+#include "mrf_devcfg.h"
+
+namespace mrf {
+
+// ------------------------------------------------------------------------------------------------
+// coupled joint-space rollout
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kTile* MRF_MAX_ROBOTS)
+    rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
+                   T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x, tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile, R = cfg.n_robots;
+    T* kin = reinterpret_cast<T*>(smem_raw);
+    T* prm = kin + kKin * NT;
+    const long long b = (long long)blockIdx.x * kTile + lane;
+    const bool live = b < B;
+    const long long bb = live ? b : B - 1; // idle lanes shadow the last scenario so barriers stay uniform
+    auto ld = [&](int f) { return rec[((long long)f * R + r) * B + bb]; };
+
+    T q[kDof], qd[kDof];
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        q[i] = ld(MRF_Q + i);
+        qd[i] = ld(MRF_QD + i);
+    }
+    load_params<T>(ld, prm, NT, tid);
+    Chain<T> ch;
+
+    if (x_ee != nullptr || goal_est != nullptr || cfg.estimate_goal) {
+        // end-effector FK at the measured state (example_pandas_Jointspace.py:236-238,328-329) and the RF-CV
+        // constant-velocity goal estimate of one robot (:346-348)
+        chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+        V3<T> p8 = kin_load(kin, NT, tid, 4, 0);
+        if (x_ee != nullptr && live) {
+            x_ee[((long long)r * 3 + 0) * B + b] = p8.x;
+            x_ee[((long long)r * 3 + 1) * B + b] = p8.y;
+            x_ee[((long long)r * 3 + 2) * B + b] = p8.z;
+        }
+        if (r == cfg.estimate_robot) {
+            V3<T> g = mk(prm[(P_G0 + 0) * NT + tid], prm[(P_G0 + 1) * NT + tid], prm[(P_G0 + 2) * NT + tid]);
+            if (cfg.estimate_goal) {
+                V3<T> l1 = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
+                // mode 1: first COLUMN of the hand Jacobian (the reference's "v_ee"); mode 2: J qdot
+                V3<T> v = cfg.estimate_goal == 1 ? cross(ch.z[0], p8 - l1) : kin_load(kin, NT, tid, 4, 3);
+                g = p8 + v * cfg.est_h;
+                prm[(P_G0 + 0) * NT + tid] = g.x;
+                prm[(P_G0 + 1) * NT + tid] = g.y;
+                prm[(P_G0 + 2) * NT + tid] = g.z;
+            }
+            if (goal_est != nullptr && live) {
+                goal_est[0 * B + b] = g.x;
+                goal_est[1 * B + b] = g.y;
+                goal_est[2 * B + b] = g.z;
+            }
+        }
+    }
+
+    SmemSrc<T> src{cfg, kin, NT, lane, r, cfg.static_or_dyn ? T(1) : T(0), cfg.static_or_dyn ? cfg.sref : T(0)};
+    T acc = T(0);
+    for (int k = 0; k < N; ++k) {
+        // Phase A (forward_planner_Jointspace.py:191-209): step with the stale velocity, then FK
+#pragma unroll
+        for (int i = 0; i < kDof; ++i) q[i] += cfg.dt * qd[i];
+        __syncthreads(); // readers of the previous step are done
+        chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+        __syncthreads(); // every robot of the tile has published
+        // Phase B (:211-249): action against the other robots' published spheres
+        T act[kDof];
+        fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+#pragma unroll
+        for (int i = 0; i < kDof; ++i) {
+            qd[i] = act[i];
+            acc += act[i] * act[i];
+        }
+        if (qN != nullptr && live) {
+#pragma unroll
+            for (int i = 0; i < kDof; ++i) qN[(((long long)r * N + k) * kDof + i) * B + b] = q[i];
+        }
+        if (qdN != nullptr && live) {
+#pragma unroll
+            for (int i = 0; i < kDof; ++i) qdN[(((long long)r * N + k) * kDof + i) * B + b] = qd[i];
+        }
+    }
+    // compute_velocity_average (:102-116): mean SQUARE joint velocity over the horizon
+    if (avg_vel != nullptr && live) avg_vel[(long long)r * B + b] = acc / (T(N) * T(kDof));
+}
+
+// ------------------------------------------------------------------------------------------------
+// single action / decoupled rollout: thread = (robot, scenario), obstacles from global memory
+// ------------------------------------------------------------------------------------------------
+constexpr int kActThreads = 128;
+
+template <typename T, bool CART>
+__global__ void __launch_bounds__(kActThreads)
+    action_kernel(const __grid_constant__ DevCfg<T> cfg, int robot_first, int n_rob, const T* __restrict__ rec, int S,
+                  const T* __restrict__ obst, int N, T* __restrict__ out, T* __restrict__ qN, T* __restrict__ qdN,
+                  long long B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x, tid = threadIdx.x;
+    T* kin = reinterpret_cast<T*>(smem_raw);
+    T* prm = kin + kKin * NT;
+    const long long total = (long long)n_rob * B;
+    long long idx = (long long)blockIdx.x * NT + tid;
+    const bool live = idx < total;
+    if (!live) idx = total - 1;
+    const int rl = (int)(idx / B);
+    const long long b = idx - (long long)rl * B;
+    const int r = robot_first + rl;
+    const long long stride = total;
+    auto ld = [&](int f) { return rec[(long long)f * stride + idx]; };
+    T q[kDof], qd[kDof];
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        q[i] = ld(MRF_Q + i);
+        qd[i] = ld(MRF_QD + i);
+    }
+    load_params<T>(ld, prm, NT, tid);
+    Chain<T> ch;
+    GlobalSrc<T, CART> src{obst, stride, idx, S, T(0)};
+    if (!CART) {
+        T act[kDof];
+        chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+        fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < kDof; ++i) out[(long long)i * stride + idx] = act[i];
+        }
+    } else {
+        // forward_planner_Cartesian.py:421-458: evaluate, then step robot and obstacles
+        T acc = T(0);
+        for (int k = 0; k < N; ++k) {
+            T act[kDof];
+            src.tk = T(k) * cfg.dt;
+            chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+#pragma unroll
+            for (int i = 0; i < kDof; ++i) {
+                qd[i] = act[i];
+                q[i] += cfg.dt * act[i];
+                acc += act[i] * act[i];
+            }
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < kDof; ++i) {
+                    if (qN != nullptr) qN[((long long)k * kDof + i) * B + b] = q[i];
+                    if (qdN != nullptr) qdN[((long long)k * kDof + i) * B + b] = qd[i];
+                }
+            }
+        }
+        if (out != nullptr && live) out[b] = acc / (T(N) * T(kDof));
+    }
+}
+
+// fk / J qdot / jdot_ref_sign * Jdot qdot of the 8 collision links
+template <typename T>
+__global__ void __launch_bounds__(kActThreads)
+    kinematics_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ qin, const T* __restrict__ qdin,
+                      T* __restrict__ x, T* __restrict__ v, T* __restrict__ a, long long B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x, tid = threadIdx.x, R = cfg.n_robots;
+    T* kin = reinterpret_cast<T*>(smem_raw);
+    const long long total = (long long)R * B;
+    long long idx = (long long)blockIdx.x * NT + tid;
+    const bool live = idx < total;
+    if (!live) idx = total - 1;
+    const int r = (int)(idx / B);
+    T q[kDof], qd[kDof];
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        q[i] = qin[(long long)i * total + idx];
+        qd[i] = qdin[(long long)i * total + idx];
+    }
+    Chain<T> ch;
+    chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+    if (!live) return;
+    const int emap[8] = {-1, -1, 0, 1, 2, 2, 3, 4};
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        V3<T> xx, vv, aa;
+        if (emap[l] < 0) {
+            xx = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
+            vv = mk(T(0), T(0), T(0));
+            aa = vv;
+        } else {
+            xx = kin_load(kin, NT, tid, emap[l], 0);
+            vv = kin_load(kin, NT, tid, emap[l], 3);
+            aa = kin_load(kin, NT, tid, emap[l], 6) * cfg.sref;
+        }
+        if (x) { x[((long long)l * 3 + 0) * total + idx] = xx.x; x[((long long)l * 3 + 1) * total + idx] = xx.y; x[((long long)l * 3 + 2) * total + idx] = xx.z; }
+        if (v) { v[((long long)l * 3 + 0) * total + idx] = vv.x; v[((long long)l * 3 + 1) * total + idx] = vv.y; v[((long long)l * 3 + 2) * total + idx] = vv.z; }
+        if (a) { a[((long long)l * 3 + 0) * total + idx] = aa.x; a[((long long)l * 3 + 1) * total + idx] = aa.y; a[((long long)l * 3 + 2) * total + idx] = aa.z; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deadlock heuristic, one thread per scenario (deadlock_prevention.py:50-118)
+// ------------------------------------------------------------------------------------------------
+struct DlCfg {
+    int R, time_wait, time_gate;
+    double avg_vel_constant, dist_constant, w_follower, w_leader, goal_scale, dist_endeff, backoff;
+};
+
+template <typename T>
+__global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
+                                const T* __restrict__ avg_vel, const int* __restrict__ sm_state,
+                                const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
+                                T* __restrict__ st_goal, int* __restrict__ flag, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int R = c.R;
+    // the reference does this arithmetic in float64 whatever the planner precision
+    double x[MRF_MAX_ROBOTS][3], g[MRF_MAX_ROBOTS][3], dist_goal[MRF_MAX_ROBOTS];
+    int st[MRF_MAX_ROBOTS];
+    double avg_sum = 0.0;
+    for (int i = 0; i < R; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
+            g[i][k] = (double)goals[((long long)i * 3 + k) * B + b];
+        }
+        double dx = x[i][0] - g[i][0], dy = x[i][1] - g[i][1], dz = x[i][2] - g[i][2];
+        dist_goal[i] = sqrt(dx * dx + dy * dy + dz * dz);
+        st[i] = sm_state[(long long)i * B + b];
+        avg_sum += (double)avg_vel[(long long)i * B + b];
+    }
+    avg_sum /= (double)R; // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375)
+    const int ts = time_step[b];
+    int t_out = tdo[b];
+    int i_leader = st_int[0 * B + b], i_follower = st_int[1 * B + b];
+    int dead0 = st_int[2 * B + b], dead1 = st_int[3 * B + b];
+    bool deadlock = false;
+    double min_dist = 100.0; // deadlock_distance initial value / deadlock_min_dist (:57,74)
+    for (int a = 0; a < R; ++a)
+        for (int bq = a + 1; bq < R; ++bq) { // itertools.combinations order (:29-30)
+            double dsum = dist_goal[a] + dist_goal[bq];
+            bool check_state = (st[a] == 0 || st[a] == 1) && (st[bq] == 0 || st[bq] == 1);
+            double dx = x[a][0] - x[bq][0], dy = x[a][1] - x[bq][1], dz = x[a][2] - x[bq][2];
+            double de = sqrt(dx * dx + dy * dy + dz * dz);
+            if (avg_sum < c.avg_vel_constant && dsum > c.dist_constant && ts > c.time_gate && check_state &&
+                de < c.dist_endeff) {
+                deadlock = true;
+                // after each hit the reference rescans all pairs for the minimum recorded distance with a
+                // strict '<' (:74-80): the first pair reaching the minimum wins
+                if (de < min_dist) {
+                    min_dist = de;
+                    dead0 = a;
+                    dead1 = bq;
+                }
+            }
+        }
+    int fl = 0;
+    double g0[3] = {(double)st_goal[0 * B + b], (double)st_goal[1 * B + b], (double)st_goal[2 * B + b]};
+    bool apply = false;
+    if (deadlock && ts > c.time_gate) {
+        fl = 1;
+        if (dist_goal[dead0] > dist_goal[dead1]) {
+            i_leader = dead1;
+            i_follower = dead0;
+        } else {
+            i_leader = dead0;
+            i_follower = dead1;
+        }
+        double d[3], dg[3], nrm = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            d[k] = x[i_leader][k] - x[i_follower][k];
+            dg[k] = d[k] * c.goal_scale;
+            nrm += dg[k] * dg[k];
+        }
+        nrm = sqrt(nrm);
+        for (int k = 0; k < 3; ++k)
+            g0[k] = nrm > 0.05 ? x[i_follower][k] - c.backoff / nrm * dg[k] : x[i_follower][k] - d[k] * c.goal_scale;
+        if (g0[2] < 0.0) g0[2] = 0.1;
+        apply = true;
+        t_out = 0;
+    } else if (st[dead0] == 2 || st[dead1] == 2) {
+        t_out = 400;
+    } else if (t_out < c.time_wait) {
+        apply = true;
+        t_out = t_out + 1;
+    }
+    if (apply) {
+        weights[(long long)i_leader * B + b] = (T)c.w_leader;
+        weights[(long long)i_follower * B + b] = (T)c.w_follower;
+        for (int k = 0; k < 3; ++k) goals[((long long)i_follower * 3 + k) * B + b] = (T)g0[k];
+    }
+    tdo[b] = t_out;
+    st_int[0 * B + b] = i_leader;
+    st_int[1 * B + b] = i_follower;
+    st_int[2 * B + b] = dead0;
+    st_int[3 * B + b] = dead1;
+    for (int k = 0; k < 3; ++k) st_goal[k * B + b] = (T)g0[k];
+    if (flag) flag[b] = fl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AoS <-> SoA staging:  aos[b][f] <-> soa[f][b], tiled through shared memory so both sides coalesce
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool TO_SOA>
+__global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, long long B, int F) {
+    __shared__ T tile[32][33];
+    const long long b0 = (long long)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    if (TO_SOA) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) { // rows = b, cols = f (contiguous in aos)
+            long long b = b0 + i;
+            int f = f0 + threadIdx.x;
+            if (b < B && f < F) tile[i][threadIdx.x] = in[b * F + f];
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            int f = f0 + i;
+            long long b = b0 + threadIdx.x;
+            if (b < B && f < F) out[(long long)f * B + b] = tile[threadIdx.x][i];
+        }
+    } else {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) { // rows = f, cols = b (contiguous in soa)
+            int f = f0 + i;
+            long long b = b0 + threadIdx.x;
+            if (b < B && f < F) tile[i][threadIdx.x] = in[(long long)f * B + b];
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            long long b = b0 + i;
+            int f = f0 + threadIdx.x;
+            if (b < B && f < F) out[b * F + f] = tile[threadIdx.x][i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FMA peak micro-benchmark: the roofline denominator for the compute-bound rollout (MEASURED_PEAKS.json
+// holds HBM and bf16 tensor peaks only).  8 independent FMA chains per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T b, T c) {
+    T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+} // namespace mrf
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+using namespace mrf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define MRF_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(MRF_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct MrfHandle_ {
+    MrfConfig cfg;
+    int device;
+    DevCfg<float> c32;
+    DevCfg<double> c64;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    void* stage[8];
+    size_t stage_bytes[8];
+    long long launches;
+    double last_ms;
+};
+
+extern "C" int mrf_version(void) { return 100; }
+extern "C" const char* mrf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mrf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
+    if (!c || n_robots < 1 || n_robots > MRF_MAX_ROBOTS) return fail(MRF_EINVAL, "mrf_config_default: bad arguments");
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(MrfConfig);
+    c->n_robots = n_robots;
+    c->mode = 1;                // fabrics_mode "vel", parameters_manipulators.py:12
+    c->static_or_dyn = 1;       // panda_config.yaml:4
+    c->has_collision_links = 1;
+    c->estimate_goal = 0;
+    c->estimate_robot = 1;      // example_pandas_Jointspace.py:347-348
+    c->estimate_horizon = 20 * 0.01;
+    c->dt = 0.01;
+    c->eps = 1e-6;
+    c->jdot_sign = -1.0;
+    c->jdot_ref_sign = -1.0;    // utils.py:28
+    c->exec_scale = 1.0;
+    static const double pos[4][3] = {{0.0, 0.0, 0.65}, {1.0, 0.0, 0.65}, {0.7, 0.6, 0.65}, {0.0, 0.0, 0.65}};
+    for (int r = 0; r < MRF_MAX_ROBOTS; ++r) { // parameters_manipulators.py:83-110,138-150
+        const double yaw = r == 0 ? 0.0 : M_PI;
+        double* T = c->mount[r];
+        T[0] = cos(yaw); T[1] = -sin(yaw); T[4] = sin(yaw); T[5] = cos(yaw); T[10] = 1.0; T[15] = 1.0;
+        T[3] = pos[r][0]; T[7] = pos[r][1]; T[11] = pos[r][2];
+        for (int l = 0; l < MRF_NLINKS; ++l) c->r_robots[r][l] = 0.08; // parameters_manipulators.py:23
+    }
+    static const double lim[7][2] = {{-2.8973, 2.8973}, {-1.7628, 1.7628}, {-2.8973, 2.8973}, {-3.0718, -0.0698},
+                                     {-2.8973, 2.8973}, {-0.0175, 3.7525}, {-2.8973, 2.8973}};
+    memcpy(c->limits, lim, sizeof(lim));
+    c->dl_avg_vel_constant = 0.16;  // deadlock_prevention.py:20-27
+    c->dl_dist_constant = 0.0;
+    c->dl_goal_weight_follower = 2.0;
+    c->dl_goal_weight_leader = 3.0;
+    c->dl_nr_goal_scale = 2.0;
+    c->dl_dist_endeff = 0.35;       // :64
+    c->dl_backoff = 0.3;            // :96
+    c->dl_time_wait = 300;
+    c->dl_time_gate = 10;           // :66,83
+    return MRF_OK;
+}
+
+extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
+    if (!cfg || !out) return fail(MRF_EINVAL, "mrf_create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(MrfConfig)) return fail(MRF_EINVAL, "mrf_create: MrfConfig size mismatch");
+    if (cfg->n_robots < 1 || cfg->n_robots > MRF_MAX_ROBOTS) return fail(MRF_EINVAL, "mrf_create: n_robots out of range");
+    if (cfg->mode != 0 && cfg->mode != 1) return fail(MRF_EINVAL, "mrf_create: mode must be 0 (acc) or 1 (vel)");
+    if (cfg->estimate_goal && (cfg->estimate_robot < 0 || cfg->estimate_robot >= cfg->n_robots))
+        return fail(MRF_EINVAL, "mrf_create: estimate_robot out of range");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MRF_ENODEV, "mrf_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(MRF_EINVAL, "mrf_create: bad device index");
+    MRF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MRF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(MRF_EUNSUPPORTED, "mrf_create: built for sm_100a (B200) only");
+    MrfHandle_* h = new (std::nothrow) MrfHandle_();
+    if (!h) return fail(MRF_ENOMEM, "mrf_create: out of memory");
+    h->cfg = *cfg;
+    h->device = device;
+    fill_devcfg(*cfg, h->c32);
+    fill_devcfg(*cfg, h->c64);
+    MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MRF_CUDA(cudaEventCreate(&h->ev0));
+    MRF_CUDA(cudaEventCreate(&h->ev1));
+    *out = h;
+    return MRF_OK;
+}
+
+extern "C" int mrf_destroy(mrf_handle_t h) {
+    if (!h) return MRF_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 8; ++i)
+        if (h->stage[i]) cudaFree(h->stage[i]);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MRF_OK;
+}
+
+extern "C" int64_t mrf_launch_count(mrf_handle_t h) { return h ? h->launches : 0; }
+extern "C" double mrf_last_kernel_ms(mrf_handle_t h) { return h ? h->last_ms : 0.0; }
+
+template <typename T> static const DevCfg<T>& devcfg(mrf_handle_t h);
+template <> const DevCfg<float>& devcfg<float>(mrf_handle_t h) { return h->c32; }
+template <> const DevCfg<double>& devcfg<double>(mrf_handle_t h) { return h->c64; }
+
+template <typename K> static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) MRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return MRF_OK;
+}
+
+// ---------------------------------- device-pointer entries --------------------------------------
+template <typename T>
+static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
+                       void* stream) {
+    if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
+    if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
+    if (h->cfg.mode != 1)
+        return fail(MRF_EUNSUPPORTED, "mrf_rollout: the joint-space rollout is defined for mode 'vel' only "
+                                      "(forward_planner_Jointspace.py:197-201,233)");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = h->cfg.n_robots, NT = kTile * R;
+    const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * NT;
+    int rc = set_smem(rollout_kernel<T>, smem);
+    if (rc) return rc;
+    const long long grid = (B + kTile - 1) / kTile;
+    rollout_kernel<T><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est,
+                                                                         qN, qdN, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+
+template <typename T, bool CART>
+static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, int S, const T* obst, int N, T* out,
+                      T* qN, T* qdN, int64_t B, void* stream) {
+    if (!h || !rec || (S > 0 && !obst)) return fail(MRF_EINVAL, "mrf_action: null argument");
+    if (B <= 0 || S < 0 || n_rob < 1 || robot_first < 0 || robot_first + n_rob > h->cfg.n_robots)
+        return fail(MRF_EINVAL, "mrf_action: bad sizes");
+    if (CART && (N <= 0 || h->cfg.mode != 1)) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0 and mode 'vel'");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * kActThreads;
+    int rc = set_smem(action_kernel<T, CART>, smem);
+    if (rc) return rc;
+    const long long total = (long long)n_rob * B;
+    const long long grid = (total + kActThreads - 1) / kActThreads;
+    action_kernel<T, CART><<<(unsigned)grid, kActThreads, smem, (cudaStream_t)stream>>>(
+        devcfg<T>(h), robot_first, n_rob, rec, S, obst, N, out, qN, qdN, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+
+template <typename T>
+static int kinematics_dev(mrf_handle_t h, const T* q, const T* qd, T* x, T* v, T* a, int64_t B, void* stream) {
+    if (!h || !q || !qd) return fail(MRF_EINVAL, "mrf_kinematics: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_kinematics: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const size_t smem = sizeof(T) * (size_t)kKin * kActThreads;
+    int rc = set_smem(kinematics_kernel<T>, smem);
+    if (rc) return rc;
+    const long long total = (long long)h->cfg.n_robots * B;
+    kinematics_kernel<T><<<(unsigned)((total + kActThreads - 1) / kActThreads), kActThreads, smem, (cudaStream_t)stream>>>(
+        devcfg<T>(h), q, qd, x, v, a, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+
+template <typename T>
+static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const int32_t* sm_state,
+                        const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal, int32_t* flag, int64_t B,
+                        void* stream) {
+    if (!h || !x_ee || !goals || !weights || !avg_vel || !sm_state || !time_step || !tdo || !st_int || !st_goal)
+        return fail(MRF_EINVAL, "mrf_deadlock: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_deadlock: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const MrfConfig& c = h->cfg;
+    DlCfg d{c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
+            c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
+    deadlock_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        d, x_ee, goals, weights, avg_vel, sm_state, time_step, tdo, st_int, st_goal, flag, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+
+extern "C" int mrf_rollout_dev_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee,
+                                   double* goal_est, double* qN, double* qdN, int64_t B, void* stream) {
+    return rollout_dev<double>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream);
+}
+extern "C" int mrf_rollout_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                                   float* qN, float* qdN, int64_t B, void* stream) {
+    return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream);
+}
+extern "C" int mrf_action_dev_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S,
+                                  const double* obst, double* action, int64_t B, void* stream) {
+    return action_dev<double, false>(h, robot_first, n_rob, rec, S, obst, 0, action, nullptr, nullptr, B, stream);
+}
+extern "C" int mrf_action_dev_f32(mrf_handle_t h, int robot_first, int n_rob, const float* rec, int S, const float* obst,
+                                  float* action, int64_t B, void* stream) {
+    return action_dev<float, false>(h, robot_first, n_rob, rec, S, obst, 0, action, nullptr, nullptr, B, stream);
+}
+extern "C" int mrf_rollout_cart_dev_f64(mrf_handle_t h, int robot, const double* rec, int S, const double* obst, int N,
+                                        double* avg_vel, double* qN, double* qdN, int64_t B, void* stream) {
+    return action_dev<double, true>(h, robot, 1, rec, S, obst, N, avg_vel, qN, qdN, B, stream);
+}
+extern "C" int mrf_rollout_cart_dev_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,
+                                        float* avg_vel, float* qN, float* qdN, int64_t B, void* stream) {
+    return action_dev<float, true>(h, robot, 1, rec, S, obst, N, avg_vel, qN, qdN, B, stream);
+}
+extern "C" int mrf_kinematics_dev_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v,
+                                      double* a, int64_t B, void* stream) {
+    return kinematics_dev<double>(h, q, qdot, x, v, a, B, stream);
+}
+extern "C" int mrf_kinematics_dev_f32(mrf_handle_t h, const float* q, const float* qdot, float* x, float* v, float* a,
+                                      int64_t B, void* stream) {
+    return kinematics_dev<float>(h, q, qdot, x, v, a, B, stream);
+}
+extern "C" int mrf_deadlock_dev_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights,
+                                    const double* avg_vel, const int32_t* sm_state, const int32_t* time_step,
+                                    int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag,
+                                    int64_t B, void* stream) {
+    return deadlock_dev<double>(h, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
+                                flag, B, stream);
+}
+extern "C" int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* goals, float* weights, const float* avg_vel,
+                                    const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                                    int32_t* st_int, float* st_goal, int32_t* flag, int64_t B, void* stream) {
+    return deadlock_dev<float>(h, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
+                               flag, B, stream);
+}
+
+// ---------------------------------- host-pointer entries ----------------------------------------
+static int stage_reserve(mrf_handle_t h, int slot, size_t bytes) {
+    if (h->stage_bytes[slot] >= bytes) return MRF_OK;
+    if (h->stage[slot]) MRF_CUDA(cudaFree(h->stage[slot]));
+    h->stage[slot] = nullptr;
+    h->stage_bytes[slot] = 0;
+    size_t want = bytes + bytes / 4;
+    if (cudaMalloc(&h->stage[slot], want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MRF_ENOMEM, "mrf: device allocation failed");
+    }
+    h->stage_bytes[slot] = want;
+    return MRF_OK;
+}
+
+// host AoS [B][F] -> device SoA [F][B] in stage[soa_slot] (via stage[aos_slot])
+template <typename T>
+static int upload_soa(mrf_handle_t h, const T* host, long long B, int F, int aos_slot, int soa_slot) {
+    const size_t bytes = sizeof(T) * (size_t)B * F;
+    int rc = stage_reserve(h, aos_slot, bytes);
+    if (rc) return rc;
+    rc = stage_reserve(h, soa_slot, bytes);
+    if (rc) return rc;
+    MRF_CUDA(cudaMemcpyAsync(h->stage[aos_slot], host, bytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+    transpose_kernel<T, true><<<grid, block, 0, h->stream>>>((const T*)h->stage[aos_slot], (T*)h->stage[soa_slot], B, F);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+// device SoA [F][B] in stage[soa_slot] -> host AoS [B][F] (via stage[aos_slot])
+template <typename T>
+static int download_aos(mrf_handle_t h, T* host, long long B, int F, int soa_slot, int aos_slot) {
+    const size_t bytes = sizeof(T) * (size_t)B * F;
+    int rc = stage_reserve(h, aos_slot, bytes);
+    if (rc) return rc;
+    dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+    transpose_kernel<T, false><<<grid, block, 0, h->stream>>>((const T*)h->stage[soa_slot], (T*)h->stage[aos_slot], B, F);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    MRF_CUDA(cudaMemcpyAsync(host, h->stage[aos_slot], bytes, cudaMemcpyDeviceToHost, h->stream));
+    return MRF_OK;
+}
+
+static int finish_timed(mrf_handle_t h) {
+    MRF_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    MRF_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    return MRF_OK;
+}
+
+// The host AoS order [B][R][F] is, per scenario, R records back to back: as a [B][R*F] matrix its transpose is
+// [R*F][B] = [r][f][b]; the kernels want [f][r][b].  The kernels' loader takes (f, r) -> row, so for the host
+// path the records are uploaded one robot at a time into the [f][r][b] layout.
+template <typename T>
+static int upload_records(mrf_handle_t h, const T* rec, long long B, int R, int slot_aos, int slot_tmp, int slot_soa) {
+    // upload whole AoS once, transpose to [R*F][B] (= [r][f][b]), then permute rows to [f][r][b] with 2-D copies
+    int rc = upload_soa<T>(h, rec, B, R * MRF_REC, slot_aos, slot_tmp);
+    if (rc) return rc;
+    if (R == 1) return MRF_OK; // [f][b] already
+    rc = stage_reserve(h, slot_soa, sizeof(T) * (size_t)B * R * MRF_REC);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r) // rows r*F+f  ->  rows f*R+r : strided 2-D copy per robot
+        MRF_CUDA(cudaMemcpy2DAsync((T*)h->stage[slot_soa] + (size_t)r * B, sizeof(T) * (size_t)R * B,
+                                   (const T*)h->stage[slot_tmp] + (size_t)r * MRF_REC * B, sizeof(T) * (size_t)B,
+                                   sizeof(T) * (size_t)B, MRF_REC, cudaMemcpyDeviceToDevice, h->stream));
+    return MRF_OK;
+}
+
+template <typename T>
+static int rollout_host(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B) {
+    if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout_host: null argument");
+    if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout_host: B and N must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = h->cfg.n_robots;
+    int rc = upload_records<T>(h, rec, B, R, 0, 1, 2);
+    if (rc) return rc;
+    const T* d_rec = (const T*)h->stage[R == 1 ? 1 : 2];
+    // outputs (SoA) packed in stage[3]: avg[R][B], x_ee[R][3][B], goal[3][B], then optional trajectories in stage[4]
+    const size_t n_small = (size_t)B * (R + 3 * R + 3);
+    rc = stage_reserve(h, 3, sizeof(T) * n_small);
+    if (rc) return rc;
+    T* d_avg = (T*)h->stage[3];
+    T* d_xee = d_avg + (size_t)R * B;
+    T* d_goal = d_xee + (size_t)3 * R * B;
+    T *d_q = nullptr, *d_qd = nullptr;
+    const size_t n_traj = (size_t)B * R * N * MRF_DOF;
+    if (qN || qdN) {
+        rc = stage_reserve(h, 4, sizeof(T) * n_traj * 2);
+        if (rc) return rc;
+        if (qN) d_q = (T*)h->stage[4];
+        if (qdN) d_qd = (T*)h->stage[4] + n_traj;
+    }
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = rollout_dev<T>(h, d_rec, N, d_avg, d_xee, d_goal, d_q, d_qd, B, h->stream);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    // SoA [R][B] -> AoS [B][R] etc.
+    if (avg_vel) { rc = download_aos<T>(h, avg_vel, B, R, 3, 5); if (rc) return rc; }
+    if (x_ee) {
+        // d_xee is [R*3][B]
+        const size_t bytes = sizeof(T) * (size_t)B * 3 * R;
+        rc = stage_reserve(h, 6, bytes);
+        if (rc) return rc;
+        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((3 * R + 31) / 32)), block(32, 8);
+        transpose_kernel<T, false><<<grid, block, 0, h->stream>>>(d_xee, (T*)h->stage[6], B, 3 * R);
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+        MRF_CUDA(cudaMemcpyAsync(x_ee, h->stage[6], bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (goal_est) {
+        const size_t bytes = sizeof(T) * (size_t)B * 3;
+        rc = stage_reserve(h, 7, bytes);
+        if (rc) return rc;
+        dim3 grid((unsigned)((B + 31) / 32), 1), block(32, 8);
+        transpose_kernel<T, false><<<grid, block, 0, h->stream>>>(d_goal, (T*)h->stage[7], B, 3);
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+        MRF_CUDA(cudaMemcpyAsync(goal_est, h->stage[7], bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (qN || qdN) {
+        // device [R][N][7][B] -> host [B][R][N][7]: one transpose of a [R*N*7][B] matrix
+        const int F = R * N * MRF_DOF;
+        rc = stage_reserve(h, 0, sizeof(T) * n_traj); // the AoS record staging is free again
+        if (rc) return rc;
+        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+        for (int which = 0; which < 2; ++which) {
+            T* hostp = which ? qdN : qN;
+            T* devp = which ? d_qd : d_q;
+            if (!hostp) continue;
+            transpose_kernel<T, false><<<grid, block, 0, h->stream>>>(devp, (T*)h->stage[0], B, F);
+            MRF_CUDA(cudaGetLastError());
+            h->launches += 1;
+            MRF_CUDA(cudaMemcpyAsync(hostp, h->stage[0], sizeof(T) * n_traj, cudaMemcpyDeviceToHost, h->stream));
+            MRF_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
+    return finish_timed(h);
+}
+
+template <typename T, bool CART>
+static int action_host(mrf_handle_t h, int robot_first, int n_rob, const T* rec, int S, const T* obst, int N, T* out,
+                       T* qN, T* qdN, int64_t B) {
+    if (!h || !rec || (S > 0 && !obst)) return fail(MRF_EINVAL, "mrf_action_host: null argument");
+    if (B <= 0 || S < 0 || n_rob < 1) return fail(MRF_EINVAL, "mrf_action_host: bad sizes");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = n_rob;
+    int rc = upload_records<T>(h, rec, B, R, 0, 1, 2);
+    if (rc) return rc;
+    const T* d_rec = (const T*)h->stage[R == 1 ? 1 : 2];
+    const T* d_obst = nullptr;
+    if (S > 0) {
+        // host [B][R][S][10] -> [R*S*10][B] = [r][o][c][b]; kernels want [o][c][r][b]
+        rc = upload_soa<T>(h, obst, B, R * S * MRF_OBST, 3, 4);
+        if (rc) return rc;
+        if (R == 1) {
+            d_obst = (const T*)h->stage[4];
+        } else {
+            rc = stage_reserve(h, 5, sizeof(T) * (size_t)B * R * S * MRF_OBST);
+            if (rc) return rc;
+            for (int r = 0; r < R; ++r)
+                MRF_CUDA(cudaMemcpy2DAsync((T*)h->stage[5] + (size_t)r * B, sizeof(T) * (size_t)R * B,
+                                           (const T*)h->stage[4] + (size_t)r * S * MRF_OBST * B, sizeof(T) * (size_t)B,
+                                           sizeof(T) * (size_t)B, (size_t)S * MRF_OBST, cudaMemcpyDeviceToDevice,
+                                           h->stream));
+            d_obst = (const T*)h->stage[5];
+        }
+    }
+    const int Fo = CART ? 1 : MRF_DOF * R;
+    rc = stage_reserve(h, 6, sizeof(T) * (size_t)B * Fo);
+    if (rc) return rc;
+    T *d_q = nullptr, *d_qd = nullptr;
+    const size_t n_traj = CART ? (size_t)B * N * MRF_DOF : 0;
+    if (CART && (qN || qdN)) {
+        rc = stage_reserve(h, 7, sizeof(T) * n_traj * 2);
+        if (rc) return rc;
+        if (qN) d_q = (T*)h->stage[7];
+        if (qdN) d_qd = (T*)h->stage[7] + n_traj;
+    }
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = action_dev<T, CART>(h, robot_first, n_rob, d_rec, S, d_obst, N, (T*)h->stage[6], d_q, d_qd, B, h->stream);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (CART) {
+        if (out) MRF_CUDA(cudaMemcpyAsync(out, h->stage[6], sizeof(T) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        const int F = N * MRF_DOF;
+        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((F + 31) / 32)), block(32, 8);
+        for (int which = 0; which < 2; ++which) {
+            T* hostp = which ? qdN : qN;
+            T* devp = which ? d_qd : d_q;
+            if (!hostp) continue;
+            rc = stage_reserve(h, 0, sizeof(T) * n_traj);
+            if (rc) return rc;
+            transpose_kernel<T, false><<<grid, block, 0, h->stream>>>(devp, (T*)h->stage[0], B, F);
+            MRF_CUDA(cudaGetLastError());
+            h->launches += 1;
+            MRF_CUDA(cudaMemcpyAsync(hostp, h->stage[0], sizeof(T) * n_traj, cudaMemcpyDeviceToHost, h->stream));
+            MRF_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    } else {
+        // device [7][R][B] -> host [B][R][7]: permute rows to [R][7][B] first
+        if (R == 1) {
+            rc = download_aos<T>(h, out, B, MRF_DOF, 6, 0);
+            if (rc) return rc;
+        } else {
+            rc = stage_reserve(h, 7, sizeof(T) * (size_t)B * Fo);
+            if (rc) return rc;
+            for (int r = 0; r < R; ++r)
+                MRF_CUDA(cudaMemcpy2DAsync((T*)h->stage[7] + (size_t)r * MRF_DOF * B, sizeof(T) * (size_t)B,
+                                           (const T*)h->stage[6] + (size_t)r * B, sizeof(T) * (size_t)R * B,
+                                           sizeof(T) * (size_t)B, MRF_DOF, cudaMemcpyDeviceToDevice, h->stream));
+            rc = download_aos<T>(h, out, B, MRF_DOF * R, 7, 0);
+            if (rc) return rc;
+        }
+    }
+    return finish_timed(h);
+}
+
+extern "C" int mrf_rollout_host_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee,
+                                    double* goal_est, double* qN, double* qdN, int64_t B) {
+    return rollout_host<double>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B);
+}
+extern "C" int mrf_rollout_host_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                                    float* qN, float* qdN, int64_t B) {
+    return rollout_host<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B);
+}
+extern "C" int mrf_action_host_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S,
+                                   const double* obst, double* action, int64_t B) {
+    return action_host<double, false>(h, robot_first, n_rob, rec, S, obst, 0, action, nullptr, nullptr, B);
+}
+extern "C" int mrf_action_host_f32(mrf_handle_t h, int robot_first, int n_rob, const float* rec, int S, const float* obst,
+                                   float* action, int64_t B) {
+    return action_host<float, false>(h, robot_first, n_rob, rec, S, obst, 0, action, nullptr, nullptr, B);
+}
+extern "C" int mrf_rollout_cart_host_f64(mrf_handle_t h, int robot, const double* rec, int S, const double* obst, int N,
+                                         double* avg_vel, double* qN, double* qdN, int64_t B) {
+    return action_host<double, true>(h, robot, 1, rec, S, obst, N, avg_vel, qN, qdN, B);
+}
+extern "C" int mrf_rollout_cart_host_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,
+                                         float* avg_vel, float* qN, float* qdN, int64_t B) {
+    return action_host<float, true>(h, robot, 1, rec, S, obst, N, avg_vel, qN, qdN, B);
+}
+
+extern "C" int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v,
+                                       double* a, int64_t B) {
+    if (!h || !q || !qdot) return fail(MRF_EINVAL, "mrf_kinematics_host: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_kinematics_host: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = h->cfg.n_robots;
+    // host [B][R][7] -> [R*7][B] = [r][i][b]; kernel wants [i][r][b]
+    const double* src[2] = {q, qdot};
+    for (int w = 0; w < 2; ++w) {
+        int rc = upload_soa<double>(h, src[w], B, R * MRF_DOF, 0, 1);
+        if (rc) return rc;
+        rc = stage_reserve(h, 2 + w, sizeof(double) * (size_t)B * R * MRF_DOF);
+        if (rc) return rc;
+        for (int r = 0; r < R; ++r)
+            MRF_CUDA(cudaMemcpy2DAsync((double*)h->stage[2 + w] + (size_t)r * B, sizeof(double) * (size_t)R * B,
+                                       (const double*)h->stage[1] + (size_t)r * MRF_DOF * B, sizeof(double) * (size_t)B,
+                                       sizeof(double) * (size_t)B, MRF_DOF, cudaMemcpyDeviceToDevice, h->stream));
+        MRF_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    const size_t n_out = (size_t)B * R * MRF_NLINKS * 3;
+    int rc = stage_reserve(h, 4, sizeof(double) * n_out * 3);
+    if (rc) return rc;
+    double* d_x = (double*)h->stage[4];
+    double* d_v = d_x + n_out;
+    double* d_a = d_v + n_out;
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = kinematics_dev<double>(h, (const double*)h->stage[2], (const double*)h->stage[3], d_x, d_v, d_a, B, h->stream);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    // device [l][c][r][b] -> host [b][r][l][c]
+    double* outs[3] = {x, v, a};
+    double* devs[3] = {d_x, d_v, d_a};
+    rc = stage_reserve(h, 5, sizeof(double) * n_out);
+    if (rc) return rc;
+    for (int w = 0; w < 3; ++w) {
+        if (!outs[w]) continue;
+        for (int r = 0; r < R; ++r) // rows (l*3+c)*R + r -> rows r*24 + (l*3+c)
+            MRF_CUDA(cudaMemcpy2DAsync((double*)h->stage[5] + (size_t)r * 24 * B, sizeof(double) * (size_t)B,
+                                       devs[w] + (size_t)r * B, sizeof(double) * (size_t)R * B, sizeof(double) * (size_t)B,
+                                       24, cudaMemcpyDeviceToDevice, h->stream));
+        rc = download_aos<double>(h, outs[w], B, R * 24, 5, 0);
+        if (rc) return rc;
+        MRF_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return finish_timed(h);
+}
+
+template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {
+    MRF_CUDA(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    MRF_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    int rc = stage_reserve(h, 0, sizeof(T) * (size_t)blocks * threads);
+    if (rc) return rc;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+        fma_peak_kernel<T><<<blocks, threads, 0, h->stream>>>((T*)h->stage[0], iters, T(0.999), T(1e-3));
+        MRF_CUDA(cudaGetLastError());
+        MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+        MRF_CUDA(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        MRF_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    return MRF_OK;
+}
+extern "C" int mrf_fma_peak(mrf_handle_t h, int is_f64, double* tflops) {
+    if (!h || !tflops) return fail(MRF_EINVAL, "mrf_fma_peak: null argument");
+    return is_f64 ? fma_peak<double>(h, tflops) : fma_peak<float>(h, tflops);
+}

@@ -1,0 +1,59 @@
+// mrf_devcfg.h -- host-side translation of the public MrfConfig into the kernels' DevCfg<T>.
+#pragma once
+#include <cstring>
+
+#include "../../include/mrf_b200.h"
+#include "mrf_device.cuh"
+
+namespace mrf {
+template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) {
+    memset(&d, 0, sizeof(d));
+    d.n_robots = c.n_robots;
+    d.mode = c.mode;
+    d.static_or_dyn = c.static_or_dyn;
+    d.has_coll = c.has_collision_links;
+    d.estimate_goal = c.estimate_goal;
+    d.estimate_robot = c.estimate_goal ? c.estimate_robot : -1;
+    d.est_h = (T)c.estimate_horizon;
+    d.dt = (T)c.dt;
+    d.eps = (T)c.eps;
+    d.sigma = (T)c.jdot_sign;
+    d.sref = (T)c.jdot_ref_sign;
+    d.s2 = (T)(2.0 * c.exec_scale);
+    for (int r = 0; r < MRF_MAX_ROBOTS; ++r) {
+        const double* M = c.mount[r];
+        const double R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+        for (int k = 0; k < 9; ++k) d.R0[r][k] = (T)R[k];
+        d.p0[r][0] = (T)M[3];
+        d.p0[r][1] = (T)M[7];
+        d.p0[r][2] = (T)M[11];
+        // panda_joint1 origin (0,0,0.333), panda_with_finger.urdf:99
+        d.link1[r][0] = (T)(M[3] + R[2] * 0.333);
+        d.link1[r][1] = (T)(M[7] + R[5] * 0.333);
+        d.link1[r][2] = (T)(M[11] + R[8] * 0.333);
+        // sphere table: links (1,2) -> point 5, 3 -> 0, 4 -> 1, (5,6) -> 2, 7 -> 3, 8 -> 4
+        const int src_of[8] = {5, 5, 0, 1, 2, 2, 3, 4};
+        int n = 0;
+        for (int l = 0; l < 8; ++l) {
+            bool merged = false;
+            if ((l == 1 || l == 5) && c.r_robots[r][l] == c.r_robots[r][l - 1]) {
+                d.ent_w[r][n - 1] = (T)2; // same point, same radius as the previous link: one entry, weight 2
+                merged = true;
+            }
+            if (!merged) {
+                d.ent_src[r][n] = src_of[l];
+                d.ent_rad[r][n] = (T)c.r_robots[r][l];
+                d.ent_w[r][n] = (T)1;
+                ++n;
+            }
+        }
+        d.ent_n[r] = n;
+    }
+    for (int i = 0; i < MRF_DOF; ++i) {
+        d.lim[i][0] = (T)c.limits[i][0];
+        d.lim[i][1] = (T)c.limits[i][1];
+    }
+}
+
+
+} // namespace mrf

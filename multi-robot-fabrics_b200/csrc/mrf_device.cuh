@@ -1,0 +1,590 @@
+// mrf_device.cuh -- per-thread device code of the multi-robot fabric hot path (sm_100a).
+//
+// One thread owns one (scenario, robot).  Its joint state, joint axes and the 7x7 metric stay in registers
+// for the whole horizon; its five distinct moving link points (x, v, Jdot*qdot) and its parameter block
+// live in shared memory, where the other robots of the same scenario (same lane, other warps of the CTA)
+// read them every rollout step.  No tensor cores: the work is tiny per-robot solves and scalar leaf algebra.
+//
+// What is computed (reference call sites; arithmetic restated from fabrics 0.9.5):
+//   chain_forward   fk / jac / jac_dot functions   multi_robot_fabrics/utils/utils.py:16-54
+//   fabric_action   planner._funs._function        examples/example_pandas_Jointspace.py:64-134,417-445
+//   (the rollout loop around them is in mrf_kernels.cu)
+//
+// The functions are MRF_HD so that tests/emul can run the same source on the host as a debugging aid;
+// the shipped library only ever calls them from __global__ kernels.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MRF_HD __host__ __device__ __forceinline__
+#else
+#define MRF_HD inline
+#include <cmath>
+#endif
+
+#include "../../include/mrf_b200.h"
+
+namespace mrf {
+
+template <int N> struct Int {
+    static constexpr int value = N;
+};
+
+constexpr int kDof = 7;
+constexpr int kEgo = 5;        // distinct moving link points: link3, link4, link5(==link6), link7, link8
+constexpr int kKin = kEgo * 9; // x, v, c per point
+constexpr int kMaxEnt = 8;     // obstacle entries per other robot
+// parameter block (per thread, shared memory)
+enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P_NH = 19, P_DN = 22, P_RB = 23, P_N = 29 };
+
+// ------------------------------------------------------------------------------------------------
+// math
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Mth;
+template <> struct Mth<float> {
+    static MRF_HD float sqrt(float x) { return ::sqrtf(x); }
+    static MRF_HD float rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+        return ::rsqrtf(x);
+#else
+        return 1.0f / ::sqrtf(x);
+#endif
+    }
+    static MRF_HD float rcp(float x) { return 1.0f / x; }
+    static MRF_HD float exp(float x) { return ::expf(x); }
+    static MRF_HD float tanh(float x) { return ::tanhf(x); }
+    static MRF_HD void sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+        ::sincosf(x, s, c);
+#else
+        *s = ::sinf(x);
+        *c = ::cosf(x);
+#endif
+    }
+    static MRF_HD float abs(float x) { return ::fabsf(x); }
+    static MRF_HD float max(float a, float b) { return ::fmaxf(a, b); }
+};
+template <> struct Mth<double> {
+    static MRF_HD double sqrt(double x) { return ::sqrt(x); }
+    static MRF_HD double rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+        return ::rsqrt(x);
+#else
+        return 1.0 / ::sqrt(x);
+#endif
+    }
+    static MRF_HD double rcp(double x) { return 1.0 / x; }
+    static MRF_HD double exp(double x) { return ::exp(x); }
+    static MRF_HD double tanh(double x) { return ::tanh(x); }
+    static MRF_HD void sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+        ::sincos(x, s, c);
+#else
+        *s = ::sin(x);
+        *c = ::cos(x);
+#endif
+    }
+    static MRF_HD double abs(double x) { return ::fabs(x); }
+    static MRF_HD double max(double a, double b) { return ::fmax(a, b); }
+};
+
+template <typename T> struct V3 {
+    T x, y, z;
+};
+template <typename T> MRF_HD V3<T> mk(T x, T y, T z) { return V3<T>{x, y, z}; }
+template <typename T> MRF_HD V3<T> operator+(V3<T> a, V3<T> b) { return V3<T>{a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> MRF_HD V3<T> operator-(V3<T> a, V3<T> b) { return V3<T>{a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> MRF_HD V3<T> operator*(V3<T> a, T s) { return V3<T>{a.x * s, a.y * s, a.z * s}; }
+template <typename T> MRF_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> MRF_HD V3<T> cross(V3<T> a, V3<T> b) {
+    return V3<T>{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration as the kernels see it (passed by value as a __grid_constant__ kernel parameter)
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct DevCfg {
+    int n_robots, mode, static_or_dyn, has_coll, estimate_goal, estimate_robot;
+    T est_h, dt, eps, sigma, sref, s2;
+    T R0[MRF_MAX_ROBOTS][9];   // mount rotation, row-major
+    T p0[MRF_MAX_ROBOTS][3];   // mount translation
+    T link1[MRF_MAX_ROBOTS][3]; // constant origin of panda_link1 == panda_link2
+    T lim[kDof][2];
+    // other-robot sphere table: distinct points with multiplicity (link1==link2, link5==link6 share a point;
+    // merged into one entry of weight 2 when their radii agree).  src 0..4 = moving point, 5 = link1.
+    int ent_n[MRF_MAX_ROBOTS];
+    int ent_src[MRF_MAX_ROBOTS][kMaxEnt];
+    T ent_rad[MRF_MAX_ROBOTS][kMaxEnt];
+    T ent_w[MRF_MAX_ROBOTS][kMaxEnt];
+};
+
+// per-thread state that persists over the horizon (registers)
+template <typename T> struct Chain {
+    V3<T> z[6]; // world axes of joints 1..6 (joint 7 moves no collision point)
+};
+
+// ------------------------------------------------------------------------------------------------
+// chain_forward: Panda FK with velocity / acceleration propagation (qdd = 0).
+// URDF constants: examples/simulation_environments/urdfs/panda_with_finger.urdf:98-106,150-158,201-209,
+// 253-261,326-334,378-386,451-465.  Writes x, v = J qdot, c = d(J qdot)/dq qdot of link3,4,5,7,8 to
+// kin[(e*9+comp)*NT + tid].
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Frame {
+    V3<T> a, b, n; // columns of the rotation
+    V3<T> p, w, al, v, ac;
+};
+
+template <typename T> MRF_HD void fr_advance(Frame<T>& f, V3<T> r) {
+    V3<T> t = cross(f.w, r);
+    f.ac = f.ac + cross(f.al, r) + cross(f.w, t);
+    f.v = f.v + t;
+    f.p = f.p + r;
+}
+// roll = +1: Rx(+pi/2), -1: Rx(-pi/2), 0: none; then Rz(q) with joint velocity qd.  Returns joint axis.
+template <typename T, int ROLL> MRF_HD V3<T> fr_joint(Frame<T>& f, T q, T qd) {
+    if (ROLL == 1) {
+        V3<T> t = f.b;
+        f.b = f.n;
+        f.n = t * T(-1);
+    } else if (ROLL == -1) {
+        V3<T> t = f.b;
+        f.b = f.n * T(-1);
+        f.n = t;
+    }
+    T s, c;
+    Mth<T>::sincos(q, &s, &c);
+    V3<T> a = f.a * c + f.b * s;
+    V3<T> b = f.b * c - f.a * s;
+    f.a = a;
+    f.b = b;
+    V3<T> zq = f.n * qd;
+    f.al = f.al + cross(f.w, zq);
+    f.w = f.w + zq;
+    return f.n;
+}
+template <typename T> MRF_HD void kin_store(T* kin, int NT, int tid, int e, const Frame<T>& f) {
+    T* k = kin + (e * 9) * NT + tid;
+    k[0 * NT] = f.p.x; k[1 * NT] = f.p.y; k[2 * NT] = f.p.z;
+    k[3 * NT] = f.v.x; k[4 * NT] = f.v.y; k[5 * NT] = f.v.z;
+    k[6 * NT] = f.ac.x; k[7 * NT] = f.ac.y; k[8 * NT] = f.ac.z;
+}
+template <typename T> MRF_HD V3<T> kin_load(const T* kin, int NT, int tid, int e, int c) {
+    const T* k = kin + (e * 9 + c) * NT + tid;
+    return V3<T>{k[0], k[NT], k[2 * NT]};
+}
+
+template <typename T>
+MRF_HD void chain_forward(const DevCfg<T>& cfg, int r, const T* q, const T* qd, Chain<T>& ch, T* kin, int NT, int tid) {
+    Frame<T> f;
+    const T* R = cfg.R0[r];
+    f.a = mk(R[0], R[3], R[6]);
+    f.b = mk(R[1], R[4], R[7]);
+    f.n = mk(R[2], R[5], R[8]);
+    f.p = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]); // p0 + R0 (0,0,0.333): base is fixed
+    f.w = mk(T(0), T(0), T(0));
+    f.al = f.w; f.v = f.w; f.ac = f.w;
+    ch.z[0] = fr_joint<T, 0>(f, q[0], qd[0]);                       // joint1
+    ch.z[1] = fr_joint<T, -1>(f, q[1], qd[1]);                      // joint2 (zero offset)
+    fr_advance(f, f.b * T(-0.316));                                  // joint3 origin (0,-0.316,0)
+    kin_store(kin, NT, tid, 0, f);                                   // link3
+    ch.z[2] = fr_joint<T, 1>(f, q[2], qd[2]);
+    fr_advance(f, f.a * T(0.0825));                                  // joint4 origin (0.0825,0,0)
+    kin_store(kin, NT, tid, 1, f);                                   // link4
+    ch.z[3] = fr_joint<T, 1>(f, q[3], qd[3]);
+    fr_advance(f, f.a * T(-0.0825) + f.b * T(0.384));                // joint5 origin (-0.0825,0.384,0)
+    kin_store(kin, NT, tid, 2, f);                                   // link5 == link6
+    ch.z[4] = fr_joint<T, -1>(f, q[4], qd[4]);
+    ch.z[5] = fr_joint<T, 1>(f, q[5], qd[5]);                        // joint6 (zero offset)
+    fr_advance(f, f.a * T(0.088));                                   // joint7 origin (0.088,0,0)
+    kin_store(kin, NT, tid, 3, f);                                   // link7
+    (void)fr_joint<T, 1>(f, q[6], qd[6]);
+    fr_advance(f, f.n * T(0.107));                                   // fixed joint8 (0,0,0.107); hand == link8
+    kin_store(kin, NT, tid, 4, f);                                   // link8
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulators
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Sym3 {
+    T xx, xy, xz, yy, yz, zz;
+};
+template <typename T> struct PointAcc {
+    Sym3<T> A;   // sum M_l g g^T
+    V3<T> b;     // sum g (f_l + M_l (sigma curv - g.a_o))
+};
+template <typename T> MRF_HD V3<T> symmul(const Sym3<T>& A, V3<T> u) {
+    return V3<T>{A.xx * u.x + A.xy * u.y + A.xz * u.z, A.xy * u.x + A.yy * u.y + A.yz * u.z,
+                 A.xz * u.x + A.yz * u.y + A.zz * u.z};
+}
+
+// Spec in joint space: 6x6 upper triangle + decoupled joint 7 (no collision point or task map moves with q7)
+template <typename T> struct Spec {
+    T M[6][6];
+    T m7;
+    T f[kDof];
+};
+
+// One sphere leaf (collision_geometry "-0.5/x^4 xdot^2", collision_finsler "0.01/x^4 xdot^2",
+// examples/example_pandas_Jointspace.py:88-89) of ego point (p, v, c) against sphere (xo, vo, ao), in the
+// point's task space.  wt = multiplicity of identical leaves.
+template <typename T>
+MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> ao, T rho, T wt, T sigma,
+                        PointAcc<T>& acc, T& num) {
+    V3<T> d = p - xo, w = v - vo;
+    T n2 = dot(d, d);
+    T inv_n = Mth<T>::rsqrt(n2);
+    T n = n2 * inv_n;
+    T inv_rho = Mth<T>::rcp(rho);
+    T x = n * inv_rho - T(1);
+    T gs = inv_n * inv_rho;              // g = d * gs  (gradient of x w.r.t. the point)
+    T dw = dot(d, w);
+    T xd = dw * gs;
+    T kappa = (dot(w, w) - dw * dw * inv_n * inv_n) * gs;
+    T ix = Mth<T>::rcp(x);
+    T ix2 = ix * ix, ix4 = ix2 * ix2;
+    T xd2 = xd * xd;
+    T Ml = T(0.02) * ix4 * wt;           // d2L/dxdot2
+    T fl = Ml * (T(-0.5) * xd2 * ix4);   // M h
+    T fel = T(-0.04) * xd2 * ix4 * ix * wt;
+    T curv = kappa + dot(d, cc) * gs;
+    T ga = dot(d, ao) * gs;
+    T gv = dot(d, v) * gs;
+    T fq = fl + Ml * (sigma * curv - ga);
+    num += gv * ((fl - fel) + Ml * (sigma - T(1)) * curv);
+    V3<T> g = d * gs;
+    V3<T> Mg = g * Ml;
+    acc.A.xx += Mg.x * g.x; acc.A.xy += Mg.x * g.y; acc.A.xz += Mg.x * g.z;
+    acc.A.yy += Mg.y * g.y; acc.A.yz += Mg.y * g.z; acc.A.zz += Mg.z * g.z;
+    acc.b = acc.b + g * fq;
+}
+
+// Plane leaf (geometry_plane_constraint "10*(1/(1+exp(-10x))-1) xdot^2", example_pandas_Jointspace.py:87;
+// finsler "0.1/x^2 s xdot^2", fabrics default)
+template <typename T>
+MRF_HD void plane_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> nh, T dn, T rb, T wt, T sigma, PointAcc<T>& acc, T& num) {
+    T x = dot(nh, p) + dn - rb;
+    T xd = dot(nh, v);
+    T s = xd > T(0) ? T(0) : (xd < T(0) ? T(1) : T(0.5)); // -0.5 (sign(xdot) - 1)
+    T ix = Mth<T>::rcp(x);
+    T xd2 = xd * xd;
+    T Ml = T(0.2) * s * ix * ix * wt;
+    T fel = T(-0.2) * s * xd2 * ix * ix * ix * wt;
+    T h = T(-10) * xd2 * Mth<T>::rcp(T(1) + Mth<T>::exp(T(10) * x));
+    T fl = Ml * h;
+    T curv = dot(nh, cc);
+    T fq = fl + Ml * sigma * curv;
+    num += xd * ((fl - fel) + Ml * (sigma - T(1)) * curv);
+    V3<T> Mg = nh * Ml;
+    acc.A.xx += Mg.x * nh.x; acc.A.xy += Mg.x * nh.y; acc.A.xz += Mg.x * nh.z;
+    acc.A.yy += Mg.y * nh.y; acc.A.yz += Mg.y * nh.z; acc.A.zz += Mg.z * nh.z;
+    acc.b = acc.b + nh * fq;
+}
+
+// Jacobian columns of a point p that rides on joints 1..K: z_j x (p - o_j).  Joint origins: o_1 = o_2 = link1,
+// o_3 = link3, o_4 = link4, o_5 = o_6 = link5.
+template <typename T, int K> MRF_HD void jac_cols(const Chain<T>& ch, V3<T> p, const V3<T>* org, V3<T>* Jc) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) Jc[j] = cross(ch.z[j], p - org[j]);
+}
+
+template <typename T, int K> MRF_HD void pullback(const V3<T>* Jc, const PointAcc<T>& acc, Spec<T>& S) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        V3<T> AJ = symmul(acc.A, Jc[j]);
+        S.f[j] += dot(Jc[j], acc.b);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) S.M[i][j] += dot(Jc[i], AJ);
+    }
+}
+
+// In-place Cholesky of the 6x6 upper triangle (M + eps I) and solve; returns x = (M + eps I)^-1 b.
+template <typename T> MRF_HD void chol_solve6(T (&M)[6][6], T eps, const T* b, T* x) {
+    T inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        T s = M[j][j] + eps;
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= M[k][j] * M[k][j];
+        T r = Mth<T>::rsqrt(s);
+        inv[j] = r;
+        M[j][j] = s * r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            T t = M[j][i];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t -= M[k][j] * M[k][i];
+            M[j][i] = t * r; // U[j][i], M = U^T U
+        }
+    }
+    T y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { // U^T y = b
+        T s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= M[k][i] * y[k];
+        y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) { // U x = y
+        T s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s -= M[i][k] * x[k];
+        x[i] = s * inv[i];
+    }
+}
+
+template <typename T> MRF_HD void attractor_scalars(T n, T w, T& dpsi, T& m2) {
+    // attractor_potential 5(|x| + 0.1 log(1 + exp(-20|x|))): d/d|x| = 5 tanh(10|x|);
+    // attractor_metric (1.7 exp(-(0.75|x|)^2) + 0.3) I, L = xdot^T m xdot -> M = 2 m I
+    dpsi = T(5) * w * Mth<T>::tanh(T(10) * n);
+    m2 = T(2) * (T(1.7) * Mth<T>::exp(T(-0.5625) * n * n) + T(0.3));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fabric_action: energised geometry + forcing + damper for one robot.  `src.each(f)` enumerates the obstacle
+// spheres: f(xo, vo, ao, radius, weight).  q, qd in registers; own kinematics in kin[..tid]; parameters in
+// prm[k*NT + tid].  Writes act[7] (velocity in 'vel' mode, acceleration in 'acc' mode).
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename Src>
+MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, const Chain<T>& ch, const T* kin,
+                          const T* prm, int NT, int tid, const Src& src, T* act) {
+    const T sigma = cfg.sigma;
+    Spec<T> G;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) G.M[i][j] = T(0);
+        G.M[i][i] = T(0.2); // base_energy 0.5*0.2*qd.qd
+        G.f[i] = T(0);
+    }
+    G.m7 = T(0.2);
+    G.f[6] = T(0);
+    T num = T(0); // qdot . (f_g - f_e,g)
+
+    // ---- joint-limit leaves (limit_geometry "-0.1/x xdot^2", limit_finsler "0.1/x s xdot^2") ----
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+#pragma unroll
+        for (int up = 0; up < 2; ++up) {
+            T x = up ? cfg.lim[i][1] - q[i] : q[i] - cfg.lim[i][0];
+            T xd = up ? -qd[i] : qd[i];
+            T s = xd > T(0) ? T(0) : (xd < T(0) ? T(1) : T(0.5));
+            T ix = Mth<T>::rcp(x);
+            T xd2 = xd * xd;
+            T Ml = T(0.2) * s * ix;
+            T fl = Ml * (T(-0.1) * xd2 * ix);
+            T fel = T(-0.1) * s * xd2 * ix * ix;
+            if (i < 6) G.M[i][i] += Ml; else G.m7 += Ml;
+            G.f[i] += up ? -fl : fl;
+            num += xd * (fl - fel);
+        }
+    }
+
+    V3<T> org[6];
+    org[0] = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
+    org[1] = org[0];
+    org[2] = kin_load(kin, NT, tid, 0, 0);
+    org[3] = kin_load(kin, NT, tid, 1, 0);
+    org[4] = kin_load(kin, NT, tid, 2, 0);
+    org[5] = org[4];
+
+    // ---- collision leaves per distinct ego point ----
+    if (cfg.has_coll) {
+        const V3<T> nh = mk(prm[(P_NH + 0) * NT + tid], prm[(P_NH + 1) * NT + tid], prm[(P_NH + 2) * NT + tid]);
+        const T dn = prm[P_DN * NT + tid];
+        auto point = [&](auto kc, int e, int rb_first, int n_links) {
+            constexpr int K = decltype(kc)::value;
+            V3<T> p = kin_load(kin, NT, tid, e, 0), v = kin_load(kin, NT, tid, e, 3), cc = kin_load(kin, NT, tid, e, 6);
+            PointAcc<T> acc;
+            acc.A = Sym3<T>{T(0), T(0), T(0), T(0), T(0), T(0)};
+            acc.b = mk(T(0), T(0), T(0));
+            T rb = prm[(P_RB + rb_first) * NT + tid];
+            T we = T(1);
+            int passes = 1;
+            if (n_links == 2) { // link5 and link6 share the point; identical leaves if their radii agree
+                T rb2 = prm[(P_RB + rb_first + 1) * NT + tid];
+                if (rb2 == rb) we = T(2); else passes = 2;
+            }
+            for (int pass = 0; pass < passes; ++pass) {
+                if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
+                src.each([&](V3<T> xo, V3<T> vo, V3<T> ao, T ro, T wo) {
+                    sphere_leaf(p, v, cc, xo, vo, ao, ro + rb, we * wo, sigma, acc, num);
+                });
+                plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
+            }
+            V3<T> Jc[K];
+            jac_cols<T, K>(ch, p, org, Jc);
+            pullback<T, K>(Jc, acc, G);
+        };
+        point(Int<2>{}, 0, 0, 1); // link3
+        point(Int<3>{}, 1, 1, 1); // link4
+        point(Int<4>{}, 2, 2, 2); // link5 + link6
+        point(Int<6>{}, 3, 4, 1); // link7
+        point(Int<6>{}, 4, 5, 1); // link8
+    }
+
+    // ---- q^T M_g q ----
+    T qMq = G.m7 * qd[6] * qd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        qMq += G.M[i][i] * qd[i] * qd[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) qMq += T(2) * G.M[i][j] * qd[i] * qd[j];
+    }
+    const T e = cfg.eps;
+    const T a_geom = -num * Mth<T>::rcp(e + qMq);
+
+    // ---- forced spec = geometry + attractors (goal struct example_pandas_Jointspace.py:25-62) ----
+    Spec<T> F = G;
+    T xpsi;
+    {
+        V3<T> p8 = kin_load(kin, NT, tid, 4, 0), c8 = kin_load(kin, NT, tid, 4, 6);
+        V3<T> p7 = kin_load(kin, NT, tid, 3, 0), c7 = kin_load(kin, NT, tid, 3, 6);
+        // sub-goal 0: world -> panda_hand
+        V3<T> x0 = p8 - mk(prm[(P_G0 + 0) * NT + tid], prm[(P_G0 + 1) * NT + tid], prm[(P_G0 + 2) * NT + tid]);
+        T n0 = Mth<T>::sqrt(dot(x0, x0));
+        xpsi = n0;
+        T dpsi0, m0;
+        attractor_scalars(n0, prm[P_W0 * NT + tid], dpsi0, m0);
+        V3<T> t0 = (x0 * (dpsi0 * Mth<T>::rcp(n0)) + c8 * sigma) * m0;
+        // sub-goal 1: angle_goal_1 (hand - link7) - x_goal_1
+        T Rg[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rg[k] = prm[(P_ANG + k) * NT + tid];
+        auto rot = [&](V3<T> u) {
+            return V3<T>{Rg[0] * u.x + Rg[1] * u.y + Rg[2] * u.z, Rg[3] * u.x + Rg[4] * u.y + Rg[5] * u.z,
+                         Rg[6] * u.x + Rg[7] * u.y + Rg[8] * u.z};
+        };
+        V3<T> d87 = p8 - p7;
+        V3<T> x1 = rot(d87) - mk(prm[(P_G1 + 0) * NT + tid], prm[(P_G1 + 1) * NT + tid], prm[(P_G1 + 2) * NT + tid]);
+        T n1 = Mth<T>::sqrt(dot(x1, x1));
+        T dpsi1, m1;
+        attractor_scalars(n1, prm[P_W1 * NT + tid], dpsi1, m1);
+        V3<T> t1 = (x1 * (dpsi1 * Mth<T>::rcp(n1)) + rot(c8 - c7) * sigma) * m1;
+        V3<T> J8[6], Jr[6];
+        jac_cols<T, 6>(ch, p8, org, J8);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Jr[j] = rot(cross(ch.z[j], d87));
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            F.f[j] += dot(J8[j], t0) + dot(Jr[j], t1);
+#pragma unroll
+            for (int i = 0; i <= j; ++i) F.M[i][j] += m0 * dot(J8[i], J8[j]) + m1 * dot(Jr[i], Jr[j]);
+        }
+        // sub-goal 2: joint 7 -> x_goal_2
+        T x2 = q[6] - prm[P_G2 * NT + tid];
+        T dpsi2, m2;
+        attractor_scalars(Mth<T>::abs(x2), prm[P_W2 * NT + tid], dpsi2, m2);
+        F.f[6] += m2 * dpsi2 * (x2 > T(0) ? T(1) : (x2 < T(0) ? T(-1) : T(0)));
+        F.m7 += m2;
+    }
+
+    // ---- solves and speed-control damper ----
+    T hg[kDof], hf[kDof];
+    chol_solve6(G.M, e, G.f, hg);
+    hg[6] = G.f[6] * Mth<T>::rcp(G.m7 + e);
+    chol_solve6(F.M, e, F.f, hf);
+    hf[6] = F.f[6] * Mth<T>::rcp(F.m7 + e);
+    T qq = T(0), qhg = T(0), qhf = T(0);
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        qq += qd[i] * qd[i];
+        qhg += qd[i] * hg[i];
+        qhf += qd[i] * hf[i];
+    }
+    const T iden = Mth<T>::rcp(e + cfg.s2 * qq);
+    const T a_ex0 = -cfg.s2 * qhg * iden, a_exf = -cfg.s2 * qhf * iden;
+    const T eta = T(0.5) * (Mth<T>::tanh(T(-0.45) * qq - T(0.5)) + T(1)); // damper_eta
+    const T a_ex = eta * a_ex0 + (T(1) - eta) * a_exf;
+    const T beta = T(0.5) * (Mth<T>::tanh(T(-0.5) * (xpsi - T(0.02))) + T(1)) * T(6.5) + T(0.01) +
+                   Mth<T>::max(T(0), a_geom - a_ex); // damper_beta
+    const T damp = a_ex + beta;
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        T qdd = -hf[i] - damp * qd[i];
+        act[i] = cfg.mode == 1 ? qd[i] + cfg.dt * qdd : qdd;
+    }
+}
+
+constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane each)
+
+// ------------------------------------------------------------------------------------------------
+// obstacle sources for fabric_action
+// ------------------------------------------------------------------------------------------------
+// other robots of the same scenario, read from the CTA's shared kinematics table
+template <typename T> struct SmemSrc {
+    const DevCfg<T>& cfg;
+    const T* kin;
+    int NT, lane, r;
+    T vref, aref;
+    template <typename F> MRF_HD void each(F f) const {
+        for (int j = 0; j < cfg.n_robots; ++j) {
+            if (j == r) continue;
+            const int ot = j * kTile + lane;
+            const int ne = cfg.ent_n[j];
+            for (int k = 0; k < ne; ++k) {
+                const int s = cfg.ent_src[j][k];
+                V3<T> xo, vo, ao;
+                if (s < kEgo) {
+                    xo = kin_load(kin, NT, ot, s, 0);
+                    vo = kin_load(kin, NT, ot, s, 3) * vref;
+                    ao = kin_load(kin, NT, ot, s, 6) * aref;
+                } else {
+                    xo = mk(cfg.link1[j][0], cfg.link1[j][1], cfg.link1[j][2]);
+                    vo = mk(T(0), T(0), T(0));
+                    ao = vo;
+                }
+                f(xo, vo, ao, cfg.ent_rad[j][k], cfg.ent_w[j][k]);
+            }
+        }
+    }
+};
+
+// caller-supplied spheres in global memory, SoA [S][MRF_OBST][stride]; tk > 0 extrapolates x + tk * xdot
+template <typename T, bool CART> struct GlobalSrc {
+    const T* obst;
+    long long stride, off;
+    int S;
+    T tk;
+    template <typename F> MRF_HD void each(F f) const {
+        for (int o = 0; o < S; ++o) {
+            const T* b = obst + (long long)o * MRF_OBST * stride + off;
+            V3<T> xo = mk(b[0], b[stride], b[2 * stride]);
+            V3<T> vo = mk(b[3 * stride], b[4 * stride], b[5 * stride]);
+            V3<T> ao;
+            if (CART) {
+                xo = xo + vo * tk;
+                ao = mk(T(0), T(0), T(0));
+            } else {
+                ao = mk(b[6 * stride], b[7 * stride], b[8 * stride]);
+            }
+            f(xo, vo, ao, b[9 * stride], T(1));
+        }
+    }
+};
+
+// load the parameter block of one record into shared memory
+template <typename T, typename L> MRF_HD void load_params(L ld, T* prm, int NT, int tid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) prm[(P_G0 + k) * NT + tid] = ld(MRF_G0 + k);
+    prm[P_W0 * NT + tid] = ld(MRF_W0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) prm[(P_G1 + k) * NT + tid] = ld(MRF_G1 + k);
+    prm[P_W1 * NT + tid] = ld(MRF_W1);
+    prm[P_G2 * NT + tid] = ld(MRF_G2);
+    prm[P_W2 * NT + tid] = ld(MRF_W2);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) prm[(P_ANG + k) * NT + tid] = ld(MRF_ANG + k);
+    T c0 = ld(MRF_CON), c1 = ld(MRF_CON + 1), c2 = ld(MRF_CON + 2), c3 = ld(MRF_CON + 3);
+    T inv = Mth<T>::rsqrt(c0 * c0 + c1 * c1 + c2 * c2);
+    prm[(P_NH + 0) * NT + tid] = c0 * inv;
+    prm[(P_NH + 1) * NT + tid] = c1 * inv;
+    prm[(P_NH + 2) * NT + tid] = c2 * inv;
+    prm[P_DN * NT + tid] = c3 * inv;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) prm[(P_RB + k) * NT + tid] = ld(MRF_RB + k);
+}
+
+
+} // namespace mrf

@@ -1,0 +1,51 @@
+"""Shared helpers for the test-suite (oracle-side input preparation)."""
+import numpy as np
+
+from oracle import o2
+
+
+def oracle_rollout(rec, R, N, estimate_goal=0, static_or_dyn=1):
+    """Oracle O2 coupled rollout incl. the RF-CV goal estimate; returns qN, qdN, avg, xee, goal_est, ok-mask."""
+    ocfg = o2.default_config(R, static_or_dyn=static_or_dyn)
+    rec_o = np.array(rec, dtype=np.float64, copy=True)
+    B = rec_o.shape[0]
+    goal = rec_o[:, 1, o2.G0:o2.G0 + 3].copy() if R > 1 else np.zeros((B, 3))
+    if estimate_goal:
+        for b in range(B):
+            x, v = o2.endeffector(ocfg, 1, rec_o[b, 1, 0:7], rec_o[b, 1, 7:14], use_jqd=(estimate_goal == 2))
+            goal[b] = x + 0.2 * v
+        rec_o[:, 1, o2.G0:o2.G0 + 3] = goal
+    lib = o2.lib()
+    qN, qdN = np.zeros((B, R, N, 7)), np.zeros((B, R, N, 7))
+    avg, xee = np.zeros((B, R)), np.zeros((B, R, 3))
+    import ctypes as C
+    lib.mrfo_rollout_jointspace_batch(C.byref(ocfg), o2._p(np.ascontiguousarray(rec_o)), B, N, o2._p(qN), o2._p(qdN),
+                                      o2._p(avg), o2._p(xee), 0)
+    mx = np.abs(qdN).max(axis=(1, 2, 3))
+    ok = np.isfinite(mx) & (mx < 10.0)   # drop numerically stiff near-contact scenarios (see scenarios.py)
+    return qN, qdN, avg, xee, goal, ok
+
+
+def random_obstacles(rng, B, n_rob, S):
+    """Spheres placed away from the arms' workspace shell so the leaves stay well conditioned."""
+    obst = np.zeros((B, n_rob, S, 10))
+    obst[..., 0:3] = rng.uniform([-0.6, -1.2, 0.9], [1.6, 1.2, 2.0], size=(B, n_rob, S, 3))
+    obst[..., 3:6] = rng.uniform(-0.3, 0.3, size=(B, n_rob, S, 3))
+    obst[..., 6:9] = rng.uniform(-0.5, 0.5, size=(B, n_rob, S, 3))
+    obst[..., 9] = 0.08
+    return obst
+
+
+def oracle_actions(rec, obst, robot_first=0, **cfgkw):
+    """rec (B,n_rob,44), obst (B,n_rob,S,10) -> actions (B,n_rob,7) from oracle O2 (NaN rows where it fails)."""
+    B, n_rob = rec.shape[:2]
+    ocfg = o2.default_config(max(2, robot_first + n_rob), **cfgkw)
+    out = np.full((B, n_rob, 7), np.nan)
+    for b in range(B):
+        for r in range(n_rob):
+            o = obst[b, r]
+            try:
+                out[b, r] = o2.action(ocfg, robot_first + r, rec[b, r], o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+            except FloatingPointError:
+                pass
+    return out

@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA kernels, called through the C-ABI, against oracle O2 on the same seeded inputs.
+
+Tolerances (north_star): FP64 within 1e-9 relative on actions / trajectories; FP32 within the tolerance stated in
+each test; deadlock flags identical.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import multi_robot_fabrics_b200 as m
+from multi_robot_fabrics_b200.api import Fabrics, to_soa
+from oracle import o2
+
+from helpers import oracle_actions, oracle_rollout, random_obstacles
+
+F64_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def fabs(built):
+    d = {}
+    yield d
+    for f in d.values():
+        f.close()
+
+
+def get_fab(fabs, R, **kw):
+    key = (R, tuple(sorted(kw.items())))
+    if key not in fabs:
+        fabs[key] = Fabrics(R, device=0, **kw)
+    return fabs[key]
+
+
+@pytest.mark.parametrize("R,N,B,est", [(2, 20, 70, 0), (2, 20, 33, 1), (3, 50, 96, 1), (3, 20, 1, 0), (3, 50, 40, 2)])
+def test_rollout_f64_matches_oracle(fabs, R, N, B, est):
+    rec = m.scenarios.generate(B, R, seed=100 + R + N)
+    fab = get_fab(fabs, R, estimate_goal=est)
+    out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N, estimate_goal=est)
+    assert ok.sum() >= max(1, int(0.9 * B))
+    scale = np.abs(qdN[ok]).max()
+    assert np.abs(out["qdN"] - qdN)[ok].max() / scale < F64_RTOL
+    assert np.abs(out["qN"] - qN)[ok].max() < F64_RTOL * np.abs(qN[ok]).max()
+    assert np.abs(out["avg_vel"] - avg)[ok].max() < F64_RTOL * np.abs(avg[ok]).max()
+    assert np.abs(out["x_ee"] - xee).max() < 1e-12
+    assert np.abs(out["goal_est"] - goal).max() < 1e-12
+
+
+@pytest.mark.parametrize("R,N", [(2, 20), (3, 50)])
+def test_rollout_f32_within_tolerance(fabs, R, N):
+    """FP32 path: |qdot - oracle| <= 2e-3 rad/s and |q - oracle| <= 2e-4 rad over the horizon, avg_vel <= 1e-3."""
+    B = 256
+    rec = m.scenarios.generate(B, R, seed=7)
+    fab = get_fab(fabs, R)
+    out = fab.rollout_host(rec, N, dtype="f32", trajectories=True)
+    qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N)
+    assert np.abs(out["qdN"] - qdN)[ok].max() < 2e-3
+    assert np.abs(out["qN"] - qN)[ok].max() < 2e-4
+    assert np.abs(out["avg_vel"] - avg)[ok].max() < 1e-3
+    assert np.abs(out["x_ee"] - xee).max() < 1e-5
+
+
+def test_rollout_static_fabrics(fabs):
+    """STATIC_OR_DYN_FABRICS = 0 zeroes the other robots' v and a (forward_planner_Jointspace.py:215-217)."""
+    R, N, B = 2, 10, 32
+    rec = m.scenarios.generate(B, R, seed=3)
+    fab = get_fab(fabs, R, static_or_dyn=0)
+    out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N, static_or_dyn=0)
+    assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
+
+
+@pytest.mark.parametrize("n_rob,S", [(2, 32), (1, 0), (3, 64), (2, 5)])
+def test_action_matches_oracle(fabs, n_rob, S):
+    """Executed action (compute_action without the small-action clamp), S dynamic obstacle spheres."""
+    B = 50
+    rng = np.random.default_rng(S + n_rob)
+    R = max(2, n_rob)
+    rec = m.scenarios.generate(B, R, seed=11, weight_goal_1=20.0)[:, :n_rob]
+    obst = random_obstacles(rng, B, n_rob, S)
+    fab = get_fab(fabs, R)
+    act = fab.action_host(rec, obst if S else None, robot_first=0, dtype="f64")
+    ref = oracle_actions(rec, obst)
+    ok = np.isfinite(ref).all(axis=(1, 2))
+    assert ok.sum() > 0.9 * B
+    assert np.abs(act - ref)[ok].max() / np.abs(ref[ok]).max() < F64_RTOL
+    act32 = fab.action_host(rec, obst if S else None, robot_first=0, dtype="f32")
+    assert np.abs(act32 - ref)[ok].max() < 2e-3
+
+
+def test_action_acc_mode_and_grasp_planner(fabs):
+    """mode 'acc' returns qdd; has_collision_links=0 is the grasp planner (example_pandas_Jointspace.py:160-166)."""
+    B = 20
+    rng = np.random.default_rng(5)
+    rec = m.scenarios.generate(B, 2, seed=12)
+    obst = random_obstacles(rng, B, 2, 4)
+    for kw in (dict(mode=0), dict(has_collision_links=0)):
+        fab = get_fab(fabs, 2, **kw)
+        act = fab.action_host(rec, obst, dtype="f64")
+        ref = oracle_actions(rec, obst, **kw)
+        assert np.abs(act - ref).max() / np.abs(ref).max() < F64_RTOL
+
+
+def test_cartesian_rollout_matches_oracle(fabs):
+    B, N, S = 24, 20, 16
+    rng = np.random.default_rng(9)
+    rec = m.scenarios.generate(B, 2, seed=13, weight_goal_1=20.0)
+    obst = random_obstacles(rng, B, 1, S)[:, 0]
+    fab = get_fab(fabs, 2)
+    ocfg = o2.default_config(2)
+    for robot in (0, 1):
+        avg, qN, qdN = fab.rollout_cart_host(robot, rec[:, robot], obst, N, dtype="f64")
+        for b in range(B):
+            rq, rqd, ravg = o2.rollout_cartesian(ocfg, robot, rec[b, robot], obst[b, :, 0:3], obst[b, :, 3:6],
+                                                 obst[b, :, 9], N)
+            if not np.isfinite(rqd).all() or np.abs(rqd).max() > 10:
+                continue
+            assert np.abs(qdN[b] - rqd).max() / np.abs(rqd).max() < F64_RTOL
+            assert np.abs(qN[b] - rq).max() < 1e-9 * np.abs(rq).max()
+            assert abs(avg[b] - ravg) < 1e-9 * abs(ravg)
+
+
+def test_kinematics_matches_oracle(fabs):
+    R, B = 3, 17
+    rec = m.scenarios.generate(B, R, seed=14)
+    fab = get_fab(fabs, R)
+    x, v, a = fab.kinematics_host(rec[..., 0:7], rec[..., 7:14])
+    ocfg = o2.default_config(R)
+    for b in range(B):
+        for r in range(R):
+            xx, vv, cc, _ = o2.kinematics(ocfg, r, rec[b, r, 0:7], rec[b, r, 7:14])
+            assert np.abs(x[b, r] - xx).max() < 1e-12
+            assert np.abs(v[b, r] - vv).max() < 1e-12
+            assert np.abs(a[b, r] + cc).max() < 1e-11   # a = -(d(J qd)/dq) qd, utils.py:28
+
+
+def test_device_api_equals_host_api(fabs):
+    """SoA device-pointer entry (torch tensors) gives the host entry's bits; shard concatenation is bitwise."""
+    import torch
+    R, N, B = 3, 20, 100
+    rec = m.scenarios.generate(B, R, seed=15)
+    fab = get_fab(fabs, R)
+    host = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    for dt, key in ((torch.float64, "f64"), (torch.float32, "f32")):
+        d_rec = torch.from_numpy(to_soa(rec)).to("cuda:0", dtype=dt)
+        qdN = torch.empty((R, N, 7, B), dtype=dt, device="cuda:0")
+        xee = torch.empty((R, 3, B), dtype=dt, device="cuda:0")
+        avg = fab.rollout_dev(d_rec, N, x_ee=xee, qdN=qdN)
+        torch.cuda.synchronize()
+        if key == "f64":
+            assert np.array_equal(avg.cpu().numpy().T, host["avg_vel"])
+            assert np.array_equal(qdN.permute(3, 0, 1, 2).cpu().numpy(), host["qdN"])
+        # two shards == one batch, bitwise (the multi-GPU sharding property)
+        h = B // 2
+        a0 = fab.rollout_dev(d_rec[:, :, :h].contiguous(), N)
+        a1 = fab.rollout_dev(d_rec[:, :, h:].contiguous(), N)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([a0, a1], dim=1), avg)
+
+
+def test_full_size_batch_properties(fabs):
+    """BASELINE config C5 shape (65536 x 3 Pandas x H50) in FP32: size-independent properties --
+    batch-permutation equivariance and agreement of a strided sample with the oracle."""
+    import torch
+    R, N, B = 3, 50, 65536
+    base = m.scenarios.generate(4096, R, seed=16)
+    rec = np.tile(base, (B // 4096, 1, 1))
+    fab = get_fab(fabs, R)
+    d_rec = torch.from_numpy(to_soa(rec)).to("cuda:0", dtype=torch.float32)
+    avg = fab.rollout_dev(d_rec, N)
+    perm = torch.randperm(B, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(0))
+    avg_p = fab.rollout_dev(d_rec[:, :, perm].contiguous(), N)
+    torch.cuda.synchronize()
+    assert torch.equal(avg[:, perm], avg_p)                       # a scenario never reads another scenario
+    assert torch.equal(avg[:, :4096], avg[:, 4096:8192])          # tiled copies give identical bits
+    idx = np.arange(0, 4096, 64)
+    qN, qdN, ravg, xee, goal, ok = oracle_rollout(base[idx], R, N)
+    got = avg[:, idx].cpu().numpy().T
+    assert np.abs(got - ravg)[ok].max() < 1e-3
