@@ -97,7 +97,7 @@ int mrf_device_count(void);
  *   rec    [MRF_REC][R][B]
  *   obst   [S][MRF_OBST][R][B]          obstacle o of robot r in scenario b
  *   action [MRF_DOF][R][B]
- *   avg_vel[R][B]   x_ee [R][3][B]   goal_est [3][B]
+ *   avg_vel[R][B]   x_ee [R][3][B]   goal_est [3][B] (x_goal_0 of robot `estimate_robot` as the rollout used it)
  *   qN, qdN [R][N][MRF_DOF][B]          (nullable)
  */
 int mrf_action_dev_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S, const double* obst,
@@ -125,16 +125,20 @@ int mrf_kinematics_dev_f32(mrf_handle_t h, const float* q, const float* qdot, fl
                            int64_t B, void* stream);
 
 /* Batched deadlock_checking step.  All arrays index b fastest; state arrays are updated in place.
- *   x_ee [R][3][B]  goals [R][3][B] (in/out)  weights [R][B] (in/out)  avg_vel [R][B]
+ *   x_ee [R][3][B]  goals [R][3][B] (in/out)  weights [R][B] (in/out)
+ *   exactly one of: avg_vel [R][B] (per-robot rollout averages; the kernel forms sum/R as
+ *   example_pandas_Jointspace.py:375 does) or avg_sum [B] (the caller's scalar); the other NULL
  *   sm_state [R][B] (state-machine codes)  time_step [B]  time_deadlock_out [B] (in/out)
- *   st_int [4][B]: i_leader, i_follower, i_robots_dead[0], i_robots_dead[1]  (in/out)
- *   st_goal [3][B]: goal_robot0 (in/out)      flag [B] (out): 1 if `deadlock` was raised this step */
+ *   st_int [4][B]: i_leader, i_follower, i_robots_dead[0], i_robots_dead[1]  (in/out; initial 0,1,0,1)
+ *   st_goal [3][B]: goal_robot0 (in/out; initial 0)      flag [B] (out, nullable): `deadlock` raised this step */
 int mrf_deadlock_dev_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights, const double* avg_vel,
-                         const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
-                         int32_t* st_int, double* st_goal, int32_t* flag, int64_t B, void* stream);
+                         const double* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                         int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag, int64_t B,
+                         void* stream);
 int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* goals, float* weights, const float* avg_vel,
-                         const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
-                         int32_t* st_int, float* st_goal, int32_t* flag, int64_t B, void* stream);
+                         const float* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                         int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
+                         void* stream);
 
 /* ------------------------------- host-pointer entries (AoS) -----------------------------------
  *   rec [B][R][MRF_REC]   obst [B][R][S][MRF_OBST]   action [B][R][MRF_DOF]
@@ -155,6 +159,12 @@ int mrf_rollout_cart_host_f32(mrf_handle_t h, int robot, const float* rec, int S
 /*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */
 int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,
                             int64_t B);
+
+/*   x_ee, goals [B][R][3]  weights [B][R]  avg_sum [B]  sm_state [B][R]  time_step, time_deadlock_out, flag [B]
+ *   st_int [B][4]  st_goal [B][3] */
+int mrf_deadlock_host_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights, const double* avg_sum,
+                          const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                          int32_t* st_int, double* st_goal, int32_t* flag, int64_t B);
 
 /* Number of kernels this library has launched through handle h since creation (for bench accounting). */
 int64_t mrf_launch_count(mrf_handle_t h);

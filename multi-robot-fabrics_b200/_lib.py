@@ -48,7 +48,7 @@ EXPORTS = [
     "mrf_rollout_cart_dev_f64", "mrf_rollout_cart_dev_f32", "mrf_kinematics_dev_f64", "mrf_kinematics_dev_f32",
     "mrf_deadlock_dev_f64", "mrf_deadlock_dev_f32", "mrf_action_host_f64", "mrf_action_host_f32",
     "mrf_rollout_host_f64", "mrf_rollout_host_f32", "mrf_rollout_cart_host_f64", "mrf_rollout_cart_host_f32",
-    "mrf_kinematics_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak",
+    "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak",
 ]
 
 
@@ -76,11 +76,12 @@ def lib():
         getattr(L, f"mrf_rollout_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_rollout_cart_dev_{p}").argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_kinematics_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
-        getattr(L, f"mrf_deadlock_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        getattr(L, f"mrf_deadlock_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_action_host_{p}").argtypes = [vp, i32, i32, vp, i32, vp, vp, i64]
         getattr(L, f"mrf_rollout_host_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i64]
         getattr(L, f"mrf_rollout_cart_host_{p}").argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, i64]
     L.mrf_kinematics_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, i64]
+    L.mrf_deadlock_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]
     L.mrf_fma_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L

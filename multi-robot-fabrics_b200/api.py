@@ -173,9 +173,10 @@ class Fabrics:
               "mrf_kinematics_dev")
         return x, v, a
 
-    def deadlock_dev(self, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
-                     flag=None):
-        """Batched deadlock_checking step; goals/weights/time_deadlock_out/st_* are updated in place."""
+    def deadlock_dev(self, x_ee, goals, weights, sm_state, time_step, time_deadlock_out, st_int, st_goal,
+                     avg_vel=None, avg_sum=None, flag=None):
+        """Batched deadlock_checking step; goals/weights/time_deadlock_out/st_* are updated in place.
+        Give avg_vel (R,B) (per-robot rollout averages) or avg_sum (B,)."""
         import torch
         p = self._prec(x_ee)
         B = x_ee.shape[-1]
@@ -183,7 +184,7 @@ class Fabrics:
             flag = torch.empty((B,), dtype=torch.int32, device=x_ee.device)
         fn = getattr(lib(), f"mrf_deadlock_dev_{p}")
         check(fn(self.handle.ptr, self._tp(x_ee), self._tp(goals), self._tp(weights), self._tp(avg_vel),
-                 self._tp(sm_state), self._tp(time_step), self._tp(time_deadlock_out), self._tp(st_int),
+                 self._tp(avg_sum), self._tp(sm_state), self._tp(time_step), self._tp(time_deadlock_out), self._tp(st_int),
                  self._tp(st_goal), self._tp(flag), B, self._stream()), "mrf_deadlock_dev")
         return flag
 

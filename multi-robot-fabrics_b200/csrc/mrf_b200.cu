@@ -24,6 +24,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/mrf_b200.h"
 #include "mrf_device.cuh"
@@ -232,7 +233,8 @@ struct DlCfg {
 
 template <typename T>
 __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
-                                const T* __restrict__ avg_vel, const int* __restrict__ sm_state,
+                                const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
+                                const int* __restrict__ sm_state,
                                 const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
                                 T* __restrict__ st_goal, int* __restrict__ flag, long long B) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,9 +252,10 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
         double dx = x[i][0] - g[i][0], dy = x[i][1] - g[i][1], dz = x[i][2] - g[i][2];
         dist_goal[i] = sqrt(dx * dx + dy * dy + dz * dz);
         st[i] = sm_state[(long long)i * B + b];
-        avg_sum += (double)avg_vel[(long long)i * B + b];
+        if (avg_vel) avg_sum += (double)avg_vel[(long long)i * B + b];
     }
-    avg_sum /= (double)R; // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375)
+    // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375), or the caller's scalar
+    avg_sum = avg_vel ? avg_sum / (double)R : (double)avg_sum_in[b];
     const int ts = time_step[b];
     int t_out = tdo[b];
     int i_leader = st_int[0 * B + b], i_follower = st_int[1 * B + b];
@@ -567,18 +570,20 @@ static int kinematics_dev(mrf_handle_t h, const T* q, const T* qd, T* x, T* v, T
 }
 
 template <typename T>
-static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const int32_t* sm_state,
-                        const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal, int32_t* flag, int64_t B,
-                        void* stream) {
-    if (!h || !x_ee || !goals || !weights || !avg_vel || !sm_state || !time_step || !tdo || !st_int || !st_goal)
+static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const T* avg_sum,
+                        const int32_t* sm_state, const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal,
+                        int32_t* flag, int64_t B, void* stream) {
+    if (!h || !x_ee || !goals || !weights || !sm_state || !time_step || !tdo || !st_int || !st_goal)
         return fail(MRF_EINVAL, "mrf_deadlock: null argument");
+    if ((avg_vel == nullptr) == (avg_sum == nullptr))
+        return fail(MRF_EINVAL, "mrf_deadlock: give exactly one of avg_vel [R][B] and avg_sum [B]");
     if (B <= 0) return fail(MRF_EINVAL, "mrf_deadlock: B must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
     const MrfConfig& c = h->cfg;
     DlCfg d{c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
             c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
     deadlock_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        d, x_ee, goals, weights, avg_vel, sm_state, time_step, tdo, st_int, st_goal, flag, (long long)B);
+        d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, (long long)B);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;
@@ -616,18 +621,19 @@ extern "C" int mrf_kinematics_dev_f32(mrf_handle_t h, const float* q, const floa
                                       int64_t B, void* stream) {
     return kinematics_dev<float>(h, q, qdot, x, v, a, B, stream);
 }
-extern "C" int mrf_deadlock_dev_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights,
-                                    const double* avg_vel, const int32_t* sm_state, const int32_t* time_step,
-                                    int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag,
-                                    int64_t B, void* stream) {
-    return deadlock_dev<double>(h, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
-                                flag, B, stream);
+extern "C" int mrf_deadlock_dev_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights, const double* avg_vel,
+                                    const double* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                                    int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag, int64_t B,
+                                    void* stream) {
+    return deadlock_dev<double>(h, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
+                             st_goal, flag, B, stream);
 }
 extern "C" int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* goals, float* weights, const float* avg_vel,
-                                    const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
-                                    int32_t* st_int, float* st_goal, int32_t* flag, int64_t B, void* stream) {
-    return deadlock_dev<float>(h, x_ee, goals, weights, avg_vel, sm_state, time_step, time_deadlock_out, st_int, st_goal,
-                               flag, B, stream);
+                                    const float* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                                    int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
+                                    void* stream) {
+    return deadlock_dev<float>(h, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
+                             st_goal, flag, B, stream);
 }
 
 // ---------------------------------- host-pointer entries ----------------------------------------
@@ -919,6 +925,75 @@ extern "C" int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const do
         MRF_CUDA(cudaStreamSynchronize(h->stream));
     }
     return finish_timed(h);
+}
+
+// host variant of the deadlock step: arrays in the reference's order, marshalled to SoA on the host (O(B R) copies)
+extern "C" int mrf_deadlock_host_f64(mrf_handle_t h, const double* x_ee, double* goals, double* weights,
+                                     const double* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                                     int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag,
+                                     int64_t B) {
+    if (!h || !x_ee || !goals || !weights || !avg_sum || !sm_state || !time_step || !time_deadlock_out || !st_int ||
+        !st_goal)
+        return fail(MRF_EINVAL, "mrf_deadlock_host: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_deadlock_host: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = h->cfg.n_robots;
+    const size_t nd = (size_t)B * (3 * R + 3 * R + R + 1 + 3), ni = (size_t)B * (R + 1 + 1 + 4 + 1);
+    std::vector<double> hd(nd);
+    std::vector<int32_t> hi(ni);
+    double* px = hd.data();
+    double* pg = px + (size_t)3 * R * B;
+    double* pw = pg + (size_t)3 * R * B;
+    double* pa = pw + (size_t)R * B;
+    double* ps = pa + B;
+    int32_t* qs = hi.data();
+    int32_t* qt = qs + (size_t)R * B;
+    int32_t* qo = qt + B;
+    int32_t* qi = qo + B;
+    int32_t* qf = qi + (size_t)4 * B;
+    for (int64_t b = 0; b < B; ++b) {
+        for (int r = 0; r < R; ++r) {
+            for (int k = 0; k < 3; ++k) {
+                px[((size_t)r * 3 + k) * B + b] = x_ee[(b * R + r) * 3 + k];
+                pg[((size_t)r * 3 + k) * B + b] = goals[(b * R + r) * 3 + k];
+            }
+            pw[(size_t)r * B + b] = weights[b * R + r];
+            qs[(size_t)r * B + b] = sm_state[b * R + r];
+        }
+        pa[b] = avg_sum[b];
+        qt[b] = time_step[b];
+        qo[b] = time_deadlock_out[b];
+        for (int k = 0; k < 4; ++k) qi[(size_t)k * B + b] = st_int[b * 4 + k];
+        for (int k = 0; k < 3; ++k) ps[(size_t)k * B + b] = st_goal[b * 3 + k];
+    }
+    int rc = stage_reserve(h, 0, sizeof(double) * nd);
+    if (rc) return rc;
+    rc = stage_reserve(h, 1, sizeof(int32_t) * ni);
+    if (rc) return rc;
+    double* dd = (double*)h->stage[0];
+    int32_t* di = (int32_t*)h->stage[1];
+    MRF_CUDA(cudaMemcpyAsync(dd, hd.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, h->stream));
+    MRF_CUDA(cudaMemcpyAsync(di, hi.data(), sizeof(int32_t) * ni, cudaMemcpyHostToDevice, h->stream));
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = deadlock_dev<double>(h, dd, dd + (pg - px), dd + (pw - px), nullptr, dd + (pa - px), di, di + (qt - qs),
+                              di + (qo - qs), di + (qi - qs), dd + (ps - px), di + (qf - qs), B, h->stream);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    MRF_CUDA(cudaMemcpyAsync(hd.data(), dd, sizeof(double) * nd, cudaMemcpyDeviceToHost, h->stream));
+    MRF_CUDA(cudaMemcpyAsync(hi.data(), di, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, h->stream));
+    rc = finish_timed(h);
+    if (rc) return rc;
+    for (int64_t b = 0; b < B; ++b) {
+        for (int r = 0; r < R; ++r) {
+            for (int k = 0; k < 3; ++k) goals[(b * R + r) * 3 + k] = pg[((size_t)r * 3 + k) * B + b];
+            weights[b * R + r] = pw[(size_t)r * B + b];
+        }
+        time_deadlock_out[b] = qo[b];
+        for (int k = 0; k < 4; ++k) st_int[b * 4 + k] = qi[(size_t)k * B + b];
+        for (int k = 0; k < 3; ++k) st_goal[b * 3 + k] = ps[(size_t)k * B + b];
+        if (flag) flag[b] = qf[b];
+    }
+    return MRF_OK;
 }
 
 template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {

@@ -13,7 +13,7 @@ template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) 
     d.static_or_dyn = c.static_or_dyn;
     d.has_coll = c.has_collision_links;
     d.estimate_goal = c.estimate_goal;
-    d.estimate_robot = c.estimate_goal ? c.estimate_robot : -1;
+    d.estimate_robot = (c.estimate_robot >= 0 && c.estimate_robot < c.n_robots) ? c.estimate_robot : -1;
     d.est_h = (T)c.estimate_horizon;
     d.dt = (T)c.dt;
     d.eps = (T)c.eps;

@@ -1,0 +1,390 @@
+"""The reference's planner call surface on top of the CUDA hot path (drop-in for that path only).
+
+Mirrors, with the same names, argument meaning and return shapes:
+  set_planner_panda(...) -> (planner, goal)      examples/example_pandas_Jointspace.py:64-134
+  planner.compute_action(**kwargs)               fabrics ParameterizedFabricPlanner.compute_action as called at
+                                                 examples/example_pandas_Jointspace.py:417-445,
+                                                 forward_planner_Cartesian.py:150-190
+  ForwardFabricsPlanner                          multi_robot_fabrics/fabrics_planner/forward_planner_Jointspace.py:12-423
+  FabricsRollouts                                multi_robot_fabrics/fabrics_planner/forward_planner_Cartesian.py:8-563
+  deadlockprevention                             multi_robot_fabrics/others_planner/deadlock_prevention.py:4-118
+
+What cannot be reproduced: ``planner._funs._function(*SX)`` symbolic inlining (forward_planner_Jointspace.py:185,233);
+the rollout classes here subsume the whole horizon instead, so ``forward_multi_fabrics_symbolic()`` /
+``symbolic_forward_fabrics()`` are cheap set-up steps.  Every number is computed by libmrf_b200.so on the GPU; if the
+library or a B200 is missing the constructors raise MrfError (no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ._lib import ANG, CON, DOF, G0, G1, G2, OBST, Q, QD, RB, REC, W0, W1, W2, MrfError, check, default_config, hptr, lib
+from .api import Fabrics
+
+PANDA_LIMITS = [[-2.8973, 2.8973], [-1.7628, 1.7628], [-2.8973, 2.8973], [-3.0718, -0.0698],
+                [-2.8973, 2.8973], [-0.0175, 3.7525], [-2.8973, 2.8973]]
+ROT_PANDA = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])
+
+
+def _vec(v, n=None):
+    a = np.asarray(v, dtype=np.float64).reshape(-1)
+    if n is not None and a.size != n:
+        raise MrfError(f"expected {n} values, got {a.size}")
+    return a
+
+
+def mount_transform(i_robot: int, mount_param: dict) -> np.ndarray:
+    """examples/example_pandas_Jointspace.py:108-118."""
+    angle = math.pi if i_robot in (1, 2) else 0.0
+    T = np.identity(4)
+    T[0:2, 0:2] = np.array([[np.cos(angle), -np.sin(angle)], [np.sin(angle), np.cos(angle)]])
+    T[0:3, 3] = mount_param["mount_positions"][i_robot]
+    return T
+
+
+class _SubGoal:
+    def __init__(self, weight, desired_position):
+        self.weight = weight
+        self.desired_position = desired_position
+
+
+class _GoalConfig:
+    def __init__(self):
+        self.subgoal0 = _SubGoal(2.0, [0.1, 0.6, 0.8])
+        self.subgoal1 = _SubGoal(10.0, [0.107, 0.0, 0.0])
+        self.subgoal2 = _SubGoal(1.0, [np.pi / 4])
+
+    def __len__(self):
+        return 3
+
+
+class PandaGoal:
+    """Stand-in for the GoalComposition of create_dummy_goal_panda (example_pandas_Jointspace.py:25-62): only the
+    attributes the rollout classes read (``_config.subgoalN.{weight,desired_position}``, ``len(_config)``)."""
+
+    def __init__(self):
+        self._config = _GoalConfig()
+
+
+class PandaFabricPlanner:
+    """compute_action drop-in for the planner built by set_planner_panda."""
+
+    def __init__(self, mount: np.ndarray, nr_obst: int, nr_obst_dyn: int, collision_links_nr, i_robot: int = 0,
+                 device: int = 0, limits=PANDA_LIMITS, mode: str = "vel", time_step: float = 0.01, dtype: str = "f64"):
+        self.mount = np.asarray(mount, dtype=np.float64).reshape(4, 4)
+        self.i_robot = i_robot
+        self.nr_obst, self.nr_obst_dyn = int(nr_obst), int(nr_obst_dyn)
+        # links with constant fk (panda_link1/2) carry no leaves; an empty list is the grasp planner
+        self.collision_links_nr = [l for l in collision_links_nr if l > 2]
+        missing = sorted(set(range(3, 9)) - set(min(l, 8) for l in self.collision_links_nr))
+        if self.collision_links_nr and missing:
+            raise MrfError(f"the CUDA path implements the reference's full link set 3..8 (or none); missing {missing}")
+        self.dtype = dtype
+        cfg = default_config(1, mode=1 if mode == "vel" else 0, dt=time_step,
+                             has_collision_links=1 if self.collision_links_nr else 0, mount=[self.mount], limits=limits)
+        self.fab = Fabrics(config=cfg, device=device)
+
+    # fabrics' CasadiFunctionWrapper expands list / dict kwargs into per-index parameters
+    def _record_and_obstacles(self, kw: dict):
+        rec = np.zeros(REC)
+        rec[Q:Q + 7] = _vec(kw["q"], 7)
+        rec[QD:QD + 7] = _vec(kw["qdot"], 7)
+        rec[G0:G0 + 3] = _vec(kw["x_goal_0"], 3)
+        rec[W0] = float(np.asarray(kw["weight_goal_0"]).reshape(-1)[0])
+        rec[G1:G1 + 3] = _vec(kw.get("x_goal_1", [0.107, 0.0, 0.0]), 3)
+        rec[W1] = float(np.asarray(kw.get("weight_goal_1", 0.0)).reshape(-1)[0])
+        rec[G2] = _vec(kw.get("x_goal_2", [0.0]))[0]
+        rec[W2] = float(np.asarray(kw.get("weight_goal_2", 0.0)).reshape(-1)[0])
+        rec[ANG:ANG + 9] = np.asarray(kw.get("angle_goal_1", ROT_PANDA), dtype=np.float64).reshape(9)
+        rec[CON:CON + 4] = _vec(kw.get("constraint_0", [0.0, 0.0, 1.0, 0.0]), 4)
+        links = kw.get("radius_body_panda_links", {})
+        for i, l in enumerate(range(3, 9)):
+            key = f"radius_body_panda_link{l}"
+            if key in kw:
+                rec[RB + i] = float(np.asarray(kw[key]).reshape(-1)[0])
+            elif str(l) in links:
+                rec[RB + i] = float(np.asarray(links[str(l)]).reshape(-1)[0])
+            elif l in links:
+                rec[RB + i] = float(np.asarray(links[l]).reshape(-1)[0])
+            elif self.collision_links_nr:
+                raise KeyError(key)
+        obst = np.zeros((self.nr_obst + self.nr_obst_dyn, OBST))
+        for i in range(self.nr_obst):                      # static spheres: x_obst_i, radius_obst_i
+            x = kw[f"x_obst_{i}"] if f"x_obst_{i}" in kw else kw["x_obsts"][i]
+            r = kw[f"radius_obst_{i}"] if f"radius_obst_{i}" in kw else kw["radius_obsts"][i]
+            obst[i, 0:3] = _vec(x, 3)
+            obst[i, 9] = float(np.asarray(r).reshape(-1)[0])
+        for i in range(self.nr_obst_dyn):                  # dynamic spheres
+            o = self.nr_obst + i
+            get = lambda single, plural: kw[f"{single}_{i}"] if f"{single}_{i}" in kw else kw[plural][i]
+            obst[o, 0:3] = _vec(get("x_obst_dynamic", "x_obsts_dynamic"), 3)
+            obst[o, 3:6] = _vec(get("xdot_obst_dynamic", "xdot_obsts_dynamic"), 3)
+            obst[o, 6:9] = _vec(get("xddot_obst_dynamic", "xddot_obsts_dynamic"), 3)
+            obst[o, 9] = float(np.asarray(get("radius_obst_dynamic", "radius_obsts_dynamic")).reshape(-1)[0])
+        if not self.collision_links_nr:
+            obst = obst[:0]
+        return rec, obst
+
+    def compute_action(self, **kwargs) -> np.ndarray:
+        rec, obst = self._record_and_obstacles(kwargs)
+        act = self.fab.action_host(rec[None, None, :], obst[None, None] if len(obst) else None, dtype=self.dtype)[0, 0]
+        act = np.asarray(act, dtype=np.float64)
+        if np.linalg.norm(act) < 1e-6:     # fabrics: "avoid too small actions"
+            act = act * 0.0
+        return act
+
+
+def set_planner_panda(degrees_of_freedom: int = 7, nr_obst=0, nr_obst_dyn=1, collision_links_nr=(5,), urdf_links=None,
+                      mount_param=None, i_robot=0, device: int = 0, dtype: str = "f64"):
+    """Same signature as the reference's set_planner_panda; the URDF constants are compiled into the kernels."""
+    if degrees_of_freedom != 7:
+        raise MrfError("the CUDA path is specialised to the 7-dof Panda chain")
+    mount = mount_transform(i_robot, mount_param)
+    return PandaFabricPlanner(mount, nr_obst, nr_obst_dyn, list(collision_links_nr), i_robot, device, dtype=dtype), PandaGoal()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ForwardFabricsPlanner:
+    """Coupled joint-space Rollout Fabrics (forward_planner_Jointspace.py)."""
+
+    def __init__(self, params, planners, N_steps=None, fk_dict=None, goal_struct_robots=None, ROLLOUTS_PLOTTING=0,
+                 device: int = 0, dtype: str = "f64", estimate_goal: int = 0):
+        self.N_horizon = params.N_HORIZON
+        self.dt = params.dt
+        self.dof = params.dof
+        self.nr_robots = len(self.dof)
+        self.nr_obsts = params.nr_obsts
+        self.planners = planners
+        self.fabrics_mode = params.fabrics_mode
+        self.r_robots = params.r_robots
+        self.rotation_matrices_pandas = params.rotation_matrix_pandas
+        self.collision_links_nrs = params.collision_links_nrs
+        self.goal_struct_robots = goal_struct_robots
+        self.nr_subgoals = [3] * self.nr_robots
+        self.dtype = dtype
+        if self.fabrics_mode != "vel":
+            raise MrfError("joint-space rollouts are defined for fabrics_mode 'vel' (forward_planner_Jointspace.py:233)")
+        if any(n != 0 for n in self.nr_obsts):
+            raise MrfError("static obstacles in the rollout planners are not used by the reference (nr_obsts = 0)")
+        # radius bodies of links > 2 (forward_planner_Jointspace.py:37-40)
+        self.r_robots_args = [[self.r_robots[i][z] for z, c in enumerate(self.collision_links_nrs[i]) if c > 2]
+                              for i in range(self.nr_robots)]
+        mounts = [np.asarray(p.mount) for p in planners]
+        cfg = default_config(self.nr_robots, dt=self.dt, static_or_dyn=int(params.STATIC_OR_DYN_FABRICS),
+                             mount=mounts, r_robots=[list(map(float, r)) for r in self.r_robots],
+                             estimate_goal=int(estimate_goal))
+        self.fab = Fabrics(config=cfg, device=device)
+
+    def forward_multi_fabrics_symbolic(self):
+        """The reference builds the CasADi graph here; the CUDA kernels need no per-configuration compilation."""
+        return {}
+
+    def _records(self, inputs_action) -> np.ndarray:
+        R = self.nr_robots
+        rec = np.zeros((1, R, REC))
+        for i in range(R):                         # argument order of forward_planner_Jointspace.py:303-329
+            rec[0, i, ANG:ANG + 9] = np.asarray(self.rotation_matrices_pandas[i], dtype=np.float64).reshape(9)
+            rec[0, i, CON:CON + 4] = _vec(inputs_action["constraints"][i], 4)
+            rec[0, i, Q:Q + 7] = _vec(inputs_action["q_robots"][i], 7)
+            rec[0, i, QD:QD + 7] = _vec(inputs_action["q_dot_robots"][i], 7)
+            rec[0, i, W0] = float(np.asarray(inputs_action["weight_goals0"][i]).reshape(-1)[0])
+            rec[0, i, W1] = float(np.asarray(inputs_action["weight_goals1"][i]).reshape(-1)[0])
+            rec[0, i, W2] = float(np.asarray(inputs_action["weight_goals2"][i]).reshape(-1)[0])
+            rec[0, i, G0:G0 + 3] = _vec(inputs_action["x_goals0"][i], 3)
+            rec[0, i, G1:G1 + 3] = _vec(inputs_action["x_goals1"][i], 3)
+            rec[0, i, G2] = _vec(inputs_action["x_goals2"][i])[0]
+            rec[0, i, RB:RB + 6] = np.asarray(self.r_robots_args[i], dtype=np.float64)
+        return rec
+
+    def get_velocity_rollouts(self, inputs_action):
+        """-> list of R arrays of shape (1,): mean square joint velocity over the horizon (:298-336)."""
+        out = self.fab.rollout_host(self._records(inputs_action), self.N_horizon, dtype=self.dtype)
+        self.last = out
+        return [np.array([float(out["avg_vel"][0, i])]) for i in range(self.nr_robots)]
+
+    def rollouts_numerical(self, inputs_action=None, **_ignored):
+        """-> (q_N, qdot_N, qddot_N) dicts keyed 'robot_i', each [array(7, N)] (:338-423)."""
+        out = self.fab.rollout_host(self._records(inputs_action), self.N_horizon, dtype=self.dtype, trajectories=True)
+        self.last = out
+        qn, qdn, qddn = {}, {}, {}
+        for i in range(self.nr_robots):
+            qn[f"robot_{i}"] = [np.asarray(out["qN"][0, i], dtype=np.float64).T.copy()]
+            qdn[f"robot_{i}"] = [np.asarray(out["qdN"][0, i], dtype=np.float64).T.copy()]
+            qddn[f"robot_{i}"] = [np.zeros((DOF, self.N_horizon))]      # q_ddot is identically 0 in 'vel' mode (:202)
+        return qn, qdn, qddn
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class _DM:
+    """Minimal stand-in for the casadi DM returned by avg_vel_fun (callers use ``.full()[0]``)."""
+
+    def __init__(self, v):
+        self._v = np.atleast_2d(np.asarray(v, dtype=np.float64))
+
+    def full(self):
+        return self._v
+
+
+class FabricsRollouts:
+    """Decoupled (Cartesian constant-velocity obstacle) rollouts, forward_planner_Cartesian.py."""
+
+    def __init__(self, N, dt, nx, nu, dof, nr_obsts, bool_ring, nr_obsts_dyn=0, v_obsts_dyn=(), fabrics_mode="acc",
+                 collision_links_nrs=(7,), nr_constraints=0, radius_sphere=0.08, constraints=None, nr_goals=3,
+                 dtype: str = "f64"):
+        self.N, self.dt, self.dof = N, dt, dof
+        self.nr_obsts, self.nr_obsts_dyn = nr_obsts, nr_obsts_dyn
+        self.v_obsts_dyn = list(v_obsts_dyn)
+        self.a_obsts_dyn = [np.zeros((3,))] * len(self.v_obsts_dyn)
+        self.fabrics_mode = fabrics_mode
+        self.collision_links_nrs = list(collision_links_nrs)
+        self.nr_constraints = nr_constraints
+        self.radius_sphere = radius_sphere
+        self.rotation_matrix_panda = ROT_PANDA.copy()
+        self.radius_obsts_dyn, self.radius_obsts = [], []
+        self.constraints = constraints
+        self.nr_goals = nr_goals
+        self.dtype = dtype
+        self.radius_body_panda_links = {str(l): np.array(radius_sphere) for l in self.collision_links_nrs if l > 2}
+        if fabrics_mode != "vel":
+            raise MrfError("the CUDA Cartesian rollout implements fabrics_mode 'vel' (the reference's setting)")
+
+    def preset_radii_obsts_dyn(self, radii_obst_dyn):
+        self.radius_obsts_dyn = radii_obst_dyn
+
+    def reset_v_obsts_dyn(self, v_obsts_dyn):
+        self.v_obsts_dyn = v_obsts_dyn
+
+    def symbolic_forward_fabrics(self, planner, goal_struct):
+        self.planner = planner
+        self.nr_subgoals = len(goal_struct._config)
+        return {}
+
+    def define_arguments_numerical(self, q_robot, q_dot_robot, weight_goals, x_goals, x_obsts, x_obsts_dyn, v_obsts_dyn,
+                                   constraints=()):
+        """Same flat argument list as forward_planner_Cartesian.py:507-536."""
+        a = []
+        if self.nr_subgoals > 1:
+            a.append(self.rotation_matrix_panda)
+        for _ in range(self.nr_constraints):
+            a.append(constraints)
+        a.append(q_robot)
+        a.append(q_dot_robot)
+        for i in range(self.nr_subgoals):
+            a.append(weight_goals["subgoal" + str(i)])
+        for i in range(self.nr_subgoals):
+            a.append(x_goals["subgoal" + str(i)])
+        for i in range(self.nr_obsts):
+            a.append(x_obsts[i])
+        for i in range(self.nr_obsts):
+            a.append(self.radius_obsts[i])
+        if self.nr_obsts + self.nr_obsts_dyn > 0:
+            for r in self.radius_body_panda_links.values():
+                a.append(r)
+        for r in self.radius_obsts_dyn:
+            a.append(r)
+        for i in range(self.nr_obsts_dyn):
+            a.append(x_obsts_dyn[i])
+        for i in range(self.nr_obsts_dyn):
+            a.append(v_obsts_dyn[i])
+        for i in range(self.nr_obsts_dyn):
+            a.append(self.a_obsts_dyn[i] if i < len(self.a_obsts_dyn) else np.zeros(3))
+        self.arguments = a
+        return a
+
+    def _unpack(self, arguments):
+        it = iter(arguments)
+        rec = np.zeros(REC)
+        if self.nr_subgoals > 1:
+            rec[ANG:ANG + 9] = np.asarray(next(it), dtype=np.float64).reshape(9)
+        for _ in range(self.nr_constraints):
+            rec[CON:CON + 4] = _vec(next(it), 4)
+        rec[Q:Q + 7] = _vec(next(it), 7)
+        rec[QD:QD + 7] = _vec(next(it), 7)
+        w = [float(np.asarray(next(it)).reshape(-1)[0]) for _ in range(self.nr_subgoals)]
+        g = [_vec(next(it)) for _ in range(self.nr_subgoals)]
+        rec[W0], rec[G0:G0 + 3] = w[0], g[0]
+        if self.nr_subgoals > 1:
+            rec[W1], rec[G1:G1 + 3] = w[1], g[1]
+        if self.nr_subgoals > 2:
+            rec[W2], rec[G2] = w[2], g[2][0]
+        xs = [_vec(next(it), 3) for _ in range(self.nr_obsts)]
+        rs = [float(np.asarray(next(it)).reshape(-1)[0]) for _ in range(self.nr_obsts)]
+        if self.nr_obsts + self.nr_obsts_dyn > 0:
+            for i, l in enumerate(range(3, 9)):
+                if str(l) in self.radius_body_panda_links:
+                    rec[RB + i] = float(np.asarray(next(it)).reshape(-1)[0])
+        rd = [float(np.asarray(next(it)).reshape(-1)[0]) for _ in range(len(self.radius_obsts_dyn))]
+        xd = [_vec(next(it), 3) for _ in range(self.nr_obsts_dyn)]
+        vd = [_vec(next(it), 3) for _ in range(self.nr_obsts_dyn)]
+        obst = np.zeros((self.nr_obsts + self.nr_obsts_dyn, OBST))
+        for i in range(self.nr_obsts):
+            obst[i, 0:3], obst[i, 9] = xs[i], rs[i]
+        for i in range(self.nr_obsts_dyn):
+            o = self.nr_obsts + i
+            obst[o, 0:3], obst[o, 3:6], obst[o, 9] = xd[i], vd[i], rd[i]
+        return rec, obst
+
+    def _run(self, arguments):
+        rec, obst = self._unpack(arguments)
+        return self.planner.fab.rollout_cart_host(0, rec[None], obst[None], self.N, dtype=self.dtype)
+
+    def rollouts_numerical(self, arguments):
+        """-> q_N, qdot_N, qddot_N, each array (7, N) (forward_planner_Cartesian.py:538-559)."""
+        _, qN, qdN = self._run(arguments)
+        return (np.asarray(qN[0], dtype=np.float64).T.copy(), np.asarray(qdN[0], dtype=np.float64).T.copy(),
+                np.zeros((DOF, self.N)))
+
+    def get_velocity_rollouts(self, arguments):
+        avg, _, _ = self._run(arguments)
+        return _DM([float(avg[0])])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class deadlockprevention:  # noqa: N801 (the reference's class name)
+    """deadlock_prevention.py drop-in; the check itself runs in the CUDA deadlock kernel (B = 1)."""
+
+    def __init__(self, dof, n_robots, N_horizon, device: int = 0):
+        if dof[0] == 2:
+            raise MrfError("the point-mass constants of deadlock_prevention.py:12-19 are not part of the Panda hot path")
+        self.dof, self.n_robots, self.N_horizon = dof, n_robots, N_horizon
+        self.fab = Fabrics(config=default_config(n_robots), device=device)
+        self._st_int = np.array([[0, 1, 0, 1]], dtype=np.int32)      # i_leader, i_follower, i_robots_dead (:10-11,33)
+        self._st_goal = np.zeros((1, 3))
+        self.deadlock = False
+
+    @property
+    def i_leader(self):
+        return int(self._st_int[0, 0])
+
+    @property
+    def i_follower(self):
+        return int(self._st_int[0, 1])
+
+    @property
+    def goal_robot0(self):
+        return self._st_goal[0].copy()
+
+    def deadlock_checking(self, x_robots, goal_robots, goal_weights, time_step, time_deadlock_out, avg_sum,
+                          state_machine_robots=()):
+        R = self.n_robots
+        x = np.ascontiguousarray(np.stack([_vec(v, 3) for v in x_robots])[None])
+        g = np.ascontiguousarray(np.stack([_vec(v, 3) for v in goal_robots])[None])
+        w = np.ascontiguousarray(np.array([[float(np.asarray(v).reshape(-1)[0]) for v in goal_weights]]))
+        a = np.array([float(np.asarray(avg_sum).reshape(-1)[0])])
+        sm = np.ascontiguousarray(np.array([list(state_machine_robots)], dtype=np.int32))
+        ts = np.array([int(time_step)], dtype=np.int32)
+        tdo = np.array([int(time_deadlock_out)], dtype=np.int32)
+        flag = np.zeros(1, dtype=np.int32)
+        check(lib().mrf_deadlock_host_f64(self.fab.handle.ptr, hptr(x), hptr(g), hptr(w), hptr(a), hptr(sm), hptr(ts),
+                                          hptr(tdo), hptr(self._st_int), hptr(self._st_goal), hptr(flag), 1),
+              "mrf_deadlock_host")
+        self.deadlock = bool(flag[0])
+        # the reference mutates the caller's lists in place (this is how the follower goal reaches compute_action)
+        for i in range(R):
+            if g[0, i].tolist() != _vec(goal_robots[i], 3).tolist():
+                goal_robots[i] = g[0, i].copy()
+            if w[0, i] != float(np.asarray(goal_weights[i]).reshape(-1)[0]):
+                goal_weights[i] = w[0, i]
+        return goal_robots, goal_weights, int(tdo[0])

@@ -1,0 +1,136 @@
+"""CPU tests of the oracle itself (no GPU): O2 (closed-form C) against the golden vectors made by O1 (autodiff,
+fabrics-structured), FK known answers derived from the reference's constants, and the deadlock restatement against
+golden sequences produced by the reference's own class."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import o2
+from oracle.deadlock_ref import DeadlockOracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold(built):
+    return np.load(os.path.join(GOLD, "fabric_golden.npz"))
+
+
+def test_fk_known_answers(built):
+    """at pos0 the hand sits at the reference's start goals (parameters_manipulators.py:93,126-128)
+    -- validates chain constants, mount convention and that sub-goal 0 is expressed in the world frame."""
+    pos0 = np.array([1.125, 0.19, 0.12, -1.66, 0.0, 1.88, np.pi / 4])
+    cfg = o2.default_config(2)
+    x0, *_ = o2.kinematics(cfg, 0, pos0, np.zeros(7))
+    x1, *_ = o2.kinematics(cfg, 1, pos0, np.zeros(7))
+    assert np.allclose(x0[2], [0.025732, 0.053847, 1.293313], atol=1e-6)
+    assert np.allclose(x0[7], [0.204352, 0.589084, 1.147689], atol=1e-6)
+    assert np.allclose(x1[7], [0.795648, -0.589084, 1.147689], atol=1e-6)
+    assert np.linalg.norm(x0[7] - [0.2, 0.6, 1.15]) < 0.012
+    assert np.linalg.norm(x1[7] - [0.8, -0.6, 1.15]) < 0.012
+    assert np.array_equal(x0[0], x0[1]) and np.array_equal(x0[4], x0[5])     # link1==link2, link5==link6 origins
+    R = o2.ROT_PANDA
+    assert np.allclose(R @ (x0[7] - x0[6]), [0.106920, 0.003952, -0.001209], atol=1e-6)   # ~ x_goal_1
+
+
+def test_o2_actions_match_o1_golden(gold):
+    for c in range(int(gold["n_act"])):
+        p = f"act{c}_"
+        cfg = o2.default_config(3, mode=int(gold[p + "mode"]), has_collision_links=0 if int(gold[p + "grasp"]) else 1)
+        obst = gold[p + "obst"]
+        a, d = o2.action(cfg, int(gold[p + "robot"]), gold[p + "rec"], obst[:, 0:3], obst[:, 3:6], obst[:, 6:9],
+                         obst[:, 9], want_diag=True)
+        ref = gold[p + "action"]
+        assert np.abs(a - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), c
+        for k in ("M_g", "f_g", "fe_g", "M_f", "f_f", "qdd"):
+            assert np.abs(d[k] - gold[p + k]).max() <= 1e-11 * max(1.0, np.abs(gold[p + k]).max()), (c, k)
+
+
+def test_o2_kinematics_match_o1_golden(gold):
+    cfg = o2.default_config(3)
+    rec = gold["kin_rec"]
+    x, v, c, _ = o2.kinematics(cfg, int(gold["kin_robot"]), rec[0:7], rec[7:14])
+    assert np.abs(x - gold["kin_xva"][:, 0]).max() < 1e-14
+    assert np.abs(v - gold["kin_xva"][:, 1]).max() < 1e-14
+    assert np.abs(-c - gold["kin_xva"][:, 2]).max() < 1e-13       # published a = Jdot_sign(-1) * d(J qd)/dq qd
+
+
+def test_o2_rollouts_match_o1_golden(gold):
+    cfg = o2.default_config(2)
+    N = int(gold["ro_N"])
+    qN, qdN, avg, _ = o2.rollout_jointspace(cfg, gold["ro_rec"], N)
+    assert np.abs(qN - gold["ro_qN"]).max() < 1e-12
+    assert np.abs(qdN - gold["ro_qdN"]).max() < 1e-11
+    assert np.abs(avg - gold["ro_avg"]).max() < 1e-11
+    obst = gold["cart_obst"]
+    cq, cqd, cavg = o2.rollout_cartesian(cfg, 0, gold["cart_rec"], obst[:, 0:3], obst[:, 3:6], obst[:, 9], 2)
+    assert np.abs(cq - gold["cart_qN"]).max() < 1e-12
+    assert np.abs(cqd - gold["cart_qdN"]).max() < 1e-11
+    assert abs(cavg - float(gold["cart_avg"])) < 1e-11
+
+
+def test_o1_live_matches_o2_small(built):
+    """One live O1 evaluation (slow path, torch autodiff) so the generator of the golden file stays exercised."""
+    from oracle import o1_fabrics as o1
+    rng = np.random.default_rng(3)
+    cfg = o2.default_config(2)
+    rec = o2.make_record([0.9, 0.2, 0.1, -1.6, 0.2, 1.8, 0.5], rng.uniform(-0.5, 0.5, 7), [0.5, 0.1, 1.0], 2.0)
+    obst = np.array([[0.6, 0.2, 1.2, 0.1, -0.2, 0.05, 0.3, 0.1, -0.2, 0.08]])
+    pl = o1.make_panda_planner(o2.mount_of(cfg, 1), n_dyn=1)
+    p = o2.record_to_params(rec)
+    p.update(x_obst_dynamic_0=obst[0, 0:3], xdot_obst_dynamic_0=obst[0, 3:6], xddot_obst_dynamic_0=obst[0, 6:9],
+             radius_obst_dynamic_0=obst[0, 9])
+    a1, _ = pl.action_raw(rec[0:7], rec[7:14], p)
+    a2 = o2.action(cfg, 1, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
+    assert np.abs(a1 - a2).max() < 1e-11
+
+
+def test_jdot_sign_and_eps_are_live_knobs(built):
+    """The restatement assumptions are configuration, not constants: changing them changes the action."""
+    rec = o2.make_record([0.9, 0.2, 0.1, -1.6, 0.2, 1.8, 0.5], [0.3, -0.2, 0.4, 0.1, -0.3, 0.2, 0.1], [0.5, 0.1, 1.0])
+    obst = np.array([[0.6, 0.2, 1.2, 0.1, -0.2, 0.05, 0.0, 0.0, 0.0, 0.08]])
+    base = o2.action(o2.default_config(2), 0, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
+    plus = o2.action(o2.default_config(2, jdot_sign=1.0), 0, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
+    assert np.abs(base - plus).max() > 1e-6
+
+
+def test_deadlock_restatement_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "deadlock_golden.npz"))
+    raised = 0
+    for c in range(int(g["n_cases"])):
+        p = f"c{c}_"
+        dl = DeadlockOracle(int(g[p + "R"]))
+        tdo = 1000
+        for t in range(len(g[p + "x"])):
+            go, wo, tdo, flag = dl.step(g[p + "x"][t], g[p + "goals"][t], g[p + "weights"][t], int(g[p + "time_step"][t]),
+                                        tdo, float(g[p + "avg"][t]), list(g[p + "states"][t]))
+            raised += int(flag)
+            assert np.array_equal(np.array(go), g[p + "goals_out"][t])
+            assert np.array_equal(np.array(wo, dtype=float), g[p + "weights_out"][t])
+            assert tdo == g[p + "tdo_out"][t]
+    assert raised > 50
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/multi_robot_fabrics/others_planner/deadlock_prevention.py"),
+                    reason="reference tree only exists in the build container")
+def test_deadlock_restatement_matches_live_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_dlp", "/root/reference/multi_robot_fabrics/others_planner/deadlock_prevention.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(99)
+    for R in (2, 3):
+        ref, mine = mod.deadlockprevention([7] * R, R, 20), DeadlockOracle(R)
+        tdo_r = tdo_m = 1000
+        for t in range(200):
+            x = rng.uniform([0.3, -0.1, 1.0], [0.6, 0.1, 1.2], size=(R, 3))
+            goals = rng.uniform([0.2, -0.6, 0.8], [0.8, 0.6, 1.25], size=(R, 3))
+            w = rng.choice([2.0, 3.0], size=R)
+            avg = float(rng.uniform(0.0, 0.3))
+            st = list(rng.choice([0, 1, 1, 0, 2], size=R))
+            gr, wr, tdo_r = ref.deadlock_checking([v.copy() for v in x], [v.copy() for v in goals], list(w), t, tdo_r, avg, st)
+            gm, wm, tdo_m, _ = mine.step(x, goals, w, t, tdo_m, avg, st)
+            assert np.array_equal(np.array(gr, dtype=float), np.array(gm)) and tdo_r == tdo_m
+            assert [float(v) for v in wr] == [float(v) for v in wm]
