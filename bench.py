@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- fabric robot-steps/s of batched 3-Panda RF-CV rollouts (BASELINE.json's metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--horizon H]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+              bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic scenarios on every rank: the coupled RF-CV rollout
+kernel (goal estimate + H horizon steps for 3 Pandas per scenario) followed by the deadlock kernel, and for N > 1 the
+final NCCL all_gather of the per-scenario results.  One robot-step = one fabric action evaluation of one robot at one
+horizon step (FK/J/Jdot qdot, leaves, pullback, solve, integrator update, avg-velocity accumulation).
+
+  value     whole-job robot-steps/s with the scenario records already resident in HBM (CUDA events per step on the
+            launching stream; L2 flushed between timed steps; max over ranks).
+  e2e       the same metric through the host-pointer C-ABI call (mrf_rollout_host_f32): every step copies the records
+            from pinned host memory, transposes, runs the kernels and reads avg_vel / x_ee / goal_est back.
+  roofline  the kernel is compute-bound on the FP32 CUDA-core pipe (arithmetic intensity > 200 FLOP/B, no tensor
+            cores): achieved = robot-steps/s x F(S=16) = 13.4 kFLOP over the FMA peak measured in this
+            run by the library's micro-benchmark (MEASURED_PEAKS.json holds HBM / bf16 peaks only); the HBM view is
+            given beside it.
+  cpu_baseline / --impl reference: the reference's dependencies (casadi / fabrics) are not installable offline, so the
+            CPU arm is oracle O2 (closed-form C port, OpenMP over scenarios) on the box's host cores, kind "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_ROBOTS = 3
+FLOPS_PER_ROBOT_STEP = 5700 + 480 * 16      # SURVEY.md 8d / Appendix E, S = 8 (R-1) = 16 spheres
+METRIC = "fabric robot-steps/sec (3 Panda RF-CV)"
+UNIT = "robot-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="scenarios per GPU (weak scaling)")
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def config_dict(a, extra=None):
+    d = {"workload": f"{a.batch} random 3-Panda scenarios per GPU x horizon {a.horizon}, RF-CV (goal estimate of "
+                     f"robot 1, deadlock heuristic), joint-space coupled rollouts",
+         "n_robots": N_ROBOTS, "horizon": a.horizon, "scenarios_per_gpu": a.batch, "spheres_seen_per_robot": 16,
+         "parallelism": f"scenario-sharded x{a.gpus}", "l2": "flushed (256 MiB write) between timed steps"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle O2, the closed-form port) -- the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample(horizon: int, target_s: float, seed: int = 0):
+    import ctypes as C
+
+    import multi_robot_fabrics_b200 as m
+    from oracle import o2
+
+    cfg = o2.default_config(N_ROBOTS)
+    cores = o2.max_threads()
+
+    def run(rec):
+        B = rec.shape[0]
+        rec = rec.copy()
+        t0 = time.perf_counter()
+        for b in range(B):   # RF-CV goal estimate (example_pandas_Jointspace.py:346-348), part of the timed path
+            x, v = o2.endeffector(cfg, 1, rec[b, 1, 0:7], rec[b, 1, 7:14], use_jqd=False)
+            rec[b, 1, o2.G0:o2.G0 + 3] = x + 0.2 * v
+        avg, xee = np.zeros((B, N_ROBOTS)), np.zeros((B, N_ROBOTS, 3))
+        o2.lib().mrfo_rollout_jointspace_batch(C.byref(cfg), o2._p(np.ascontiguousarray(rec)), B, horizon, None, None,
+                                               o2._p(avg), o2._p(xee), 0)
+        return time.perf_counter() - t0
+
+    probe = m.scenarios.generate(256, N_ROBOTS, seed=seed)
+    run(probe[:32])
+    t = run(probe)
+    n = int(max(256, min(262144, 256 * target_s / max(t, 1e-6))))
+    rec = m.scenarios.generate(n, N_ROBOTS, seed=seed + 1)
+    t = run(rec)
+    rs = n * N_ROBOTS * horizon / t
+    return dict(value=rs, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} scenarios x 3 Pandas x H{horizon} in {t:.2f} s, oracle O2 (closed-form C, float64, OpenMP "
+                       f"over scenarios); the reference's casadi/fabrics wheels are not installable offline"), n, t
+
+
+def reference_arm(a):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    g.build()
+    per = max(1.0, min(8.0, 120.0 / max(1, a.steps + a.warmup)))
+    base, n, _ = cpu_sample(a.horizon, per)
+    times = []
+    import ctypes as C
+
+    import multi_robot_fabrics_b200 as m
+    from oracle import o2
+    cfg = o2.default_config(N_ROBOTS)
+    rec0 = m.scenarios.generate(n, N_ROBOTS, seed=2)
+    for it in range(a.warmup + a.steps):
+        rec = rec0.copy()
+        t0 = time.perf_counter()
+        for b in range(n):
+            x, v = o2.endeffector(cfg, 1, rec[b, 1, 0:7], rec[b, 1, 7:14], use_jqd=False)
+            rec[b, 1, o2.G0:o2.G0 + 3] = x + 0.2 * v
+        avg, xee = np.zeros((n, N_ROBOTS)), np.zeros((n, N_ROBOTS, 3))
+        o2.lib().mrfo_rollout_jointspace_batch(C.byref(cfg), o2._p(np.ascontiguousarray(rec)), n, a.horizon, None, None,
+                                               o2._p(avg), o2._p(xee), 0)
+        dt = time.perf_counter() - t0
+        if it >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * N_ROBOTS * a.horizon * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(a, {"reference_sample_scenarios_per_step": n}),
+            "cpu_baseline": dict(base, value=value,
+                                 sample=f"each step = {n} scenarios x 3 Pandas x H{a.horizon} (bounded sample of the "
+                                        f"GPU arm's workload), oracle O2 port on {base['cores']} host threads"),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+    import multi_robot_fabrics_b200 as m
+    from multi_robot_fabrics_b200.api import Fabrics, to_soa
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist.barrier()
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+    ndt = np.float32 if a.dtype == "f32" else np.float64
+    R, B, H = N_ROBOTS, a.batch, a.horizon
+
+    # ---- synthetic scenarios: PCG64(seed = rank), 4096 distinct rejection-sampled scenarios tiled to the batch ----
+    base = m.scenarios.generate(min(B, 4096), R, seed=rank)
+    reps = (B + len(base) - 1) // len(base)
+    rec_h = np.ascontiguousarray(np.tile(base, (reps, 1, 1))[:B], dtype=ndt)            # (B,R,44) AoS
+    fab = Fabrics(R, device=local, estimate_goal=1)                                         # RF-CV
+    d_rec = torch.from_numpy(to_soa(rec_h)).to(dev)
+    avg = torch.empty((R, B), dtype=tdt, device=dev)
+    xee = torch.empty((R, 3, B), dtype=tdt, device=dev)
+    gest = torch.empty((3, B), dtype=tdt, device=dev)
+    goals = torch.empty((R, 3, B), dtype=tdt, device=dev)
+    weights = torch.empty((R, B), dtype=tdt, device=dev)
+    sm_state = torch.zeros((R, B), dtype=torch.int32, device=dev)
+    tstep = torch.full((B,), 100, dtype=torch.int32, device=dev)
+    tdo = torch.full((B,), 1000, dtype=torch.int32, device=dev)
+    st_int = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous()
+    st_goal = torch.zeros((3, B), dtype=tdt, device=dev)
+    flag = torch.empty((B,), dtype=torch.int32, device=dev)
+    result = torch.empty((R + 1, B), dtype=tdt, device=dev)          # what a caller gathers: avg_vel[R] + deadlock flag
+    gathered = torch.empty((world, R + 1, B), dtype=tdt, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        fab.rollout_dev(d_rec, H, avg_vel=avg, x_ee=xee, goal_est=gest)
+        goals.copy_(d_rec[14:17].permute(1, 0, 2))                    # caller's goal list (robot 1 gets the estimate)
+        goals[1].copy_(gest)
+        weights.copy_(d_rec[17])
+        fab.deadlock_dev(xee, goals, weights, sm_state, tstep, tdo, st_int, st_goal, avg_vel=avg, flag=flag)
+        if world > 1:
+            result[:R].copy_(avg)
+            result[R].copy_(flag)
+            dist.all_gather_into_tensor(gathered, result)
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    torch.cuda.synchronize()
+    peak32 = fab.handle.fma_peak_tflops(False)
+    peak64 = fab.handle.fma_peak_tflops(True)
+
+    # ---- timed region: value (device-resident inputs) ----
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = fab.handle.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for i in range(a.steps):
+        flush.fill_(i & 0xFF)                       # L2 flush, outside the per-step events
+        ev[i][0].record()
+        kev[i][0].record()
+        fab.rollout_dev(d_rec, H, avg_vel=avg, x_ee=xee, goal_est=gest)
+        kev[i][1].record()
+        goals.copy_(d_rec[14:17].permute(1, 0, 2))
+        goals[1].copy_(gest)
+        weights.copy_(d_rec[17])
+        fab.deadlock_dev(xee, goals, weights, sm_state, tstep, tdo, st_int, st_goal, avg_vel=avg, flag=flag)
+        if world > 1:
+            result[:R].copy_(avg)
+            result[R].copy_(flag)
+            dist.all_gather_into_tensor(gathered, result)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = fab.handle.launches - launches0
+    clocks = sampler.stop()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in kev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    units = world * B * R * H * a.steps
+    value = units / total_s
+    kernel_ms = statistics.mean(kern_ms)
+
+    # ---- e2e: host-pointer C-ABI, pinned host buffers, copies inside the timed region ----
+    pin = lambda shape: torch.empty(shape, dtype=tdt).pin_memory().numpy()
+    h_rec = pin((B, R, 44))
+    h_rec[...] = rec_h
+    out = {"avg_vel": pin((B, R)), "x_ee": pin((B, R, 3)), "goal_est": pin((B, 3))}
+    for _ in range(3):
+        fab.rollout_host(h_rec, H, dtype=a.dtype, out=out)
+    if world > 1:
+        dist.barrier()
+    t_e2e = []
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(e2e_steps):
+        t0 = time.perf_counter()
+        fab.rollout_host(h_rec, H, dtype=a.dtype, out=out)          # synchronous: returns after the D2H copies
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_total = torch.tensor([sum(t_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * R * H * e2e_steps / float(e2e_total.item())
+    h2d = int(h_rec.nbytes)
+    d2h = int(sum(v.nbytes for v in out.values()))
+
+    # parity spot-check of what was timed (oracle as the checker; not timed)
+    if rank == 0:
+        from oracle import o2
+        idx = np.arange(0, min(B, 4096), 257)
+        ocfg = o2.default_config(R)
+        rec_o = base[idx].copy()
+        for k in range(len(idx)):
+            x, v = o2.endeffector(ocfg, 1, rec_o[k, 1, 0:7], rec_o[k, 1, 7:14])
+            rec_o[k, 1, o2.G0:o2.G0 + 3] = x + 0.2 * v
+        ravg, _ = o2.rollout_jointspace_avg(ocfg, rec_o, H)
+        got = avg[:, torch.from_numpy(idx).to(dev)].T.double().cpu().numpy()
+        okm = np.isfinite(ravg).all(axis=1) & (ravg.max(axis=1) < 2.0)
+        parity_err = float(np.abs(got - ravg)[okm].max())
+    else:
+        parity_err = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline ----
+    peak = peak32 if a.dtype == "f32" else peak64
+    rs_kernel = B * R * H / (kernel_ms * 1e-3)                       # one GPU, dominant kernel alone
+    achieved_tf = rs_kernel * FLOPS_PER_ROBOT_STEP / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_file):
+        hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    esz = 4 if a.dtype == "f32" else 8
+    alg_bytes = B * (R * 43 * esz + (R + 3 * R + 3) * esz)        # records in, avg_vel + x_ee + goal_est out
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tfile):
+        traffic = json.load(open(tfile)).get(f"rollout_{a.dtype}_bytes_per_launch")
+    roofline = {"bound": "fp32" if a.dtype == "f32" else "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak, "traffic": traffic,
+                "kernel": f"rollout_kernel<{'float' if a.dtype == 'f32' else 'double'}>",
+                "kernel_ms": kernel_ms, "flops_per_robot_step": FLOPS_PER_ROBOT_STEP,
+                "peak_source": "FMA micro-benchmark (mrf_fma_peak) measured in this run; MEASURED_PEAKS.json has no "
+                               "FP32/FP64 CUDA-core figure",
+                "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "peak_source": hbm_src},
+                "fp64_peak_tflops": peak64, "fp32_peak_tflops": peak32}
+
+    # ---- single-rollout latency (3 Pandas, H = 20, one scenario, device-resident) ----
+    one = torch.from_numpy(to_soa(base[:1].astype(ndt))).to(dev)
+    a1 = torch.empty((R, 1), dtype=tdt, device=dev)
+    for _ in range(10):
+        fab.rollout_dev(one, 20, avg_vel=a1)
+    torch.cuda.synchronize()
+    lat = []
+    for _ in range(50):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fab.rollout_dev(one, 20, avg_vel=a1)
+        e1.record()
+        torch.cuda.synchronize()
+        lat.append(e0.elapsed_time(e1) * 1e3)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        fab.rollout_dev(one, 20, avg_vel=a1)
+    torch.cuda.synchronize()
+    lat_wall = (time.perf_counter() - t0) / 200 * 1e6
+
+    cpu = None
+    if not a.no_cpu:
+        cpu, _, _ = cpu_sample(H, a.cpu_seconds)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic", "config": config_dict(a),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timing": "host wall clock around the synchronous mrf_rollout_host call, max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "single_rollout_us": {"device_events_median": statistics.median(lat), "wall_back_to_back": lat_wall,
+                                  "shape": "1 scenario x 3 Pandas x H20"},
+            "parity_spot_check_max_abs_err_avg_vel": parity_err}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_arm(a)
+    return ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,12 +35,13 @@ namespace mrf {
 // ------------------------------------------------------------------------------------------------
 // coupled joint-space rollout
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kTile* MRF_MAX_ROBOTS)
+template <typename T, int R>
+__global__ void __launch_bounds__(kTile* R)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = blockDim.x, tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile, R = cfg.n_robots;
+    constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
+    const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
     T* kin = reinterpret_cast<T*>(smem_raw);
     T* prm = kin + kKin * NT;
     const long long b = (long long)blockIdx.x * kTile + lane;
@@ -523,11 +524,23 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
     const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * NT;
-    int rc = set_smem(rollout_kernel<T>, smem);
-    if (rc) return rc;
     const long long grid = (B + kTile - 1) / kTile;
-    rollout_kernel<T><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est,
-                                                                         qN, qdN, (long long)B);
+    int rc = MRF_OK;
+#define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
+    case RR:                                                                                                         \
+        rc = set_smem(rollout_kernel<T, RR>, smem);                                                                  \
+        if (rc) return rc;                                                                                           \
+        rollout_kernel<T, RR><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, \
+                                                                                 goal_est, qN, qdN, (long long)B);   \
+        break;
+    switch (R) {
+        MRF_LAUNCH_ROLLOUT(1)
+        MRF_LAUNCH_ROLLOUT(2)
+        MRF_LAUNCH_ROLLOUT(3)
+        MRF_LAUNCH_ROLLOUT(4)
+        default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
+    }
+#undef MRF_LAUNCH_ROLLOUT
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;

@@ -31,18 +31,22 @@ template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) 
         d.link1[r][0] = (T)(M[3] + R[2] * 0.333);
         d.link1[r][1] = (T)(M[7] + R[5] * 0.333);
         d.link1[r][2] = (T)(M[11] + R[8] * 0.333);
-        // sphere table: links (1,2) -> point 5, 3 -> 0, 4 -> 1, (5,6) -> 2, 7 -> 3, 8 -> 4
+    }
+    // sphere table of robot r: links of every other robot j (ascending), (1,2) -> point 5, 3 -> 0, 4 -> 1,
+    // (5,6) -> 2, 7 -> 3, 8 -> 4
+    for (int r = 0; r < c.n_robots; ++r) {
         const int src_of[8] = {5, 5, 0, 1, 2, 2, 3, 4};
         int n = 0;
-        for (int l = 0; l < 8; ++l) {
-            bool merged = false;
-            if ((l == 1 || l == 5) && c.r_robots[r][l] == c.r_robots[r][l - 1]) {
-                d.ent_w[r][n - 1] = (T)2; // same point, same radius as the previous link: one entry, weight 2
-                merged = true;
-            }
-            if (!merged) {
+        for (int j = 0; j < c.n_robots; ++j) {
+            if (j == r) continue;
+            for (int l = 0; l < 8; ++l) {
+                if ((l == 1 || l == 5) && c.r_robots[j][l] == c.r_robots[j][l - 1]) {
+                    d.ent_w[r][n - 1] = (T)2; // same point and radius as the previous link: one entry, weight 2
+                    continue;
+                }
+                d.ent_rob[r][n] = j;
                 d.ent_src[r][n] = src_of[l];
-                d.ent_rad[r][n] = (T)c.r_robots[r][l];
+                d.ent_rad[r][n] = (T)c.r_robots[j][l];
                 d.ent_w[r][n] = (T)1;
                 ++n;
             }

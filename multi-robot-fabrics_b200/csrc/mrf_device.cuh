@@ -33,8 +33,9 @@ template <int N> struct Int {
 
 constexpr int kDof = 7;
 constexpr int kEgo = 5;        // distinct moving link points: link3, link4, link5(==link6), link7, link8
-constexpr int kKin = kEgo * 9; // x, v, c per point
-constexpr int kMaxEnt = 8;     // obstacle entries per other robot
+constexpr int kPts = kEgo + 1; // + the constant point link1 == link2 (slot 5), so readers need no special case
+constexpr int kKin = kPts * 9; // x, v, c per point
+constexpr int kMaxEnt = 8 * (MRF_MAX_ROBOTS - 1); // sphere entries one robot sees (all links of all other robots)
 // parameter block (per thread, shared memory)
 enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P_NH = 19, P_DN = 22, P_RB = 23, P_N = 29 };
 
@@ -44,14 +45,26 @@ enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P
 template <typename T> struct Mth;
 template <> struct Mth<float> {
     static MRF_HD float sqrt(float x) { return ::sqrtf(x); }
+    // FP32 throughput path: single MUFU.RSQ / MUFU.RCP (2^-22 relative error, below the FP32 rounding that the
+    // stated FP32 tolerance already covers); an IEEE 1.0f/x costs ~8 extra instructions and was 20 % of all stalls
     static MRF_HD float rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-        return ::rsqrtf(x);
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
 #else
         return 1.0f / ::sqrtf(x);
 #endif
     }
-    static MRF_HD float rcp(float x) { return 1.0f / x; }
+    static MRF_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+#else
+        return 1.0f / x;
+#endif
+    }
     static MRF_HD float exp(float x) { return ::expf(x); }
     static MRF_HD float tanh(float x) { return ::tanhf(x); }
     static MRF_HD void sincos(float x, float* s, float* c) {
@@ -111,9 +124,11 @@ template <typename T> struct DevCfg {
     T p0[MRF_MAX_ROBOTS][3];   // mount translation
     T link1[MRF_MAX_ROBOTS][3]; // constant origin of panda_link1 == panda_link2
     T lim[kDof][2];
-    // other-robot sphere table: distinct points with multiplicity (link1==link2, link5==link6 share a point;
-    // merged into one entry of weight 2 when their radii agree).  src 0..4 = moving point, 5 = link1.
+    // spheres robot r sees in a coupled rollout, flattened over the other robots (ascending) and their distinct
+    // points with multiplicity: link1==link2 and link5==link6 share a point and are merged into one entry of weight
+    // 2 when their radii agree.  ent_off = kinematics-table offset (point * 9 * NT + other_robot * 32).
     int ent_n[MRF_MAX_ROBOTS];
+    int ent_rob[MRF_MAX_ROBOTS][kMaxEnt];
     int ent_src[MRF_MAX_ROBOTS][kMaxEnt];
     T ent_rad[MRF_MAX_ROBOTS][kMaxEnt];
     T ent_w[MRF_MAX_ROBOTS][kMaxEnt];
@@ -184,6 +199,7 @@ MRF_HD void chain_forward(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     f.p = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]); // p0 + R0 (0,0,0.333): base is fixed
     f.w = mk(T(0), T(0), T(0));
     f.al = f.w; f.v = f.w; f.ac = f.w;
+    kin_store(kin, NT, tid, 5, f);                                   // link1 == link2 (constant, v = c = 0)
     ch.z[0] = fr_joint<T, 0>(f, q[0], qd[0]);                       // joint1
     ch.z[1] = fr_joint<T, -1>(f, q[1], qd[1]);                      // joint2 (zero offset)
     fr_advance(f, f.b * T(-0.316));                                  // joint3 origin (0,-0.316,0)
@@ -235,28 +251,29 @@ MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> ao
     T n2 = dot(d, d);
     T inv_n = Mth<T>::rsqrt(n2);
     T n = n2 * inv_n;
-    T inv_rho = Mth<T>::rcp(rho);
-    T x = n * inv_rho - T(1);
-    T gs = inv_n * inv_rho;              // g = d * gs  (gradient of x w.r.t. the point)
+    // x = n/rho - 1.  One reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) (gradient scale) and 1/x.
+    T t = n - rho;
+    T nr = n * rho;
+    T u = Mth<T>::rcp(nr * t);
+    T gs = u * t;                        // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
+    T ix = u * nr * rho;                 // 1/x = rho/(n - rho)
     T dw = dot(d, w);
     T xd = dw * gs;
-    T kappa = (dot(w, w) - dw * dw * inv_n * inv_n) * gs;
-    T ix = Mth<T>::rcp(x);
     T ix2 = ix * ix, ix4 = ix2 * ix2;
     T xd2 = xd * xd;
     T Ml = T(0.02) * ix4 * wt;           // d2L/dxdot2
-    T fl = Ml * (T(-0.5) * xd2 * ix4);   // M h
-    T fel = T(-0.04) * xd2 * ix4 * ix * wt;
-    T curv = kappa + dot(d, cc) * gs;
+    T hx = xd2 * ix4;
+    T fl = Ml * (T(-0.5) * hx);          // M h
+    T fel = T(-0.04) * hx * ix * wt;
+    T curv = (dot(w, w) - dw * dw * (inv_n * inv_n) + dot(d, cc)) * gs;   // kappa + g.c
     T ga = dot(d, ao) * gs;
     T gv = dot(d, v) * gs;
     T fq = fl + Ml * (sigma * curv - ga);
     num += gv * ((fl - fel) + Ml * (sigma - T(1)) * curv);
-    V3<T> g = d * gs;
-    V3<T> Mg = g * Ml;
-    acc.A.xx += Mg.x * g.x; acc.A.xy += Mg.x * g.y; acc.A.xz += Mg.x * g.z;
-    acc.A.yy += Mg.y * g.y; acc.A.yz += Mg.y * g.z; acc.A.zz += Mg.z * g.z;
-    acc.b = acc.b + g * fq;
+    V3<T> Md = d * (Ml * gs * gs);
+    acc.A.xx += Md.x * d.x; acc.A.xy += Md.x * d.y; acc.A.xz += Md.x * d.z;
+    acc.A.yy += Md.y * d.y; acc.A.yz += Md.y * d.z; acc.A.zz += Md.z * d.z;
+    acc.b = acc.b + d * (gs * fq);
 }
 
 // Plane leaf (geometry_plane_constraint "10*(1/(1+exp(-10x))-1) xdot^2", example_pandas_Jointspace.py:87;
@@ -389,12 +406,15 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     org[4] = kin_load(kin, NT, tid, 2, 0);
     org[5] = org[4];
 
-    // ---- collision leaves per distinct ego point ----
+    // ---- collision leaves per distinct ego point (runtime loop: one copy of the leaf code keeps the kernel
+    //      inside the instruction cache; the column count K of each point is warp-uniform) ----
     if (cfg.has_coll) {
         const V3<T> nh = mk(prm[(P_NH + 0) * NT + tid], prm[(P_NH + 1) * NT + tid], prm[(P_NH + 2) * NT + tid]);
         const T dn = prm[P_DN * NT + tid];
-        auto point = [&](auto kc, int e, int rb_first, int n_links) {
-            constexpr int K = decltype(kc)::value;
+#pragma unroll 1
+        for (int e = 0; e < kEgo; ++e) {
+            const int K = e < 3 ? e + 2 : 6;           // link3: 2, link4: 3, link5/6: 4, link7: 6, link8: 6 joints
+            const int rb_first = e + (e > 2 ? 1 : 0);  // index into radius_body_panda_link3..8
             V3<T> p = kin_load(kin, NT, tid, e, 0), v = kin_load(kin, NT, tid, e, 3), cc = kin_load(kin, NT, tid, e, 6);
             PointAcc<T> acc;
             acc.A = Sym3<T>{T(0), T(0), T(0), T(0), T(0), T(0)};
@@ -402,7 +422,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             T rb = prm[(P_RB + rb_first) * NT + tid];
             T we = T(1);
             int passes = 1;
-            if (n_links == 2) { // link5 and link6 share the point; identical leaves if their radii agree
+            if (e == 2) { // link5 and link6 share the point; identical leaves if their radii agree
                 T rb2 = prm[(P_RB + rb_first + 1) * NT + tid];
                 if (rb2 == rb) we = T(2); else passes = 2;
             }
@@ -413,15 +433,20 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 });
                 plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
             }
-            V3<T> Jc[K];
-            jac_cols<T, K>(ch, p, org, Jc);
-            pullback<T, K>(Jc, acc, G);
-        };
-        point(Int<2>{}, 0, 0, 1); // link3
-        point(Int<3>{}, 1, 1, 1); // link4
-        point(Int<4>{}, 2, 2, 2); // link5 + link6
-        point(Int<6>{}, 3, 4, 1); // link7
-        point(Int<6>{}, 4, 5, 1); // link8
+            V3<T> Jc[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (j < K) Jc[j] = cross(ch.z[j], p - org[j]);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                if (j < K) {
+                    V3<T> AJ = symmul(acc.A, Jc[j]);
+                    G.f[j] += dot(Jc[j], acc.b);
+#pragma unroll
+                    for (int i = 0; i <= j; ++i) G.M[i][j] += dot(Jc[i], AJ);
+                }
+            }
+        }
     }
 
     // ---- q^T M_g q ----
@@ -519,24 +544,14 @@ template <typename T> struct SmemSrc {
     int NT, lane, r;
     T vref, aref;
     template <typename F> MRF_HD void each(F f) const {
-        for (int j = 0; j < cfg.n_robots; ++j) {
-            if (j == r) continue;
-            const int ot = j * kTile + lane;
-            const int ne = cfg.ent_n[j];
-            for (int k = 0; k < ne; ++k) {
-                const int s = cfg.ent_src[j][k];
-                V3<T> xo, vo, ao;
-                if (s < kEgo) {
-                    xo = kin_load(kin, NT, ot, s, 0);
-                    vo = kin_load(kin, NT, ot, s, 3) * vref;
-                    ao = kin_load(kin, NT, ot, s, 6) * aref;
-                } else {
-                    xo = mk(cfg.link1[j][0], cfg.link1[j][1], cfg.link1[j][2]);
-                    vo = mk(T(0), T(0), T(0));
-                    ao = vo;
-                }
-                f(xo, vo, ao, cfg.ent_rad[j][k], cfg.ent_w[j][k]);
-            }
+        const int ne = cfg.ent_n[r];
+#pragma unroll 2
+        for (int k = 0; k < ne; ++k) {
+            const T* b = kin + cfg.ent_src[r][k] * 9 * NT + cfg.ent_rob[r][k] * kTile + lane;
+            V3<T> xo = mk(b[0], b[NT], b[2 * NT]);
+            V3<T> vo = mk(b[3 * NT], b[4 * NT], b[5 * NT]) * vref;
+            V3<T> ao = mk(b[6 * NT], b[7 * NT], b[8 * NT]) * aref;
+            f(xo, vo, ao, cfg.ent_rad[r][k], cfg.ent_w[r][k]);
         }
     }
 };
@@ -548,6 +563,7 @@ template <typename T, bool CART> struct GlobalSrc {
     int S;
     T tk;
     template <typename F> MRF_HD void each(F f) const {
+#pragma unroll 2
         for (int o = 0; o < S; ++o) {
             const T* b = obst + (long long)o * MRF_OBST * stride + off;
             V3<T> xo = mk(b[0], b[stride], b[2 * stride]);

@@ -328,8 +328,12 @@ static int action_from_kin(const mrfo_config* c, const kin_t* k, const double* r
     /* energisation + speed-control damper */
     const double e = c->eps;
     double hg[DOF], hf[DOF];
-    if (cholesky_solve(g.M, e, g.f, hg)) return 1;
-    if (cholesky_solve(Mf, e, ff, hf)) return 1;
+    if (cholesky_solve(g.M, e, g.f, hg) || cholesky_solve(Mf, e, ff, hf)) {
+        /* metric not positive definite (a joint beyond its limit makes the limit-leaf metric 0.2 s/x negative): the
+         * reference's symbolic inverse would return garbage here; flag it as NaN so callers can drop the scenario */
+        for (int a = 0; a < DOF; a++) action[a] = NAN;
+        return 1;
+    }
     double num = 0, qMq = 0, qq = 0, qhg = 0, qhf = 0;
     for (int a = 0; a < DOF; a++) {
         num += qd[a] * (g.f[a] - g.fe[a]);

@@ -117,9 +117,8 @@ def rollout_jointspace(cfg, rec, N, n_threads=0):
     B = rec3.shape[0]
     qN, qdN = np.zeros((B, R, N, 7)), np.zeros((B, R, N, 7))
     avg, xee = np.zeros((B, R)), np.zeros((B, R, 3))
-    rc = lib().mrfo_rollout_jointspace_batch(C.byref(cfg), _p(rec3), B, N, _p(qN), _p(qdN), _p(avg), _p(xee), n_threads)
-    if rc:
-        raise FloatingPointError("oracle: Cholesky failed")
+    lib().mrfo_rollout_jointspace_batch(C.byref(cfg), _p(rec3), B, N, _p(qN), _p(qdN), _p(avg), _p(xee), n_threads)
+    # scenarios whose metric lost positive definiteness come back as NaN (see mrf_oracle.c)
     if single:
         return qN[0], qdN[0], avg[0], xee[0]
     return qN, qdN, avg, xee
@@ -132,9 +131,7 @@ def rollout_jointspace_avg(cfg, rec, N, n_threads=0):
     rec3 = rec.reshape(-1, R, ROBOT_IN)
     B = rec3.shape[0]
     avg, xee = np.zeros((B, R)), np.zeros((B, R, 3))
-    rc = lib().mrfo_rollout_jointspace_batch(C.byref(cfg), _p(rec3), B, N, None, None, _p(avg), _p(xee), n_threads)
-    if rc:
-        raise FloatingPointError("oracle: Cholesky failed")
+    lib().mrfo_rollout_jointspace_batch(C.byref(cfg), _p(rec3), B, N, None, None, _p(avg), _p(xee), n_threads)
     return avg, xee
 
 
@@ -142,10 +139,8 @@ def rollout_cartesian(cfg, robot, rec, xo, vo, ro, N):
     rec = _c(rec)
     xo, vo, ro = _c(xo).reshape(-1, 3), _c(vo).reshape(-1, 3), _c(ro).reshape(-1)
     qN, qdN, avg = np.zeros((N, 7)), np.zeros((N, 7)), np.zeros(1)
-    rc = lib().mrfo_rollout_cartesian(C.byref(cfg), robot, _p(rec), ro.shape[0], _p(xo), _p(vo), _p(ro), N, _p(qN),
-                                      _p(qdN), _p(avg))
-    if rc:
-        raise FloatingPointError("oracle: rollout failed")
+    lib().mrfo_rollout_cartesian(C.byref(cfg), robot, _p(rec), ro.shape[0], _p(xo), _p(vo), _p(ro), N, _p(qN),
+                                 _p(qdN), _p(avg))
     return qN, qdN, float(avg[0])
 
 

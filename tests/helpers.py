@@ -26,10 +26,17 @@ def oracle_rollout(rec, R, N, estimate_goal=0, static_or_dyn=1):
     return qN, qdN, avg, xee, goal, ok
 
 
-def random_obstacles(rng, B, n_rob, S):
-    """Spheres placed away from the arms' workspace shell so the leaves stay well conditioned."""
+def random_obstacles(rng, B, n_rob, S, rec=None, robot_first=0):
+    """Random spheres; with `rec` (B,n_rob,44) those closer than a normalised clearance of 0.5 to any link of the ego
+    robot are pushed up out of the workspace so the leaves stay well conditioned (0.02/x^4 metric)."""
     obst = np.zeros((B, n_rob, S, 10))
     obst[..., 0:3] = rng.uniform([-0.6, -1.2, 0.9], [1.6, 1.2, 2.0], size=(B, n_rob, S, 3))
+    if rec is not None and S > 0:
+        from multi_robot_fabrics_b200 import scenarios as sc
+        for r in range(n_rob):
+            pos = sc.link_positions(rec[:, r, 0:7], sc.mount_matrix(robot_first + r))          # B,8,3
+            d = np.linalg.norm(obst[:, r, :, None, 0:3] - pos[:, None, :, :], axis=-1).min(axis=-1)   # B,S
+            obst[:, r, :, 2] += np.where(d / 0.16 - 1.0 < 0.5, 1.5, 0.0)
     obst[..., 3:6] = rng.uniform(-0.3, 0.3, size=(B, n_rob, S, 3))
     obst[..., 6:9] = rng.uniform(-0.5, 0.5, size=(B, n_rob, S, 3))
     obst[..., 9] = 0.08

@@ -78,7 +78,7 @@ def test_action_matches_oracle(fabs, n_rob, S):
     rng = np.random.default_rng(S + n_rob)
     R = max(2, n_rob)
     rec = m.scenarios.generate(B, R, seed=11, weight_goal_1=20.0)[:, :n_rob]
-    obst = random_obstacles(rng, B, n_rob, S)
+    obst = random_obstacles(rng, B, n_rob, S, rec)
     fab = get_fab(fabs, R)
     act = fab.action_host(rec, obst if S else None, robot_first=0, dtype="f64")
     ref = oracle_actions(rec, obst)
@@ -94,7 +94,7 @@ def test_action_acc_mode_and_grasp_planner(fabs):
     B = 20
     rng = np.random.default_rng(5)
     rec = m.scenarios.generate(B, 2, seed=12)
-    obst = random_obstacles(rng, B, 2, 4)
+    obst = random_obstacles(rng, B, 2, 4, rec)
     for kw in (dict(mode=0), dict(has_collision_links=0)):
         fab = get_fab(fabs, 2, **kw)
         act = fab.action_host(rec, obst, dtype="f64")
@@ -106,7 +106,7 @@ def test_cartesian_rollout_matches_oracle(fabs):
     B, N, S = 24, 20, 16
     rng = np.random.default_rng(9)
     rec = m.scenarios.generate(B, 2, seed=13, weight_goal_1=20.0)
-    obst = random_obstacles(rng, B, 1, S)[:, 0]
+    obst = random_obstacles(rng, B, 1, S, rec[:, :1] if rec.ndim == 3 else rec[:, None])[:, 0]
     fab = get_fab(fabs, 2)
     ocfg = o2.default_config(2)
     for robot in (0, 1):

@@ -123,7 +123,7 @@ def test_emulated_kernel_action_matches_oracle(emul, kw):
     B, S = 24, 7
     rng = np.random.default_rng(2)
     rec = m.scenarios.generate(B, 2, seed=31, weight_goal_1=20.0)
-    obst = random_obstacles(rng, B, 2, S)
+    obst = random_obstacles(rng, B, 2, S, rec)
     cfg = _lib.default_config(2, **kw)
     ref = oracle_actions(rec, obst, **kw)
     for robot in (0, 1):
@@ -137,7 +137,7 @@ def test_emulated_kernel_cartesian_rollout(emul):
     B, S, N = 6, 5, 10
     rng = np.random.default_rng(4)
     rec = m.scenarios.generate(B, 2, seed=41, weight_goal_1=20.0)[:, 0]
-    obst = random_obstacles(rng, B, 1, S)[:, 0]
+    obst = random_obstacles(rng, B, 1, S, rec[:, :1] if rec.ndim == 3 else rec[:, None])[:, 0]
     cfg, ocfg = _lib.default_config(2), o2.default_config(2)
     avg, qN, qdN = np.zeros(B), np.zeros((B, N, 7)), np.zeros((B, N, 7))
     emul.emul_cart_f64(C.byref(cfg), 0, _dp(np.ascontiguousarray(rec)), S, _dp(np.ascontiguousarray(obst)), N, _dp(avg),
