@@ -35,7 +35,7 @@ namespace mrf {
 // ------------------------------------------------------------------------------------------------
 // coupled joint-space rollout
 // ------------------------------------------------------------------------------------------------
-template <typename T, int R>
+template <typename T, int R, bool UNIFORM>
 __global__ void __launch_bounds__(kTile* R)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B) {
@@ -57,48 +57,57 @@ __global__ void __launch_bounds__(kTile* R)
     }
     load_params<T>(ld, prm, NT, tid);
     Chain<T> ch;
-
-    if (x_ee != nullptr || goal_est != nullptr || cfg.estimate_goal) {
-        // end-effector FK at the measured state (example_pandas_Jointspace.py:236-238,328-329) and the RF-CV
-        // constant-velocity goal estimate of one robot (:346-348)
-        chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
-        V3<T> p8 = kin_load(kin, NT, tid, 4, 0);
-        if (x_ee != nullptr && live) {
-            x_ee[((long long)r * 3 + 0) * B + b] = p8.x;
-            x_ee[((long long)r * 3 + 1) * B + b] = p8.y;
-            x_ee[((long long)r * 3 + 2) * B + b] = p8.z;
-        }
-        if (r == cfg.estimate_robot) {
-            V3<T> g = mk(prm[(P_G0 + 0) * NT + tid], prm[(P_G0 + 1) * NT + tid], prm[(P_G0 + 2) * NT + tid]);
-            if (cfg.estimate_goal) {
-                V3<T> l1 = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
-                // mode 1: first COLUMN of the hand Jacobian (the reference's "v_ee"); mode 2: J qdot
-                V3<T> v = cfg.estimate_goal == 1 ? cross(ch.z[0], p8 - l1) : kin_load(kin, NT, tid, 4, 3);
-                g = p8 + v * cfg.est_h;
-                prm[(P_G0 + 0) * NT + tid] = g.x;
-                prm[(P_G0 + 1) * NT + tid] = g.y;
-                prm[(P_G0 + 2) * NT + tid] = g.z;
-            }
-            if (goal_est != nullptr && live) {
-                goal_est[0 * B + b] = g.x;
-                goal_est[1 * B + b] = g.y;
-                goal_est[2 * B + b] = g.z;
-            }
-        }
-    }
-
-    SmemSrc<T> src{cfg, kin, NT, lane, r, cfg.static_or_dyn ? T(1) : T(0), cfg.static_or_dyn ? cfg.sref : T(0)};
+    const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
     T acc = T(0);
-    for (int k = 0; k < N; ++k) {
+    // k = -1: FK at the measured state only (end-effector position, RF-CV goal estimate); k >= 0: horizon steps.
+    // One loop body keeps a single copy of chain_forward in the instruction stream.
+    const bool want_pre = x_ee != nullptr || goal_est != nullptr || cfg.estimate_goal != 0;
+    for (int k = want_pre ? -1 : 0; k < N; ++k) {
         // Phase A (forward_planner_Jointspace.py:191-209): step with the stale velocity, then FK
+        if (k >= 0) {
 #pragma unroll
-        for (int i = 0; i < kDof; ++i) q[i] += cfg.dt * qd[i];
+            for (int i = 0; i < kDof; ++i) q[i] += cfg.dt * qd[i];
+        }
         __syncthreads(); // readers of the previous step are done
         chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
+        if (k < 0) {
+            // end-effector FK at the measured state (example_pandas_Jointspace.py:236-238,328-329) and the RF-CV
+            // constant-velocity goal estimate of one robot (:346-348)
+            V3<T> p8 = kin_load(kin, NT, tid, 4, 0);
+            if (x_ee != nullptr && live) {
+                x_ee[((long long)r * 3 + 0) * B + b] = p8.x;
+                x_ee[((long long)r * 3 + 1) * B + b] = p8.y;
+                x_ee[((long long)r * 3 + 2) * B + b] = p8.z;
+            }
+            if (r == cfg.estimate_robot) {
+                V3<T> g = mk(prm[(P_G0 + 0) * NT + tid], prm[(P_G0 + 1) * NT + tid], prm[(P_G0 + 2) * NT + tid]);
+                if (cfg.estimate_goal) {
+                    V3<T> l1 = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
+                    // mode 1: first COLUMN of the hand Jacobian (the reference's "v_ee"); mode 2: J qdot
+                    V3<T> v = cfg.estimate_goal == 1 ? cross(ch.z[0], p8 - l1) : kin_load(kin, NT, tid, 4, 3);
+                    g = p8 + v * cfg.est_h;
+                    prm[(P_G0 + 0) * NT + tid] = g.x;
+                    prm[(P_G0 + 1) * NT + tid] = g.y;
+                    prm[(P_G0 + 2) * NT + tid] = g.z;
+                }
+                if (goal_est != nullptr && live) {
+                    goal_est[0 * B + b] = g.x;
+                    goal_est[1 * B + b] = g.y;
+                    goal_est[2 * B + b] = g.z;
+                }
+            }
+            continue;
+        }
         __syncthreads(); // every robot of the tile has published
         // Phase B (:211-249): action against the other robots' published spheres
         T act[kDof];
-        fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+        if (UNIFORM) {
+            SmemSrcUniform<T, R> src{kin, lane, r, vref, aref, cfg.r_obst};
+            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+        } else {
+            SmemSrc<T> src{cfg, kin, NT, lane, r, vref, aref};
+            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+        }
 #pragma unroll
         for (int i = 0; i < kDof; ++i) {
             qd[i] = act[i];
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(kActThreads)
     }
     load_params<T>(ld, prm, NT, tid);
     Chain<T> ch;
-    GlobalSrc<T, CART> src{obst, stride, idx, S, T(0)};
+    GlobalSrc<T, CART> src{obst, stride, idx, S, T(0), T(1), T(1)};
     if (!CART) {
         T act[kDof];
         chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
@@ -466,9 +475,11 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     if (cfg->estimate_goal && (cfg->estimate_robot < 0 || cfg->estimate_robot >= cfg->n_robots))
         return fail(MRF_EINVAL, "mrf_create: estimate_robot out of range");
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
         cudaGetLastError();
-        return fail(MRF_ENODEV, "mrf_create: no CUDA device (this library has no CPU fallback)");
+        return fail(MRF_ENODEV, std::string("mrf_create: no CUDA device (this library has no CPU fallback): ") +
+                                    (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
     }
     if (device < 0 || device >= n) return fail(MRF_EINVAL, "mrf_create: bad device index");
     MRF_CUDA(cudaSetDevice(device));
@@ -528,10 +539,17 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     int rc = MRF_OK;
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
-        rc = set_smem(rollout_kernel<T, RR>, smem);                                                                  \
-        if (rc) return rc;                                                                                           \
-        rollout_kernel<T, RR><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, \
-                                                                                 goal_est, qN, qdN, (long long)B);   \
+        if (devcfg<T>(h).uniform_obst) {                                                                             \
+            rc = set_smem(rollout_kernel<T, RR, true>, smem);                                                        \
+            if (rc) return rc;                                                                                       \
+            rollout_kernel<T, RR, true><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                         \
+                devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B);                               \
+        } else {                                                                                                     \
+            rc = set_smem(rollout_kernel<T, RR, false>, smem);                                                       \
+            if (rc) return rc;                                                                                       \
+            rollout_kernel<T, RR, false><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                        \
+                devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B);                               \
+        }                                                                                                            \
         break;
     switch (R) {
         MRF_LAUNCH_ROLLOUT(1)

@@ -32,6 +32,11 @@ template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) 
         d.link1[r][1] = (T)(M[7] + R[5] * 0.333);
         d.link1[r][2] = (T)(M[11] + R[8] * 0.333);
     }
+    d.uniform_obst = 1;
+    d.r_obst = (T)c.r_robots[0][0];
+    for (int r = 0; r < c.n_robots; ++r)
+        for (int l = 0; l < 8; ++l)
+            if (c.r_robots[r][l] != c.r_robots[0][0]) d.uniform_obst = 0;
     // sphere table of robot r: links of every other robot j (ascending), (1,2) -> point 5, 3 -> 0, 4 -> 1,
     // (5,6) -> 2, 7 -> 3, 8 -> 4
     for (int r = 0; r < c.n_robots; ++r) {

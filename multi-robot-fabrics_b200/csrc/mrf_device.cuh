@@ -67,13 +67,22 @@ template <> struct Mth<float> {
     }
     static MRF_HD float exp(float x) { return ::expf(x); }
     static MRF_HD float tanh(float x) { return ::tanhf(x); }
+    // Joint angles are bounded by the Panda limits (|q| < 3.8 rad): Cody-Waite reduction by pi/2 and degree-7/8
+    // minimax polynomials on [-pi/4, pi/4] (~1e-7 abs error) in ~22 instructions, without the argument-reduction slow
+    // path that ::sincosf drags into every call site (it was 2 % of instructions and much more of the code size).
     static MRF_HD void sincos(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-        ::sincosf(x, s, c);
-#else
-        *s = ::sinf(x);
-        *c = ::cosf(x);
-#endif
+        float k = ::rintf(x * 0.636619772f);
+        float r = ::fmaf(k, -1.57079601e+00f, x);
+        r = ::fmaf(k, -3.13916473e-07f, r);
+        r = ::fmaf(k, -5.39030253e-15f, r);
+        float r2 = r * r;
+        float sp = ::fmaf(::fmaf(::fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+        float cp = ::fmaf(::fmaf(::fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f),
+                          r2 * r2, ::fmaf(-0.5f, r2, 1.0f));
+        int q = (int)k;
+        float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+        *s = (q & 2) ? -ss : ss;
+        *c = ((q + 1) & 2) ? -cc : cc;
     }
     static MRF_HD float abs(float x) { return ::fabsf(x); }
     static MRF_HD float max(float a, float b) { return ::fmaxf(a, b); }
@@ -127,6 +136,8 @@ template <typename T> struct DevCfg {
     // spheres robot r sees in a coupled rollout, flattened over the other robots (ascending) and their distinct
     // points with multiplicity: link1==link2 and link5==link6 share a point and are merged into one entry of weight
     // 2 when their radii agree.  ent_off = kinematics-table offset (point * 9 * NT + other_robot * 32).
+    int uniform_obst;           // every r_robots[j][l] equal -> SmemSrcUniform fast path with radius r_obst
+    T r_obst;
     int ent_n[MRF_MAX_ROBOTS];
     int ent_rob[MRF_MAX_ROBOTS][kMaxEnt];
     int ent_src[MRF_MAX_ROBOTS][kMaxEnt];
@@ -245,32 +256,32 @@ template <typename T> struct Spec {
 // examples/example_pandas_Jointspace.py:88-89) of ego point (p, v, c) against sphere (xo, vo, ao), in the
 // point's task space.  wt = multiplicity of identical leaves.
 template <typename T>
-MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> ao, T rho, T wt, T sigma,
-                        PointAcc<T>& acc, T& num) {
-    V3<T> d = p - xo, w = v - vo;
+MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> co, T vref, T aref, T rho, T wt,
+                        T sigma, PointAcc<T>& acc, T& num) {
+    // obstacle velocity = vref * vo, obstacle acceleration = aref * co (the scalars are applied to dot products)
+    V3<T> d = p - xo;
+    V3<T> w = mk(v.x - vref * vo.x, v.y - vref * vo.y, v.z - vref * vo.z);
     T n2 = dot(d, d);
-    T inv_n = Mth<T>::rsqrt(n2);
-    T n = n2 * inv_n;
+    T in1 = Mth<T>::rsqrt(n2);
+    T n = n2 * in1;
     // x = n/rho - 1.  One reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) (gradient scale) and 1/x.
     T t = n - rho;
     T nr = n * rho;
     T u = Mth<T>::rcp(nr * t);
     T gs = u * t;                        // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
-    T ix = u * nr * rho;                 // 1/x = rho/(n - rho)
-    T dw = dot(d, w);
+    T ix = (u * nr) * rho;               // 1/x = rho/(n - rho)
+    T dw = dot(d, w), dc = dot(d, cc), da = dot(d, co), dv = dot(d, v), ww = dot(w, w);
+    T inner = (ww - (dw * dw) * (in1 * in1)) + dc;   // (kappa + g.c) / gs
     T xd = dw * gs;
     T ix2 = ix * ix, ix4 = ix2 * ix2;
-    T xd2 = xd * xd;
-    T Ml = T(0.02) * ix4 * wt;           // d2L/dxdot2
-    T hx = xd2 * ix4;
+    T hx = (xd * xd) * ix4;
+    T Ml = (T(0.02) * wt) * ix4;         // d2L/dxdot2 (x multiplicity)
     T fl = Ml * (T(-0.5) * hx);          // M h
-    T fel = T(-0.04) * hx * ix * wt;
-    T curv = (dot(w, w) - dw * dw * (inv_n * inv_n) + dot(d, cc)) * gs;   // kappa + g.c
-    T ga = dot(d, ao) * gs;
-    T gv = dot(d, v) * gs;
-    T fq = fl + Ml * (sigma * curv - ga);
-    num += gv * ((fl - fel) + Ml * (sigma - T(1)) * curv);
-    V3<T> Md = d * (Ml * gs * gs);
+    T fel = (T(-0.04) * wt) * (hx * ix); // Euler-Lagrange force of the leaf energy
+    T Mg = Ml * gs;
+    T fq = fl + Mg * (sigma * inner - aref * da);
+    num += (dv * gs) * ((fl - fel) + (Mg * (sigma - T(1))) * inner);
+    V3<T> Md = d * (Mg * gs);
     acc.A.xx += Md.x * d.x; acc.A.xy += Md.x * d.y; acc.A.xz += Md.x * d.z;
     acc.A.yy += Md.y * d.y; acc.A.yz += Md.y * d.z; acc.A.zz += Md.z * d.z;
     acc.b = acc.b + d * (gs * fq);
@@ -360,7 +371,7 @@ template <typename T> MRF_HD void attractor_scalars(T n, T w, T& dpsi, T& m2) {
 
 // ------------------------------------------------------------------------------------------------
 // fabric_action: energised geometry + forcing + damper for one robot.  `src.each(f)` enumerates the obstacle
-// spheres: f(xo, vo, ao, radius, weight).  q, qd in registers; own kinematics in kin[..tid]; parameters in
+// spheres: f(xo, vo, co, radius, weight) with velocity src.vref * vo and acceleration src.aref * co.  q, qd in registers; own kinematics in kin[..tid]; parameters in
 // prm[k*NT + tid].  Writes act[7] (velocity in 'vel' mode, acceleration in 'acc' mode).
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename Src>
@@ -428,8 +439,8 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             }
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
-                src.each([&](V3<T> xo, V3<T> vo, V3<T> ao, T ro, T wo) {
-                    sphere_leaf(p, v, cc, xo, vo, ao, ro + rb, we * wo, sigma, acc, num);
+                src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
+                    sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
                 });
                 plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
             }
@@ -537,7 +548,7 @@ constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane e
 // ------------------------------------------------------------------------------------------------
 // obstacle sources for fabric_action
 // ------------------------------------------------------------------------------------------------
-// other robots of the same scenario, read from the CTA's shared kinematics table
+// other robots of the same scenario, read from the CTA's shared kinematics table (generic: table driven, any radii)
 template <typename T> struct SmemSrc {
     const DevCfg<T>& cfg;
     const T* kin;
@@ -548,10 +559,32 @@ template <typename T> struct SmemSrc {
 #pragma unroll 2
         for (int k = 0; k < ne; ++k) {
             const T* b = kin + cfg.ent_src[r][k] * 9 * NT + cfg.ent_rob[r][k] * kTile + lane;
-            V3<T> xo = mk(b[0], b[NT], b[2 * NT]);
-            V3<T> vo = mk(b[3 * NT], b[4 * NT], b[5 * NT]) * vref;
-            V3<T> ao = mk(b[6 * NT], b[7 * NT], b[8 * NT]) * aref;
-            f(xo, vo, ao, cfg.ent_rad[r][k], cfg.ent_w[r][k]);
+            f(mk(b[0], b[NT], b[2 * NT]), mk(b[3 * NT], b[4 * NT], b[5 * NT]), mk(b[6 * NT], b[7 * NT], b[8 * NT]),
+              cfg.ent_rad[r][k], cfg.ent_w[r][k]);
+        }
+    }
+};
+
+// same, specialised to the reference's set-up in which every robot sphere has the same radius
+// (parameters_manipulators.py:23,37-43): no table look-ups, the six distinct points of each other robot are unrolled
+// with their multiplicities (link3, link4, link5==6 [x2], link7, link8, link1==2 [x2]) as compile-time constants.
+template <typename T, int R> struct SmemSrcUniform {
+    const T* kin;
+    int lane, r;
+    T vref, aref, ro;
+    template <typename F> MRF_HD void each(F f) const {
+        constexpr int NT = kTile * R;
+        // runtime loops (pairs of leaves unrolled for ILP): a fully unrolled body overflows the instruction cache
+        // (measured: stall_no_inst 46 % with 12 inlined leaves vs 7 % with 2)
+#pragma unroll 1
+        for (int j = 0; j < R; ++j) {
+            if (j == r) continue;
+            const T* b = kin + j * kTile + lane;
+#pragma unroll 2
+            for (int pt = 0; pt < kPts; ++pt, b += 9 * NT) {
+                f(mk(b[0], b[NT], b[2 * NT]), mk(b[3 * NT], b[4 * NT], b[5 * NT]), mk(b[6 * NT], b[7 * NT], b[8 * NT]),
+                  ro, (pt == 2 || pt == 5) ? T(2) : T(1));
+            }
         }
     }
 };
@@ -562,6 +595,7 @@ template <typename T, bool CART> struct GlobalSrc {
     long long stride, off;
     int S;
     T tk;
+    T vref, aref;
     template <typename F> MRF_HD void each(F f) const {
 #pragma unroll 2
         for (int o = 0; o < S; ++o) {

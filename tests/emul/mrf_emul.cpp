@@ -55,10 +55,18 @@ static int rollout(const MrfConfig* mc, const double* rec, int N, double* avg, d
             for (int tid = 0; tid < NT; ++tid) {
                 int lane = tid % kTile, r = tid / kTile;
                 long long b = t0 + lane;
-                SmemSrc<T> src{cfg, kin.data(), NT, lane, r, cfg.static_or_dyn ? T(1) : T(0),
-                               cfg.static_or_dyn ? cfg.sref : T(0)};
+                const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
                 T act[7];
-                fabric_action(cfg, r, &q[tid * 7], &qd[tid * 7], ch[tid], kin.data(), prm.data(), NT, tid, src, act);
+                if (cfg.uniform_obst && R == 3) {
+                    SmemSrcUniform<T, 3> src{kin.data(), lane, r, vref, aref, cfg.r_obst};
+                    fabric_action(cfg, r, &q[tid * 7], &qd[tid * 7], ch[tid], kin.data(), prm.data(), NT, tid, src, act);
+                } else if (cfg.uniform_obst && R == 2) {
+                    SmemSrcUniform<T, 2> src{kin.data(), lane, r, vref, aref, cfg.r_obst};
+                    fabric_action(cfg, r, &q[tid * 7], &qd[tid * 7], ch[tid], kin.data(), prm.data(), NT, tid, src, act);
+                } else {
+                    SmemSrc<T> src{cfg, kin.data(), NT, lane, r, vref, aref};
+                    fabric_action(cfg, r, &q[tid * 7], &qd[tid * 7], ch[tid], kin.data(), prm.data(), NT, tid, src, act);
+                }
                 for (int i = 0; i < 7; ++i) {
                     qd[tid * 7 + i] = act[i];
                     acc[tid] += act[i] * act[i];
@@ -92,7 +100,7 @@ static int action(const MrfConfig* mc, int robot, const double* rec, int S, cons
         load_params<T>(ld, prm.data(), NT, 0);
         for (int o = 0; o < S * MRF_OBST; ++o) ob[o] = (T)obst[b * S * MRF_OBST + o]; // [o][c] with stride 1
         Chain<T> ch;
-        GlobalSrc<T, CART> src{ob.data(), 1, 0, S, T(0)};
+        GlobalSrc<T, CART> src{ob.data(), 1, 0, S, T(0), T(1), T(1)};
         T act[7];
         if (!CART) {
             chain_forward(cfg, robot, q, qd, ch, kin.data(), NT, 0);

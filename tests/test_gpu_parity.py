@@ -156,7 +156,8 @@ def test_device_api_equals_host_api(fabs):
         a0 = fab.rollout_dev(d_rec[:, :, :h].contiguous(), N)
         a1 = fab.rollout_dev(d_rec[:, :, h:].contiguous(), N)
         torch.cuda.synchronize()
-        assert torch.equal(torch.cat([a0, a1], dim=1), avg)
+        assert torch.equal(torch.cat([a0, a1], dim=1).view(torch.int32 if key == "f32" else torch.int64),
+                           avg.view(torch.int32 if key == "f32" else torch.int64))
 
 
 def test_full_size_batch_properties(fabs):
@@ -172,8 +173,10 @@ def test_full_size_batch_properties(fabs):
     perm = torch.randperm(B, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(0))
     avg_p = fab.rollout_dev(d_rec[:, :, perm].contiguous(), N)
     torch.cuda.synchronize()
-    assert torch.equal(avg[:, perm], avg_p)                       # a scenario never reads another scenario
-    assert torch.equal(avg[:, :4096], avg[:, 4096:8192])          # tiled copies give identical bits
+    bits = lambda t: t.contiguous().view(torch.int32)            # bitwise (NaN-safe) comparison
+    assert torch.equal(bits(avg[:, perm]), bits(avg_p))           # a scenario never reads another scenario
+    assert torch.equal(bits(avg[:, :4096]), bits(avg[:, 4096:8192]))   # tiled copies give identical bits
+    assert torch.isfinite(avg).float().mean() > 0.98
     idx = np.arange(0, 4096, 64)
     qN, qdN, ravg, xee, goal, ok = oracle_rollout(base[idx], R, N)
     got = avg[:, idx].cpu().numpy().T
