@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrf_b200.so")
+LIB_PATH = os.environ.get("MRF_B200_LIB", os.path.join(_HERE, "libmrf_b200.so"))   # override: A/B builds only
 
 MAX_ROBOTS, DOF, NLINKS, REC, OBST = 4, 7, 8, 44, 10
 Q, QD, G0, W0, G1, W1, G2, W2, ANG, CON, RB = 0, 7, 14, 17, 18, 21, 22, 23, 24, 33, 37

@@ -110,6 +110,10 @@ class PandaFabricPlanner:
                 rec[RB + i] = float(np.asarray(links[l]).reshape(-1)[0])
             elif self.collision_links_nr:
                 raise KeyError(key)
+        if not self.collision_links_nr:
+            # no collision links -> fabrics creates no obstacle leaves, so no obstacle parameter exists in the function
+            # (the grasp planner is built with nr_obst = nr_obst_dyn = i_robot, example_pandas_Jointspace.py:160-166)
+            return rec, np.zeros((0, OBST))
         obst = np.zeros((self.nr_obst + self.nr_obst_dyn, OBST))
         for i in range(self.nr_obst):                      # static spheres: x_obst_i, radius_obst_i
             x = kw[f"x_obst_{i}"] if f"x_obst_{i}" in kw else kw["x_obsts"][i]
@@ -123,8 +127,6 @@ class PandaFabricPlanner:
             obst[o, 3:6] = _vec(get("xdot_obst_dynamic", "xdot_obsts_dynamic"), 3)
             obst[o, 6:9] = _vec(get("xddot_obst_dynamic", "xddot_obsts_dynamic"), 3)
             obst[o, 9] = float(np.asarray(get("radius_obst_dynamic", "radius_obsts_dynamic")).reshape(-1)[0])
-        if not self.collision_links_nr:
-            obst = obst[:0]
         return rec, obst
 
     def compute_action(self, **kwargs) -> np.ndarray:

@@ -1,0 +1,197 @@
+"""GPU tests of the reference-facing Python surface: the drop-in classes call the CUDA library and must reproduce
+the oracle (fabric arithmetic) and the reference's own deadlock class (golden sequences)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import multi_robot_fabrics_b200 as m
+from multi_robot_fabrics_b200 import planner as P
+from multi_robot_fabrics_b200.api import Fabrics
+from oracle import o2
+from oracle.deadlock_ref import DeadlockOracle
+
+from helpers import oracle_rollout, random_obstacles
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MOUNT = {"z_table": 0.65, "mount_positions": [np.array([0.0, 0.0, 0.65]), np.array([1.0, 0.0, 0.65]),
+                                              np.array([0.7, 0.6, 0.65])]}
+LINKS = [1, 2, 3, 4, 5, 6, 7, 8]
+
+
+def make_params(R, N):
+    """The attributes ForwardFabricsPlanner reads from manipulator_parameters (parameters_manipulators.py)."""
+    p = types.SimpleNamespace()
+    p.N_HORIZON, p.dt, p.dof, p.nr_obsts = N, 0.01, [7] * R, [0] * R
+    p.fabrics_mode, p.STATIC_OR_DYN_FABRICS = "vel", 1
+    p.collision_links_nrs = [LINKS] * R
+    p.r_robots = [[0.08] * 8 for _ in range(R)]
+    p.rotation_matrix_pandas = [P.ROT_PANDA] * R
+    p.nr_obsts_dyn = [8 * (R - 1)] * R
+    return p
+
+
+def test_compute_action_dropin_matches_oracle(built):
+    """planner.compute_action(**kwargs) with the kwargs of examples/example_pandas_Jointspace.py:421-439."""
+    rng = np.random.default_rng(0)
+    S = 8
+    rec = m.scenarios.generate(6, 2, seed=51, weight_goal_1=20.0)
+    obst = random_obstacles(rng, 6, 2, S, rec)
+    ocfg = o2.default_config(2)
+    for robot in (0, 1):
+        pl, goal = P.set_planner_panda(7, 0, S, LINKS, {}, MOUNT, robot)
+        assert len(goal._config) == 3
+        for b in range(6):
+            r, o = rec[b, robot], obst[b, robot]
+            xs = [o[i, 0:3] for i in range(S)]
+            kw = dict(q=r[0:7], qdot=r[7:14], x_goal_0=r[14:17], weight_goal_0=r[17], angle_goal_1=P.ROT_PANDA,
+                      x_goal_1=np.array([0.107, 0.0, 0.0]), weight_goal_1=20.0, x_goal_2=np.array([np.pi / 4]),
+                      weight_goal_2=1.0, x_obsts=xs, radius_obsts=[0.08] * S, constraint_0=np.array([0, 0, 1, -0.65]),
+                      radius_body_panda_links={str(l): np.array(0.08) for l in range(3, 9)},
+                      radius_body_panda_hand=np.array([0.08]), x_obsts_dynamic=xs,
+                      xdot_obsts_dynamic=[o[i, 3:6] for i in range(S)], xddot_obsts_dynamic=[o[i, 6:9] for i in range(S)],
+                      radius_obsts_dynamic=[0.08] * S)
+            act = pl.compute_action(**kw)
+            ref = o2.action(ocfg, robot, r, o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+            assert act.shape == (7,) and np.abs(act - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    # grasp planner (collision_links_nr=[]) and the small-action clamp
+    pg, _ = P.set_planner_panda(7, 1, 1, [], {}, MOUNT, 1)
+    r = rec[0, 1]
+    act = pg.compute_action(q=r[0:7], qdot=r[7:14], x_goal_0=r[14:17], weight_goal_0=r[17], angle_goal_1=P.ROT_PANDA,
+                            x_goal_1=[0.107, 0, 0], weight_goal_1=20.0, x_goal_2=[np.pi / 4], weight_goal_2=1.0,
+                            x_obsts=[np.zeros(3)], radius_obsts=[0.1], constraint_0=[0, 0, 1, -0.65])
+    ref = o2.action(o2.default_config(2, has_collision_links=0), 1, np.concatenate([r[:21], [20.0], r[22:]]),
+                    np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
+    assert np.abs(act - ref).max() < 1e-9
+
+
+def test_forward_fabrics_planner_dropin(built):
+    R, N = 2, 20
+    rec = m.scenarios.generate(3, R, seed=52)
+    planners = [P.set_planner_panda(7, 0, 8, LINKS, {}, MOUNT, i)[0] for i in range(R)]
+    goals = [P.PandaGoal() for _ in range(R)]
+    fp = P.ForwardFabricsPlanner(make_params(R, N), planners, 100, None, goals)
+    assert fp.forward_multi_fabrics_symbolic() == {}
+    for b in range(3):
+        ia = {"q_robots": [rec[b, i, 0:7] for i in range(R)], "q_dot_robots": [rec[b, i, 7:14] for i in range(R)],
+              "x_obsts": [[] * R], "x_goals0": [rec[b, i, 14:17] for i in range(R)],
+              "x_goals1": [goals[i]._config.subgoal1.desired_position for i in range(R)],
+              "x_goals2": [goals[i]._config.subgoal2.desired_position for i in range(R)],
+              "weight_goals0": [rec[b, i, 17] for i in range(R)],
+              "weight_goals1": [goals[i]._config.subgoal1.weight for i in range(R)],
+              "weight_goals2": [goals[i]._config.subgoal2.weight for i in range(R)],
+              "constraints": [np.array([0, 0, 1, -0.65])] * R}
+        vel_avg = fp.get_velocity_rollouts(ia)
+        qN, qdN, avg, *_ = oracle_rollout(rec[b:b + 1], R, N)
+        assert len(vel_avg) == R and vel_avg[0].shape == (1,)
+        assert np.abs(np.array([v[0] for v in vel_avg]) - avg[0]).max() < 1e-9
+        q_n, qd_n, qdd_n = fp.rollouts_numerical(ia)
+        for i in range(R):
+            assert q_n[f"robot_{i}"][0].shape == (7, N)
+            assert np.abs(q_n[f"robot_{i}"][0] - qN[0, i].T).max() < 1e-9
+            assert np.abs(qd_n[f"robot_{i}"][0] - qdN[0, i].T).max() < 1e-9
+            assert not qdd_n[f"robot_{i}"][0].any()
+
+
+def test_fabrics_rollouts_cartesian_dropin(built):
+    N, S = 10, 8
+    rng = np.random.default_rng(3)
+    rec = m.scenarios.generate(2, 2, seed=53, weight_goal_1=20.0)
+    obst = random_obstacles(rng, 2, 2, S, rec)
+    ocfg = o2.default_config(2)
+    for robot in (0, 1):
+        pl, goal = P.set_planner_panda(7, 0, S, LINKS, {}, MOUNT, robot)
+        fr = P.FabricsRollouts(N=N, dt=0.01, nx=7, nu=7, dof=7, nr_obsts=0, bool_ring=False, nr_obsts_dyn=S,
+                               v_obsts_dyn=[np.zeros(3)] * S, fabrics_mode="vel", collision_links_nrs=LINKS,
+                               nr_constraints=1, constraints=np.array([0, 0, 1, -0.65]), nr_goals=3)
+        fr.preset_radii_obsts_dyn([0.08] * S)
+        fr.symbolic_forward_fabrics(pl, goal)
+        r, o = rec[0, robot], obst[0, robot]
+        args = fr.define_arguments_numerical(
+            q_robot=r[0:7], q_dot_robot=r[7:14], weight_goals={"subgoal0": r[17], "subgoal1": 20.0, "subgoal2": 1.0},
+            x_goals={"subgoal0": r[14:17], "subgoal1": np.array([0.107, 0, 0]), "subgoal2": np.array([np.pi / 4])},
+            x_obsts=[], x_obsts_dyn=[o[i, 0:3] for i in range(S)], v_obsts_dyn=[o[i, 3:6] for i in range(S)],
+            constraints=np.array([0, 0, 1, -0.65]))
+        q_n, qd_n, qdd_n = fr.rollouts_numerical(args)
+        rq, rqd, ravg = o2.rollout_cartesian(ocfg, robot, r, o[:, 0:3], o[:, 3:6], o[:, 9], N)
+        assert q_n.shape == (7, N) and np.abs(q_n - rq.T).max() < 1e-9 and np.abs(qd_n - rqd.T).max() < 1e-9
+        assert abs(fr.get_velocity_rollouts(args).full()[0][0] - ravg) < 1e-9
+
+
+def test_deadlock_dropin_matches_reference_golden(built):
+    """The CUDA deadlock kernel behind the reference's class interface replays the reference's own outputs bit for bit
+    (goals, weights, time_deadlock_out) -- 'deadlock flags identical'."""
+    g = np.load(os.path.join(GOLD, "deadlock_golden.npz"))
+    raised = 0
+    for c in range(int(g["n_cases"])):
+        p = f"c{c}_"
+        R = int(g[p + "R"])
+        dl, ref = P.deadlockprevention([7] * R, R, 20), DeadlockOracle(R)
+        tdo = tdo_r = 1000
+        for t in range(len(g[p + "x"])):
+            goals = [v.copy() for v in g[p + "goals"][t]]
+            weights = [float(w) for w in g[p + "weights"][t]]
+            go, wo, tdo = dl.deadlock_checking([v.copy() for v in g[p + "x"][t]], goals, weights, int(g[p + "time_step"][t]),
+                                               tdo, float(g[p + "avg"][t]), list(g[p + "states"][t]))
+            _, _, tdo_r, flag = ref.step(g[p + "x"][t], g[p + "goals"][t], g[p + "weights"][t], int(g[p + "time_step"][t]),
+                                         tdo_r, float(g[p + "avg"][t]), list(g[p + "states"][t]))
+            raised += int(dl.deadlock)
+            assert dl.deadlock == flag
+            assert np.array_equal(np.array(go), g[p + "goals_out"][t]), (c, t)
+            assert np.array_equal(np.array(wo, dtype=float), g[p + "weights_out"][t]), (c, t)
+            assert tdo == g[p + "tdo_out"][t]
+            assert go is goals and wo is weights            # mutated in place like the reference
+    assert raised > 50
+
+
+def test_batched_deadlock_from_rollout_flags_identical(built):
+    """Fused path used by bench.py: rollout (FP64 and FP32) -> batched deadlock kernel; flags / follower goals equal the
+    oracle's on every scenario."""
+    import torch
+    from multi_robot_fabrics_b200.api import to_soa
+    R, N, B = 3, 20, 512
+    rec = m.scenarios.generate(B, R, seed=54)
+    rec[:, :, 7:14] *= 0.1                                  # slow scenarios so that avg_vel < 0.16 happens
+    # pull end effectors of half of the scenarios close together by giving identical goals (deadlock candidates)
+    fab = Fabrics(R, device=0, estimate_goal=1)
+    qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N, estimate_goal=1)
+    states = np.random.default_rng(1).choice([0, 1, 1, 0, 2], size=(B, R)).astype(np.int32)
+    exp_flag = np.zeros(B, dtype=np.int32)
+    exp_goals = rec[:, :, 14:17].copy()
+    exp_goals[:, 1] = goal
+    exp_w = rec[:, :, 17].copy()
+    xe = xee.copy()
+    xe[::2, 1] = xe[::2, 0] + [0.05, 0.02, 0.01]            # make every other scenario a near-contact pair (0,1)
+    for b in range(B):
+        d = DeadlockOracle(R)
+        go, wo, _, fl = d.step(xe[b], exp_goals[b], exp_w[b], 100, 1000, float(sum(avg[b]) / R), list(states[b]))
+        exp_flag[b], exp_goals[b], exp_w[b] = fl, np.array(go), np.array(wo, dtype=float)
+    for dt in (torch.float64, torch.float32):
+        dev = "cuda:0"
+        d_rec = torch.from_numpy(to_soa(rec)).to(dev, dtype=dt)
+        a = torch.empty((R, B), dtype=dt, device=dev)
+        x = torch.empty((R, 3, B), dtype=dt, device=dev)
+        ge = torch.empty((3, B), dtype=dt, device=dev)
+        fab.rollout_dev(d_rec, N, avg_vel=a, x_ee=x, goal_est=ge)
+        x = torch.from_numpy(np.ascontiguousarray(xe.transpose(1, 2, 0))).to(dev, dtype=dt)   # the engineered ee positions
+        goals = d_rec[14:17].permute(1, 0, 2).contiguous()
+        goals[1] = ge
+        w = d_rec[17].clone()
+        sm = torch.from_numpy(np.ascontiguousarray(states.T)).to(dev)
+        ts = torch.full((B,), 100, dtype=torch.int32, device=dev)
+        tdo = torch.full((B,), 1000, dtype=torch.int32, device=dev)
+        st_int = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous()
+        st_goal = torch.zeros((3, B), dtype=dt, device=dev)
+        flag = fab.deadlock_dev(x, goals, w, sm, ts, tdo, st_int, st_goal, avg_vel=a)
+        torch.cuda.synchronize()
+        okb = ok & (np.abs(avg.sum(axis=1) / R - 0.16) > 1e-4)          # FP32 avg_vel may not sit on the 0.16 knife edge
+        assert np.array_equal(flag.cpu().numpy()[okb], exp_flag[okb])
+        assert exp_flag[okb].sum() > 20
+        tol = 1e-12 if dt == torch.float64 else 1e-5
+        got = goals.permute(2, 0, 1).double().cpu().numpy()
+        assert np.abs(got - exp_goals)[okb].max() < tol
+        assert np.array_equal(w.T.double().cpu().numpy()[okb], exp_w[okb])
+    fab.close()
