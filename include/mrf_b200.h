@@ -166,6 +166,11 @@ int mrf_deadlock_host_f64(mrf_handle_t h, const double* x_ee, double* goals, dou
                           const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
                           int32_t* st_int, double* st_goal, int32_t* flag, int64_t B);
 
+/* mrf_rollout_* picks between two kernels computing the same recurrence: the cooperative low-latency kernel (one CTA
+ * per scenario, one warp per robot) for B <= max_batch, the throughput kernel (one thread per scenario and robot)
+ * above.  Default 512; 0 disables the cooperative kernel. */
+int mrf_set_coop_max_batch(mrf_handle_t h, int64_t max_batch);
+
 /* Number of kernels this library has launched through handle h since creation (for bench accounting). */
 int64_t mrf_launch_count(mrf_handle_t h);
 /* Device time in ms of the last *_host_* call's kernel(s) (CUDA events on the handle's stream). */

@@ -48,7 +48,7 @@ EXPORTS = [
     "mrf_rollout_cart_dev_f64", "mrf_rollout_cart_dev_f32", "mrf_kinematics_dev_f64", "mrf_kinematics_dev_f32",
     "mrf_deadlock_dev_f64", "mrf_deadlock_dev_f32", "mrf_action_host_f64", "mrf_action_host_f32",
     "mrf_rollout_host_f64", "mrf_rollout_host_f32", "mrf_rollout_cart_host_f64", "mrf_rollout_cart_host_f32",
-    "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak",
+    "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak", "mrf_set_coop_max_batch",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
         getattr(L, f"mrf_rollout_cart_host_{p}").argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, i64]
     L.mrf_kinematics_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, i64]
     L.mrf_deadlock_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]
+    L.mrf_set_coop_max_batch.argtypes = [vp, i64]
     L.mrf_fma_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -146,6 +147,10 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(lib().mrf_launch_count(self._h))
+
+    def set_coop_max_batch(self, max_batch: int) -> None:
+        """Batches up to max_batch use the cooperative low-latency rollout kernel (0 = never)."""
+        check(lib().mrf_set_coop_max_batch(self._h, int(max_batch)), "mrf_set_coop_max_batch")
 
     def fma_peak_tflops(self, f64: bool = False) -> float:
         out = C.c_double(0.0)

@@ -29,6 +29,7 @@
 #include "../../include/mrf_b200.h"
 #include "mrf_device.cuh"
 #include "mrf_devcfg.h"
+#include "mrf_coop.cuh"
 
 namespace mrf {
 
@@ -423,6 +424,7 @@ struct MrfHandle_ {
     size_t stage_bytes[8];
     long long launches;
     double last_ms;
+    long long coop_max_batch; // batches up to this size use the cooperative low-latency rollout kernel
 };
 
 extern "C" int mrf_version(void) { return 100; }
@@ -499,6 +501,8 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     if (!h) return fail(MRF_ENOMEM, "mrf_create: out of memory");
     h->cfg = *cfg;
     h->device = device;
+    h->coop_max_batch = 512;
+    if (const char* e = getenv("MRF_COOP_MAX_BATCH")) h->coop_max_batch = atoll(e);
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -520,6 +524,11 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     return MRF_OK;
 }
 
+extern "C" int mrf_set_coop_max_batch(mrf_handle_t h, int64_t max_batch) {
+    if (!h || max_batch < 0) return fail(MRF_EINVAL, "mrf_set_coop_max_batch: bad argument");
+    h->coop_max_batch = max_batch;
+    return MRF_OK;
+}
 extern "C" int64_t mrf_launch_count(mrf_handle_t h) { return h ? h->launches : 0; }
 extern "C" double mrf_last_kernel_ms(mrf_handle_t h) { return h ? h->last_ms : 0.0; }
 
@@ -543,6 +552,18 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
                                       "(forward_planner_Jointspace.py:197-201,233)");
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
+    if (R >= 2 && B <= h->coop_max_batch) {
+        // few scenarios: latency matters, not throughput -> one CTA per scenario, one warp per robot (mrf_coop.cuh)
+        switch (R) {
+            case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            case 3: rollout_coop_kernel<T, 3><<<(unsigned)B, 96, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            case 4: rollout_coop_kernel<T, 4><<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
+        }
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return MRF_OK;
+    }
     const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * NT;
     const long long grid = (B + kTile - 1) / kTile;
     int rc = MRF_OK;

@@ -32,6 +32,16 @@ template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) 
         d.link1[r][1] = (T)(M[7] + R[5] * 0.333);
         d.link1[r][2] = (T)(M[11] + R[8] * 0.333);
     }
+    for (int r = 0; r < c.n_robots; ++r) {
+        const int la[kPts] = {2, 3, 4, 6, 7, 0}, lb[kPts] = {-1, -1, 5, -1, -1, 1}; // link indices sharing each point
+        for (int pt = 0; pt < kPts; ++pt) {
+            d.pt_rad[r][pt][0] = (T)c.r_robots[r][la[pt]];
+            d.pt_rad[r][pt][1] = (T)(lb[pt] >= 0 ? c.r_robots[r][lb[pt]] : 0.0);
+            const bool two = lb[pt] >= 0, same = two && c.r_robots[r][la[pt]] == c.r_robots[r][lb[pt]];
+            d.pt_n[r][pt] = (two && !same) ? 2 : 1;
+            d.pt_w[r][pt] = (T)(same ? 2 : 1);
+        }
+    }
     d.uniform_obst = 1;
     d.r_obst = (T)c.r_robots[0][0];
     for (int r = 0; r < c.n_robots; ++r)

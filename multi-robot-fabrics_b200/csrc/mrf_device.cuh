@@ -136,6 +136,11 @@ template <typename T> struct DevCfg {
     // spheres robot r sees in a coupled rollout, flattened over the other robots (ascending) and their distinct
     // points with multiplicity: link1==link2 and link5==link6 share a point and are merged into one entry of weight
     // 2 when their radii agree.  ent_off = kinematics-table offset (point * 9 * NT + other_robot * 32).
+    // per distinct point of robot j (slot order link3, link4, link5==6, link7, link8, link1==2): the radii of the one or
+    // two links sharing it; pt_n = 1 with weight 2 when both radii agree (used by the cooperative low-latency kernel)
+    int pt_n[MRF_MAX_ROBOTS][kPts];
+    T pt_w[MRF_MAX_ROBOTS][kPts];
+    T pt_rad[MRF_MAX_ROBOTS][kPts][2];
     int uniform_obst;           // every r_robots[j][l] equal -> SmemSrcUniform fast path with radius r_obst
     T r_obst;
     int ent_n[MRF_MAX_ROBOTS];

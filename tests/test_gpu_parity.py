@@ -32,11 +32,14 @@ def get_fab(fabs, R, **kw):
     return fabs[key]
 
 
+@pytest.mark.parametrize("kernel", ["throughput", "cooperative"])
 @pytest.mark.parametrize("R,N,B,est", [(2, 20, 70, 0), (2, 20, 33, 1), (3, 50, 96, 1), (3, 20, 1, 0), (3, 50, 40, 2)])
-def test_rollout_f64_matches_oracle(fabs, R, N, B, est):
+def test_rollout_f64_matches_oracle(fabs, R, N, B, est, kernel):
     rec = m.scenarios.generate(B, R, seed=100 + R + N)
     fab = get_fab(fabs, R, estimate_goal=est)
+    fab.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
     out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    fab.handle.set_coop_max_batch(512)
     qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N, estimate_goal=est)
     assert ok.sum() >= max(1, int(0.9 * B))
     scale = np.abs(qdN[ok]).max()
@@ -47,13 +50,16 @@ def test_rollout_f64_matches_oracle(fabs, R, N, B, est):
     assert np.abs(out["goal_est"] - goal).max() < 1e-12
 
 
+@pytest.mark.parametrize("kernel", ["throughput", "cooperative"])
 @pytest.mark.parametrize("R,N", [(2, 20), (3, 50)])
-def test_rollout_f32_within_tolerance(fabs, R, N):
+def test_rollout_f32_within_tolerance(fabs, R, N, kernel):
     """FP32 path: |qdot - oracle| <= 2e-3 rad/s and |q - oracle| <= 2e-4 rad over the horizon, avg_vel <= 1e-3."""
     B = 256
     rec = m.scenarios.generate(B, R, seed=7)
     fab = get_fab(fabs, R)
+    fab.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
     out = fab.rollout_host(rec, N, dtype="f32", trajectories=True)
+    fab.handle.set_coop_max_batch(512)
     qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N)
     assert np.abs(out["qdN"] - qdN)[ok].max() < 2e-3
     assert np.abs(out["qN"] - qN)[ok].max() < 2e-4
@@ -61,13 +67,30 @@ def test_rollout_f32_within_tolerance(fabs, R, N):
     assert np.abs(out["x_ee"] - xee).max() < 1e-5
 
 
-def test_rollout_static_fabrics(fabs):
-    """STATIC_OR_DYN_FABRICS = 0 zeroes the other robots' v and a (forward_planner_Jointspace.py:215-217)."""
+@pytest.mark.parametrize("kernel", ["throughput", "cooperative"])
+def test_rollout_static_fabrics_and_nonuniform_radii(fabs, kernel):
+    """STATIC_OR_DYN_FABRICS = 0 zeroes the other robots' v and a (forward_planner_Jointspace.py:215-217); unequal
+    sphere radii disable the merged-point fast path (link1/link2 and link5/link6 become separate leaves)."""
     R, N, B = 2, 10, 32
     rec = m.scenarios.generate(B, R, seed=3)
     fab = get_fab(fabs, R, static_or_dyn=0)
+    fab.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
     out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
     qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N, static_or_dyn=0)
+    assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
+    rr = [[0.08, 0.06, 0.08, 0.08, 0.07, 0.09, 0.08, 0.08], [0.05, 0.05, 0.08, 0.1, 0.08, 0.08, 0.06, 0.08]]
+    rec[:, :, o2.RB:o2.RB + 6] = [0.08, 0.07, 0.09, 0.06, 0.08, 0.1]
+    fab2 = Fabrics(R, device=0, r_robots=rr)
+    fab2.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
+    out = fab2.rollout_host(rec, N, dtype="f64", trajectories=True)
+    fab2.close()
+    ocfg = o2.default_config(R)
+    for r in range(R):
+        for l in range(8):
+            ocfg.r_robots[r][l] = rr[r][l]
+    qN, qdN, avg, _ = o2.rollout_jointspace(ocfg, rec, N)
+    ok = np.isfinite(qdN).all(axis=(1, 2, 3)) & (np.abs(qdN).max(axis=(1, 2, 3)) < 3)
+    assert ok.sum() > B // 2
     assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
 
 
