@@ -65,8 +65,26 @@ template <> struct Mth<float> {
         return 1.0f / x;
 #endif
     }
-    static MRF_HD float exp(float x) { return ::expf(x); }
-    static MRF_HD float tanh(float x) { return ::tanhf(x); }
+    // exp / tanh through MUFU.EX2 (2 ulp): ~1e-7 relative on exp; tanh = (t-1)/(t+1), t = 2^(2x log2 e), absolute
+    // error < 3e-7 (argument clamped so t stays finite).  Used 7 times per action; ::expf / ::tanhf cost ~30 each.
+    static MRF_HD float exp(float x) {
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        return r;
+#else
+        return ::expf(x);
+#endif
+    }
+    static MRF_HD float tanh(float x) {
+#if defined(__CUDA_ARCH__)
+        float xc = ::fminf(::fmaxf(x, -15.0f), 15.0f), t;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(xc * 2.8853900817779268f));
+        return (t - 1.0f) * rcp(t + 1.0f);
+#else
+        return ::tanhf(x);
+#endif
+    }
     // Joint angles are bounded by the Panda limits (|q| < 3.8 rad): Cody-Waite reduction by pi/2 and degree-7/8
     // minimax polynomials on [-pi/4, pi/4] (~1e-7 abs error) in ~22 instructions, without the argument-reduction slow
     // path that ::sincosf drags into every call site (it was 2 % of instructions and much more of the code size).
