@@ -394,6 +394,26 @@ template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T* 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// AoS records [B][Ro][Fi] -> SoA [Fi][Ro][B] in one pass (the layout the kernels read), same 32x33 tiling
+template <typename T>
+__global__ void records_to_soa_kernel(const T* __restrict__ in, T* __restrict__ out, long long B, int Ro, int Fi) {
+    __shared__ T tile[32][33];
+    const int F = Ro * Fi;
+    const long long b0 = (long long)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long long b = b0 + i;
+        int f = f0 + threadIdx.x;
+        if (b < B && f < F) tile[i][threadIdx.x] = in[b * F + f];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int f = f0 + i; // input column = r * Fi + field
+        long long b = b0 + threadIdx.x;
+        if (b < B && f < F) out[((long long)(f % Fi) * Ro + f / Fi) * B + b] = tile[threadIdx.x][i];
+    }
+}
+
 } // namespace mrf
 
 // =================================================================================================
@@ -418,8 +438,8 @@ struct MrfHandle_ {
     int device;
     DevCfg<float> c32;
     DevCfg<double> c64;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
+    cudaStream_t stream, s_copy, s_chunk[4];
+    cudaEvent_t ev0, ev1, ev_up[8], ev_free, ev_chunk[4];
     void* stage[8];
     size_t stage_bytes[8];
     long long launches;
@@ -506,8 +526,15 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MRF_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     MRF_CUDA(cudaEventCreate(&h->ev0));
     MRF_CUDA(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 8; ++i) MRF_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    MRF_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) {
+        MRF_CUDA(cudaStreamCreateWithFlags(&h->s_chunk[i], cudaStreamNonBlocking));
+        MRF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    }
     *out = h;
     return MRF_OK;
 }
@@ -519,7 +546,14 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
         if (h->stage[i]) cudaFree(h->stage[i]);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_up[i]);
+    cudaEventDestroy(h->ev_free);
+    for (int i = 0; i < 4; ++i) {
+        cudaEventDestroy(h->ev_chunk[i]);
+        cudaStreamDestroy(h->s_chunk[i]);
+    }
     cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->s_copy);
     delete h;
     return MRF_OK;
 }
@@ -767,12 +801,78 @@ static int upload_records(mrf_handle_t h, const T* rec, long long B, int R, int 
     return MRF_OK;
 }
 
+// Large batches without trajectory output: the batch is cut into chunks; the H2D copy of chunk c+1 (copy stream)
+// overlaps the transpose + rollout + result read-back of chunk c (compute stream).
+template <typename T>
+static int rollout_host_pipelined(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B) {
+    const int R = h->cfg.n_robots, C = 4;
+    const long long Bc = (((B + C - 1) / C) + 31) / 32 * 32; // chunk size, multiple of the CTA tile
+    const size_t rec_elems = (size_t)B * R * MRF_REC;
+    int rc = stage_reserve(h, 0, sizeof(T) * rec_elems);   // AoS records
+    if (rc) return rc;
+    rc = stage_reserve(h, 2, sizeof(T) * (size_t)Bc * C * R * MRF_REC); // SoA records, one block per chunk
+    if (rc) return rc;
+    const size_t per = (size_t)(R + 3 * R + 3);
+    rc = stage_reserve(h, 3, sizeof(T) * per * Bc * C);   // SoA results per chunk
+    if (rc) return rc;
+    rc = stage_reserve(h, 5, sizeof(T) * per * B);        // AoS results: avg [B][R], x_ee [B][3R], goal [B][3]
+    if (rc) return rc;
+    T* a_avg = (T*)h->stage[5];
+    T* a_xee = a_avg + (size_t)B * R;
+    T* a_goal = a_xee + (size_t)B * 3 * R;
+    // make sure earlier work on the compute stream no longer reads the staging buffers the copy stream overwrites
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    MRF_CUDA(cudaEventRecord(h->ev_free, h->stream));
+    MRF_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_free, 0));
+    int used = 0;
+    for (int c = 0; c < C; ++c) {
+        const long long lo = (long long)c * Bc, n = (lo + Bc <= B ? Bc : B - lo);
+        if (n <= 0) break;
+        used = c + 1;
+        // one stream per chunk: the rollout kernels of consecutive chunks overlap on the GPU (a 16k-scenario chunk
+        // alone is less than one wave of CTAs), only the copy -> compute order of each chunk is enforced
+        cudaStream_t cs = h->s_chunk[c];
+        MRF_CUDA(cudaStreamWaitEvent(cs, h->ev_free, 0));
+        T* d_aos = (T*)h->stage[0] + (size_t)lo * R * MRF_REC;
+        MRF_CUDA(cudaMemcpyAsync(d_aos, rec + (size_t)lo * R * MRF_REC, sizeof(T) * (size_t)n * R * MRF_REC,
+                                 cudaMemcpyHostToDevice, h->s_copy));
+        MRF_CUDA(cudaEventRecord(h->ev_up[c], h->s_copy));
+        MRF_CUDA(cudaStreamWaitEvent(cs, h->ev_up[c], 0));
+        T* d_soa = (T*)h->stage[2] + (size_t)c * Bc * R * MRF_REC;
+        dim3 grid((unsigned)((n + 31) / 32), (unsigned)((R * MRF_REC + 31) / 32)), block(32, 8);
+        records_to_soa_kernel<T><<<grid, block, 0, cs>>>(d_aos, d_soa, n, R, MRF_REC);
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+        T* d_avg = (T*)h->stage[3] + (size_t)c * Bc * per;
+        T* d_xee = d_avg + (size_t)R * n;
+        T* d_goal = d_xee + (size_t)3 * R * n;
+        rc = rollout_dev<T>(h, d_soa, N, d_avg, d_xee, d_goal, nullptr, nullptr, n, cs);
+        if (rc) return rc;
+        struct { T* src; T* dst; T* host; int F; } outs[3] = {{d_avg, a_avg + (size_t)lo * R, avg_vel, R},
+                                                              {d_xee, a_xee + (size_t)lo * 3 * R, x_ee, 3 * R},
+                                                              {d_goal, a_goal + (size_t)lo * 3, goal_est, 3}};
+        for (auto& o : outs) {
+            if (!o.host) continue;
+            dim3 g2((unsigned)((n + 31) / 32), (unsigned)((o.F + 31) / 32));
+            transpose_kernel<T, false><<<g2, block, 0, cs>>>(o.src, o.dst, n, o.F);
+            MRF_CUDA(cudaGetLastError());
+            h->launches += 1;
+            MRF_CUDA(cudaMemcpyAsync(o.host + (size_t)lo * o.F, o.dst, sizeof(T) * (size_t)n * o.F, cudaMemcpyDeviceToHost, cs));
+        }
+        MRF_CUDA(cudaEventRecord(h->ev_chunk[c], cs));
+    }
+    for (int c = 0; c < used; ++c) MRF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_chunk[c], 0));
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    return finish_timed(h);
+}
+
 template <typename T>
 static int rollout_host(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout_host: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout_host: B and N must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots;
+    if (!qN && !qdN && B >= 8192) return rollout_host_pipelined<T>(h, rec, N, avg_vel, x_ee, goal_est, B);
     int rc = upload_records<T>(h, rec, B, R, 0, 1, 2);
     if (rc) return rc;
     const T* d_rec = (const T*)h->stage[R == 1 ? 1 : 2];

@@ -204,3 +204,24 @@ def test_full_size_batch_properties(fabs):
     qN, qdN, ravg, xee, goal, ok = oracle_rollout(base[idx], R, N)
     got = avg[:, idx].cpu().numpy().T
     assert np.abs(got - ravg)[ok].max() < 1e-3
+
+
+def test_host_api_pipelined_large_batch(fabs):
+    """mrf_rollout_host chunks large batches (H2D of chunk c+1 overlaps the kernels of chunk c): results must equal the
+    device-pointer entry bit for bit, including a batch that is not a multiple of the chunk / tile size."""
+    import torch
+    R, N = 3, 5
+    for B in (8192, 10007):
+        base = m.scenarios.generate(1024, R, seed=17)
+        rec = np.tile(base, ((B + 1023) // 1024, 1, 1))[:B]
+        rec[:, 0, 17] += np.arange(B) % 7 * 1e-3                     # make every scenario distinct
+        fab = get_fab(fabs, R, estimate_goal=1)
+        host = fab.rollout_host(rec.astype(np.float32), N, dtype="f32")
+        d_rec = torch.from_numpy(to_soa(rec.astype(np.float32))).to("cuda:0")
+        xee = torch.empty((R, 3, B), dtype=torch.float32, device="cuda:0")
+        ge = torch.empty((3, B), dtype=torch.float32, device="cuda:0")
+        avg = fab.rollout_dev(d_rec, N, x_ee=xee, goal_est=ge)
+        torch.cuda.synchronize()
+        assert np.array_equal(host["avg_vel"], avg.cpu().numpy().T, equal_nan=True)
+        assert np.array_equal(host["x_ee"], xee.permute(2, 0, 1).cpu().numpy())
+        assert np.array_equal(host["goal_est"], ge.cpu().numpy().T)
