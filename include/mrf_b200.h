@@ -45,6 +45,7 @@ extern "C" {
 #define MRF_NLINKS 8   /* panda_link1..8, examples/parameters_manipulators.py:25-26 */
 #define MRF_REC 44     /* scalars per robot record */
 #define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
+#define MRF_MAX_SPHERES_PER_LINK 8   /* n_obst_per_link, examples/configs/panda_config.yaml:8 (reference default 4) */
 
 /* Per-robot record = the numeric arguments of one fabric action / of get_velocity_rollouts
  * (forward_planner_Jointspace.py:303-329), fixed order:
@@ -123,6 +124,20 @@ int mrf_kinematics_dev_f64(mrf_handle_t h, const double* q, const double* qdot, 
                            int64_t B, void* stream);
 int mrf_kinematics_dev_f32(mrf_handle_t h, const float* q, const float* qdot, float* x, float* v, float* a,
                            int64_t B, void* stream);
+
+/* Obstacle staging for the executed action (replaces the per-step CasADi / environment calls of
+ * examples/example_pandas_Jointspace.py:324-343,400-412 and multi_robot_fabrics/utils/utils_apply_fk.py:3-33 with the
+ * sphere functions of multi_robot_fabrics/utils/utils.py:87-119): every robot's 8 * n_per_link collision spheres,
+ * sphere s of link l at p_link + R_link * offsets[l][s] (offsets: HOST pointer, [8][n_per_link][3], link frame, see
+ * create_simulation_manipulators.py:188-245), assembled into each ego robot's obstacle list (other robots ascending).
+ *   vel_mode 0: every sphere carries its link ORIGIN's velocity J_link qdot (example_pandas_Jointspace.py:406-410)
+ *   vel_mode 1: true sphere velocity J_sphere qdot (utils.py:109, utils_apply_fk.py:28)
+ *   accelerations are 0, radius = r_robots[j][l]; STATIC_OR_DYN_FABRICS == 0 zeroes the velocities.
+ *   q, qdot [MRF_DOF][R][B] -> obst [8 n (R-1)][MRF_OBST][R][B] (nullable), spheres_x, spheres_v [8 n][3][R][B] (nullable) */
+int mrf_obstacles_dev_f64(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const double* q,
+                          const double* qdot, double* obst, double* spheres_x, double* spheres_v, int64_t B, void* stream);
+int mrf_obstacles_dev_f32(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const float* q,
+                          const float* qdot, float* obst, float* spheres_x, float* spheres_v, int64_t B, void* stream);
 
 /* Batched deadlock_checking step.  All arrays index b fastest; state arrays are updated in place.
  *   x_ee [R][3][B]  goals [R][3][B] (in/out)  weights [R][B] (in/out)

@@ -173,6 +173,21 @@ class Fabrics:
               "mrf_kinematics_dev")
         return x, v, a
 
+    def obstacles_dev(self, q, qdot, n_per_link: int = 1, vel_mode: int = 0, offsets=None, obst=None, spheres_x=None,
+                      spheres_v=None, want_obst: bool = True):
+        """q, qdot (7,R,B) -> obst (8 n (R-1), 10, R, B): the other robots' collision spheres of every ego robot."""
+        import torch
+        from .spheres import sphere_offsets
+        p = self._prec(q)
+        _, R, B = q.shape
+        off = np.ascontiguousarray(sphere_offsets(n_per_link) if offsets is None else offsets, dtype=np.float64)
+        if want_obst and obst is None:
+            obst = torch.empty((8 * n_per_link * (R - 1), OBST, R, B), dtype=q.dtype, device=q.device)
+        fn = getattr(lib(), f"mrf_obstacles_dev_{p}")
+        check(fn(self.handle.ptr, n_per_link, hptr(off), vel_mode, self._tp(q), self._tp(qdot), self._tp(obst),
+                 self._tp(spheres_x), self._tp(spheres_v), B, self._stream()), "mrf_obstacles_dev")
+        return obst
+
     def deadlock_dev(self, x_ee, goals, weights, sm_state, time_step, time_deadlock_out, st_int, st_goal,
                      avg_vel=None, avg_sum=None, flag=None):
         """Batched deadlock_checking step; goals/weights/time_deadlock_out/st_* are updated in place.

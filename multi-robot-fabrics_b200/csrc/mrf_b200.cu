@@ -380,6 +380,87 @@ __global__ void transpose_kernel(const T* __restrict__ in, T* __restrict__ out, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// obstacle staging for the executed action: collision spheres of every robot with per-link offsets
+// (n_obst_per_link spheres per link, offsets in the link frame as placed by
+// examples/simulation_environments/create_simulation_manipulators.py:188-245 and evaluated symbolically by
+// multi_robot_fabrics/utils/utils.py:87-119), assembled per ego robot like
+// examples/example_pandas_Jointspace.py:400-412 / multi_robot_fabrics/utils/utils_apply_fk.py:3-33.
+// thread = (robot j, scenario b): computes robot j's 8n spheres and scatters them into the obstacle lists of every
+// other robot i (block j' = index of j among i's others, ascending).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct SphereOffsets {
+    int n;
+    T t[MRF_NLINKS][MRF_MAX_SPHERES_PER_LINK][3];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kActThreads)
+    obstacles_kernel(const __grid_constant__ DevCfg<T> cfg, const __grid_constant__ SphereOffsets<T> off, int vel_mode,
+                     const T* __restrict__ qin, const T* __restrict__ qdin, T* __restrict__ obst, T* __restrict__ sx,
+                     T* __restrict__ sv, long long B) {
+    const int R = cfg.n_robots, n = off.n;
+    const long long total = (long long)R * B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx / B);
+    const long long b = idx - (long long)j * B;
+    T q[kDof], qd[kDof];
+#pragma unroll
+    for (int i = 0; i < kDof; ++i) {
+        q[i] = qin[(long long)i * total + idx];
+        qd[i] = qdin[(long long)i * total + idx];
+    }
+    const int S = MRF_NLINKS * n * (R - 1);
+    const T vsc = cfg.static_or_dyn ? T(1) : T(0); // STATIC_OR_DYN_FABRICS == 0: zero velocities (:337-338)
+    auto emit = [&](int link, const Frame<T>& f) {
+        for (int s = 0; s < n; ++s) {
+            const T* t = off.t[link][s];
+            V3<T> rt = f.a * t[0] + f.b * t[1] + f.n * t[2];
+            V3<T> xs = f.p + rt;
+            V3<T> vs = vel_mode ? f.v + cross(f.w, rt) : f.v; // 1: J_sphere qdot; 0: link-origin velocity replicated
+            vs = vs * vsc;
+            const int k = link * n + s;
+            if (sx) { sx[((long long)k * 3 + 0) * total + idx] = xs.x; sx[((long long)k * 3 + 1) * total + idx] = xs.y; sx[((long long)k * 3 + 2) * total + idx] = xs.z; }
+            if (sv) { sv[((long long)k * 3 + 0) * total + idx] = vs.x; sv[((long long)k * 3 + 1) * total + idx] = vs.y; sv[((long long)k * 3 + 2) * total + idx] = vs.z; }
+            if (obst) {
+                for (int i = 0; i < R; ++i) {
+                    if (i == j) continue;
+                    const int o = (j - (j > i ? 1 : 0)) * MRF_NLINKS * n + k;
+                    T* p = obst + ((long long)o * MRF_OBST * R + i) * B + b;
+                    const long long st = (long long)R * B;
+                    p[0 * st] = xs.x; p[1 * st] = xs.y; p[2 * st] = xs.z;
+                    p[3 * st] = vs.x; p[4 * st] = vs.y; p[5 * st] = vs.z;
+                    p[6 * st] = T(0); p[7 * st] = T(0); p[8 * st] = T(0); // accelerations are not communicated (:411)
+                    p[9 * st] = (T)cfg.r_link[j][link];
+                }
+            }
+        }
+    };
+    (void)S;
+    Frame<T> f;
+    const T* Rm = cfg.R0[j];
+    f.a = mk(Rm[0], Rm[3], Rm[6]);
+    f.b = mk(Rm[1], Rm[4], Rm[7]);
+    f.n = mk(Rm[2], Rm[5], Rm[8]);
+    f.p = mk(cfg.link1[j][0], cfg.link1[j][1], cfg.link1[j][2]);
+    f.w = mk(T(0), T(0), T(0));
+    f.al = f.w; f.v = f.w; f.ac = f.w;
+    (void)fr_joint<T, 0>(f, q[0], qd[0]);  emit(0, f);
+    (void)fr_joint<T, -1>(f, q[1], qd[1]); emit(1, f);
+    fr_advance(f, f.b * T(-0.316));
+    (void)fr_joint<T, 1>(f, q[2], qd[2]);  emit(2, f);
+    fr_advance(f, f.a * T(0.0825));
+    (void)fr_joint<T, 1>(f, q[3], qd[3]);  emit(3, f);
+    fr_advance(f, f.a * T(-0.0825) + f.b * T(0.384));
+    (void)fr_joint<T, -1>(f, q[4], qd[4]); emit(4, f);
+    (void)fr_joint<T, 1>(f, q[5], qd[5]);  emit(5, f);
+    fr_advance(f, f.a * T(0.088));
+    (void)fr_joint<T, 1>(f, q[6], qd[6]);  emit(6, f);
+    fr_advance(f, f.n * T(0.107));
+    emit(7, f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // FMA peak micro-benchmark: the roofline denominator for the compute-bound rollout (MEASURED_PEAKS.json
 // holds HBM and bf16 tensor peaks only).  8 independent FMA chains per thread.
 // ------------------------------------------------------------------------------------------------
@@ -1155,6 +1236,38 @@ extern "C" int mrf_deadlock_host_f64(mrf_handle_t h, const double* x_ee, double*
         if (flag) flag[b] = qf[b];
     }
     return MRF_OK;
+}
+
+template <typename T>
+static int obstacles_dev(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const T* q, const T* qd,
+                         T* obst, T* sx, T* sv, int64_t B, void* stream) {
+    if (!h || !offsets || !q || !qd) return fail(MRF_EINVAL, "mrf_obstacles: null argument");
+    if (B <= 0 || n_per_link < 1 || n_per_link > MRF_MAX_SPHERES_PER_LINK)
+        return fail(MRF_EINVAL, "mrf_obstacles: n_per_link must be 1..MRF_MAX_SPHERES_PER_LINK");
+    if (obst && h->cfg.n_robots < 2) return fail(MRF_EINVAL, "mrf_obstacles: obstacle lists need at least 2 robots");
+    MRF_CUDA(cudaSetDevice(h->device));
+    SphereOffsets<T> off;
+    memset(&off, 0, sizeof(off));
+    off.n = n_per_link;
+    for (int l = 0; l < MRF_NLINKS; ++l)
+        for (int s = 0; s < n_per_link; ++s)
+            for (int k = 0; k < 3; ++k) off.t[l][s][k] = (T)offsets[((size_t)l * n_per_link + s) * 3 + k];
+    const long long total = (long long)h->cfg.n_robots * B;
+    obstacles_kernel<T><<<(unsigned)((total + kActThreads - 1) / kActThreads), kActThreads, 0, (cudaStream_t)stream>>>(
+        devcfg<T>(h), off, vel_mode, q, qd, obst, sx, sv, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+extern "C" int mrf_obstacles_dev_f64(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const double* q,
+                                     const double* qdot, double* obst, double* spheres_x, double* spheres_v, int64_t B,
+                                     void* stream) {
+    return obstacles_dev<double>(h, n_per_link, offsets, vel_mode, q, qdot, obst, spheres_x, spheres_v, B, stream);
+}
+extern "C" int mrf_obstacles_dev_f32(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const float* q,
+                                     const float* qdot, float* obst, float* spheres_x, float* spheres_v, int64_t B,
+                                     void* stream) {
+    return obstacles_dev<float>(h, n_per_link, offsets, vel_mode, q, qdot, obst, spheres_x, spheres_v, B, stream);
 }
 
 template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {

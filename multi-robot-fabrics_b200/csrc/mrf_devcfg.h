@@ -31,6 +31,7 @@ template <typename T> inline void fill_devcfg(const MrfConfig& c, DevCfg<T>& d) 
         d.link1[r][0] = (T)(M[3] + R[2] * 0.333);
         d.link1[r][1] = (T)(M[7] + R[5] * 0.333);
         d.link1[r][2] = (T)(M[11] + R[8] * 0.333);
+        for (int l = 0; l < MRF_NLINKS; ++l) d.r_link[r][l] = (T)c.r_robots[r][l];
     }
     for (int r = 0; r < c.n_robots; ++r) {
         const int la[kPts] = {2, 3, 4, 6, 7, 0}, lb[kPts] = {-1, -1, 5, -1, -1, 1}; // link indices sharing each point

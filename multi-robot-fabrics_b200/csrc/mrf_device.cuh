@@ -151,6 +151,7 @@ template <typename T> struct DevCfg {
     T p0[MRF_MAX_ROBOTS][3];   // mount translation
     T link1[MRF_MAX_ROBOTS][3]; // constant origin of panda_link1 == panda_link2
     T lim[kDof][2];
+    T r_link[MRF_MAX_ROBOTS][MRF_NLINKS]; // sphere radius of each link as seen by the other robots
     // spheres robot r sees in a coupled rollout, flattened over the other robots (ascending) and their distinct
     // points with multiplicity: link1==link2 and link5==link6 share a point and are merged into one entry of weight
     // 2 when their radii agree.  ent_off = kinematics-table offset (point * 9 * NT + other_robot * 32).

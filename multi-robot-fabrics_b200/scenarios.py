@@ -92,9 +92,13 @@ def generate(n: int, n_robots: int, seed: int = 0, min_clearance: float = 0.25, 
     rng = np.random.Generator(np.random.PCG64(seed))
     out = np.zeros((n, n_robots, REC))
     have = 0
+    drawn = 0
     while have < n:
         m = max(256, int((n - have) * 2.0))
         rec = _draw(rng, m, n_robots, weight_goal_1)
+        drawn += m
+        if drawn > 200 * n + 100000 and have < 0.01 * drawn:
+            raise ValueError(f"min_clearance={min_clearance} rejects (almost) every scenario (accepted {have} of {drawn})")
         ok = clearance(rec) >= min_clearance
         rec = rec[ok][: n - have]
         out[have:have + len(rec)] = rec

@@ -79,6 +79,8 @@ void mrfo_config_default(mrfo_config* c, int n_robots) {
 /* Kinematics.  Frame i = panda_link(i+1).  p[i] origin, z[i] joint axis (world), explicit J.  */
 /* ------------------------------------------------------------------------------------------- */
 typedef struct {
+    double Rl[8][9];   /* rotation of the link frames link1..8 (after the joint rotation; link8 = link7) */
+    double wl[8][3];   /* angular velocity of the links */
     double p[8][3];    /* link origins link1..8 */
     double z[7][3];    /* joint axes */
     double R7[9];      /* rotation of link7 frame */
@@ -120,7 +122,11 @@ static void kinematics(const double T0[16], const double* q, const double* qd, k
             al[a] += wz[a];
             w[a] += zq[a];
         }
+        memcpy(k->Rl[i], R, sizeof(R));
+        memcpy(k->wl[i], w, sizeof(w));
     }
+    memcpy(k->Rl[7], R, sizeof(R));
+    memcpy(k->wl[7], w, sizeof(w));
     memcpy(k->R7, R, sizeof(R));
     { /* link8 = link7 + R7 (0,0,0.107) */
         double r[3] = {R[2] * LINK8_Z, R[5] * LINK8_Z, R[8] * LINK8_Z}, t[3], u[3], wt[3];
@@ -442,6 +448,27 @@ int mrfo_rollout_cartesian(const mrfo_config* c, int robot, const double* rec_in
     }
     if (avg_vel) *avg_vel = acc / ((double)N * DOF);
     return rc;
+}
+
+/* Collision spheres with link-frame offsets (utils.py:87-119 with the transformations of
+ * create_simulation_manipulators.py:188-245): x = p_link + R_link t, v_sphere = v_link + omega_link x (R_link t),
+ * v_origin = J_link qdot. off [8][n][3]; outputs [8 n][3]. */
+void mrfo_spheres(const mrfo_config* c, int robot, const double* q, const double* qd, int n, const double* off,
+                  double* x, double* v_origin, double* v_sphere) {
+    kin_t k;
+    kinematics(c->mount[robot], q, qd, &k);
+    for (int l = 0; l < 8; l++)
+        for (int s = 0; s < n; s++) {
+            const double* t = off + ((size_t)l * n + s) * 3;
+            double rt[3], wr[3];
+            for (int a = 0; a < 3; a++) rt[a] = k.Rl[l][3 * a] * t[0] + k.Rl[l][3 * a + 1] * t[1] + k.Rl[l][3 * a + 2] * t[2];
+            cross(k.wl[l], rt, wr);
+            for (int a = 0; a < 3; a++) {
+                x[(l * n + s) * 3 + a] = k.p[l][a] + rt[a];
+                v_origin[(l * n + s) * 3 + a] = k.v[l][a];
+                v_sphere[(l * n + s) * 3 + a] = k.v[l][a] + wr[a];
+            }
+        }
 }
 
 int mrfo_max_threads(void) {

@@ -77,6 +77,11 @@ int mrfo_action_batch(const mrfo_config* c, int robot, const double* rec, long b
 void mrfo_endeffector(const mrfo_config* c, int robot, const double* q, const double* qd, int use_jqd,
                       double x_ee[3], double v_ee[3]);
 
+/* Collision spheres with link-frame offsets off[8][n][3] (utils.py:87-119, create_simulation_manipulators.py:188-245):
+ * x, v_origin (= J_link qdot), v_sphere (= J_sphere qdot), each [8 n][3]. */
+void mrfo_spheres(const mrfo_config* c, int robot, const double* q, const double* qd, int n, const double* off,
+                  double* x, double* v_origin, double* v_sphere);
+
 int mrfo_max_threads(void);
 
 #ifdef __cplusplus

@@ -491,6 +491,21 @@ def link_kinematics(q, qdot, mount, link: str, jdot_ref_sign: float = -1.0):
     return fkl(q).numpy().copy(), (J @ qdot).numpy().copy(), Jdq.numpy().copy(), J.numpy().copy()
 
 
+def sphere_kinematics(q, qdot, mount, link: str, t_link):
+    """UtilsKinematics.define_symbolic_collision_link_poses (utils.py:99-114): position of the sphere
+    fk(child=link, link_transformation=T)[0:3, 3] and its velocity jacobian(fk) @ qdot."""
+    t = lambda v: torch.as_tensor(np.asarray(v, dtype=np.float64), dtype=F64).reshape(-1)
+    q, qdot, tl = t(q), t(qdot), t(t_link)
+    idx = int(link[len("panda_link"):]) - 1
+
+    def fks(qq):
+        T = panda_link_frames(qq, mount)[idx]
+        return T[:3, 3] + T[:3, :3] @ tl
+
+    J = jacrev(fks)(q)
+    return fks(q).numpy().copy(), (J @ qdot).numpy().copy()
+
+
 # --------------------------------------------------------------------------- #
 # Rollouts
 # --------------------------------------------------------------------------- #

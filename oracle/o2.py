@@ -54,6 +54,7 @@ def lib():
         _lib.mrfo_rollout_cartesian.argtypes = [cp, C.c_int, d, C.c_int, d, d, d, C.c_int, d, d, d]
         _lib.mrfo_rollout_jointspace_batch.argtypes = [cp, d, C.c_long, C.c_int, d, d, d, d, C.c_int]
         _lib.mrfo_action_batch.argtypes = [cp, C.c_int, d, C.c_long, C.c_int, d, d, d, d, d, C.c_int]
+        _lib.mrfo_spheres.argtypes = [cp, C.c_int, d, d, C.c_int, d, d, d, d]
         _lib.mrfo_max_threads.restype = C.c_int
     return _lib
 
@@ -142,6 +143,56 @@ def rollout_cartesian(cfg, robot, rec, xo, vo, ro, N):
     lib().mrfo_rollout_cartesian(C.byref(cfg), robot, _p(rec), ro.shape[0], _p(xo), _p(vo), _p(ro), N, _p(qN),
                                  _p(qdN), _p(avg))
     return qN, qdN, float(avg[0])
+
+
+def sphere_offsets_ref(n: int) -> np.ndarray:
+    """Oracle-side restatement of create_simulation_manipulators.py:188-245 -> (8, n, 3) link-frame offsets."""
+    length = [0.333, 0.2, 0.3164, 0.2, 0.3840, 0.2, 0.088, 0.2]
+    off = np.zeros((8, n, 3))
+    for idx in range(8):
+        z_start = length[idx] if idx % 2 == 0 else length[idx] / 2     # 'linear' / 'rotational' alternate (:193)
+        for i in range(n):
+            tr = np.array([0.0, 0.0, -z_start + i * length[idx] / n])
+            if idx == 7:          # env link 16 == panda_joint8
+                if i == 1:
+                    tr = np.array([0.03, 0.03, -z_start + (i + 1) * length[idx] / n])
+                elif i == 2:
+                    tr[0:2] = [-0.03, -0.03]
+            if idx == 4 and i in (2, 3):   # env link 11 == panda_joint5
+                tr[0:2] = [0.0, 0.02 if i == 2 else 0.06]
+            off[idx, i] = tr
+    return off
+
+
+def spheres(cfg, robot, q, qd, off):
+    """-> x, v_origin, v_sphere, each (8 n, 3)."""
+    q, qd, off = _c(q), _c(qd), _c(off)
+    n = off.shape[1]
+    x, vo, vs = np.zeros((8 * n, 3)), np.zeros((8 * n, 3)), np.zeros((8 * n, 3))
+    lib().mrfo_spheres(C.byref(cfg), robot, _p(q), _p(qd), n, _p(off), _p(x), _p(vo), _p(vs))
+    return x, vo, vs
+
+
+def obstacle_lists(cfg, q, qd, off, vel_mode=0, static_or_dyn=1):
+    """q, qd (R,7) -> per ego robot the (8 n (R-1), 10) obstacle records assembled as
+    example_pandas_Jointspace.py:400-412 (vel_mode 0) / utils_apply_fk.py:3-33 (vel_mode 1) do."""
+    R = cfg.n_robots
+    n = off.shape[1]
+    per = [spheres(cfg, j, q[j], qd[j], off) for j in range(R)]
+    out = []
+    for i in range(R):
+        rows = []
+        for j in range(R):
+            if j == i:
+                continue
+            x, vo, vs = per[j]
+            o = np.zeros((8 * n, 10))
+            o[:, 0:3] = x
+            o[:, 3:6] = (vs if vel_mode else vo) * (1.0 if static_or_dyn else 0.0)
+            o[:, 9] = np.repeat(np.array(cfg.r_robots[j][:]), n)
+            rows.append(o)
+        out.append(np.concatenate(rows))
+    return out
 
 
 def max_threads() -> int:

@@ -225,3 +225,62 @@ def test_host_api_pipelined_large_batch(fabs):
         assert np.array_equal(host["avg_vel"], avg.cpu().numpy().T, equal_nan=True)
         assert np.array_equal(host["x_ee"], xee.permute(2, 0, 1).cpu().numpy())
         assert np.array_equal(host["goal_est"], ge.cpu().numpy().T)
+
+
+@pytest.mark.parametrize("R,n,vel_mode,sd", [(2, 4, 0, 1), (3, 4, 1, 1), (2, 1, 0, 0), (3, 2, 1, 1)])
+def test_obstacle_staging_matches_oracle(fabs, R, n, vel_mode, sd):
+    """mrf_obstacles: other robots' collision spheres with n_obst_per_link offsets, assembled per ego robot."""
+    import torch
+    from multi_robot_fabrics_b200.spheres import sphere_offsets
+    B = 37
+    rec = m.scenarios.generate(B, R, seed=61)
+    fab = get_fab(fabs, R, static_or_dyn=sd)
+    q = torch.from_numpy(np.ascontiguousarray(rec[:, :, 0:7].transpose(2, 1, 0))).to("cuda:0")
+    qd = torch.from_numpy(np.ascontiguousarray(rec[:, :, 7:14].transpose(2, 1, 0))).to("cuda:0")
+    sx = torch.empty((8 * n, 3, R, B), dtype=torch.float64, device="cuda:0")
+    sv = torch.empty((8 * n, 3, R, B), dtype=torch.float64, device="cuda:0")
+    obst = fab.obstacles_dev(q, qd, n_per_link=n, vel_mode=vel_mode, spheres_x=sx, spheres_v=sv)
+    torch.cuda.synchronize()
+    got = obst.permute(3, 2, 0, 1).cpu().numpy()                    # B,R,S,10
+    ocfg = o2.default_config(R)
+    off = sphere_offsets(n)
+    for b in range(0, B, 6):
+        ref = o2.obstacle_lists(ocfg, rec[b, :, 0:7], rec[b, :, 7:14], off, vel_mode=vel_mode, static_or_dyn=sd)
+        for i in range(R):
+            assert np.abs(got[b, i] - ref[i]).max() < 1e-12
+        x, vo, vs = o2.spheres(ocfg, R - 1, rec[b, R - 1, 0:7], rec[b, R - 1, 7:14], off)
+        assert np.abs(sx[:, :, R - 1, b].cpu().numpy() - x).max() < 1e-12
+        assert np.abs(sv[:, :, R - 1, b].cpu().numpy() - (vs if vel_mode else vo) * sd).max() < 1e-12
+
+
+@pytest.mark.parametrize("R,n", [(2, 4), (3, 4)])
+def test_mrdf_control_step_configs_c2_c4(fabs, R, n):
+    """BASELINE configs C2 / C4: one MRDF control step entirely on the GPU -- obstacle staging (n = 4 spheres per
+    link: S = 32 for 2 Pandas, 64 for 3) feeding the executed action (weight_goal_1 = 20) -- against the oracle."""
+    import torch
+    from multi_robot_fabrics_b200.spheres import sphere_offsets
+    B = 48
+    rec = m.scenarios.generate(B, R, seed=62, weight_goal_1=20.0)
+    fab = get_fab(fabs, R)
+    d_rec = torch.from_numpy(to_soa(rec)).to("cuda:0")
+    obst = fab.obstacles_dev(d_rec[0:7].contiguous(), d_rec[7:14].contiguous(), n_per_link=n, vel_mode=0)
+    act = fab.action_dev(d_rec, obst)
+    torch.cuda.synchronize()
+    assert obst.shape[0] == 8 * n * (R - 1)
+    got = act.permute(2, 1, 0).cpu().numpy()
+    ocfg = o2.default_config(R)
+    off = sphere_offsets(n)
+    n_ok = 0
+    for b in range(B):
+        lists = o2.obstacle_lists(ocfg, rec[b, :, 0:7], rec[b, :, 7:14], off, vel_mode=0)
+        for i in range(R):
+            o = lists[i]
+            try:
+                ref = o2.action(ocfg, i, rec[b, i], o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+            except FloatingPointError:
+                continue
+            if not np.isfinite(ref).all() or np.abs(ref).max() > 5:
+                continue
+            n_ok += 1
+            assert np.abs(got[b, i] - ref).max() < F64_RTOL * max(1.0, np.abs(ref).max())
+    assert n_ok > 0.7 * B * R

@@ -134,3 +134,32 @@ def test_deadlock_restatement_matches_live_reference():
             gm, wm, tdo_m, _ = mine.step(x, goals, w, t, tdo_m, avg, st)
             assert np.array_equal(np.array(gr, dtype=float), np.array(gm)) and tdo_r == tdo_m
             assert [float(v) for v in wr] == [float(v) for v in wm]
+
+
+def test_sphere_offsets_and_sphere_kinematics(built):
+    """Row 4 of the scope table: collision spheres with per-link offsets (create_simulation_manipulators.py:188-245,
+    utils.py:87-119).  The package's offset table equals the oracle's restatement of the placement rule, and the
+    closed-form sphere kinematics (O2) equal the autodiff ones (O1)."""
+    from multi_robot_fabrics_b200.spheres import sphere_offsets
+    from oracle import o1_fabrics as o1
+    for n in (1, 2, 4, 5):
+        assert np.array_equal(sphere_offsets(n), o2.sphere_offsets_ref(n))
+    off4 = sphere_offsets(4)
+    assert np.allclose(off4[0, :, 2], [-0.333, -0.24975, -0.1665, -0.08325])        # linear link: starts one length below
+    assert np.allclose(off4[1, :, 2], [-0.1, -0.05, 0.0, 0.05])                      # rotational link: half a length
+    assert np.allclose(off4[7, 1], [0.03, 0.03, 0.0]) and np.allclose(off4[7, 2], [-0.03, -0.03, 0.0])
+    assert np.allclose(off4[4, 2], [0.0, 0.02, -0.192]) and np.allclose(off4[4, 3], [0.0, 0.06, -0.096])
+    cfg = o2.default_config(3)
+    rng = np.random.default_rng(0)
+    q, qd = rng.uniform(-1, 1, 7), rng.uniform(-1, 1, 7)
+    q[3] = -1.5
+    off = sphere_offsets(2)
+    x, vo, vs = o2.spheres(cfg, 2, q, qd, off)
+    xl, vl, _, _ = o2.kinematics(cfg, 2, q, qd)
+    for l in (0, 1, 4, 7):
+        for s in range(2):
+            xx, vv = o1.sphere_kinematics(q, qd, o2.mount_of(cfg, 2), f"panda_link{l + 1}", off[l, s])
+            assert np.abs(xx - x[l * 2 + s]).max() < 1e-14 and np.abs(vv - vs[l * 2 + s]).max() < 1e-14
+            assert np.array_equal(vo[l * 2 + s], vl[l])
+    x1, _, _ = o2.spheres(cfg, 2, q, qd, np.zeros((8, 1, 3)))
+    assert np.abs(x1 - xl).max() < 1e-15                                             # zero offsets = link origins
