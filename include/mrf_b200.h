@@ -139,6 +139,20 @@ int mrf_obstacles_dev_f64(mrf_handle_t h, int n_per_link, const double* offsets,
 int mrf_obstacles_dev_f32(mrf_handle_t h, int n_per_link, const double* offsets, int vel_mode, const float* q,
                           const float* qdot, float* obst, float* spheres_x, float* spheres_v, int64_t B, void* stream);
 
+/* Point-mass planner of BASELINE config C1 (examples/example_pointmasses_static.py:102-129,191-199 and
+ * examples/example_pointmasses_dynamic.py:102-131,192-212): planner.compute_action for the 3-dof (x, y, theta) point
+ * robot with Ss static spheres, Sd dynamic 2-D spheres and one 2-D goal, mode 'acc'.  Uses eps / jdot_sign / exec_scale
+ * of the handle's MrfConfig.  Device layouts (b fastest):
+ *   rec [10][B]: q[3], qdot[3], x_goal_0[2], weight_goal_0, radius_body_base_link
+ *   stat [Ss][4][B]: x_obst[3], radius_obst       dyn [Sd][7][B]: x[2], xdot[2], xddot[2], radius      action [3][B]
+ * Host layouts: rec [B][10], stat [B][Ss][4], dyn [B][Sd][7], action [B][3]. */
+int mrf_point_action_dev_f64(mrf_handle_t h, const double* rec, int Ss, const double* stat, int Sd, const double* dyn,
+                             double* action, int64_t B, void* stream);
+int mrf_point_action_dev_f32(mrf_handle_t h, const float* rec, int Ss, const float* stat, int Sd, const float* dyn,
+                             float* action, int64_t B, void* stream);
+int mrf_point_action_host_f64(mrf_handle_t h, const double* rec, int Ss, const double* stat, int Sd, const double* dyn,
+                              double* action, int64_t B);
+
 /* Batched deadlock_checking step.  All arrays index b fastest; state arrays are updated in place.
  *   x_ee [R][3][B]  goals [R][3][B] (in/out)  weights [R][B] (in/out)
  *   exactly one of: avg_vel [R][B] (per-robot rollout averages; the kernel forms sum/R as

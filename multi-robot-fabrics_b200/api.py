@@ -188,6 +188,19 @@ class Fabrics:
                  self._tp(spheres_x), self._tp(spheres_v), B, self._stream()), "mrf_obstacles_dev")
         return obst
 
+    def point_action_dev(self, rec, stat=None, dyn=None, action=None):
+        """Point-mass planner (config C1): rec (10,B), stat (Ss,4,B), dyn (Sd,7,B) -> action (3,B)."""
+        import torch
+        p = self._prec(rec)
+        B = rec.shape[-1]
+        if action is None:
+            action = torch.empty((3, B), dtype=rec.dtype, device=rec.device)
+        fn = getattr(lib(), f"mrf_point_action_dev_{p}")
+        check(fn(self.handle.ptr, self._tp(rec), 0 if stat is None else stat.shape[0], self._tp(stat),
+                 0 if dyn is None else dyn.shape[0], self._tp(dyn), self._tp(action), B, self._stream()),
+              "mrf_point_action_dev")
+        return action
+
     def deadlock_dev(self, x_ee, goals, weights, sm_state, time_step, time_deadlock_out, st_int, st_goal,
                      avg_vel=None, avg_sum=None, flag=None):
         """Batched deadlock_checking step; goals/weights/time_deadlock_out/st_* are updated in place.

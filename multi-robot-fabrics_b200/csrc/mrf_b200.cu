@@ -461,6 +461,85 @@ __global__ void __launch_bounds__(kActThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// point-mass planner (BASELINE config C1): examples/example_pointmasses_static.py:102-129,
+// examples/example_pointmasses_dynamic.py:102-131.  3 dof (x, y, theta); collision link base_link at (x, y, 0.05)
+// (pointRobot1.urdf:91-113); collision_geometry "-2/x xdot^2", collision_finsler "1/x^2 (1 - heaviside(xdot)) xdot^2";
+// one 2-D attractor; no limits; mode 'acc'.  thread = scenario (one robot each).
+//   rec [10][B]: q[3], qdot[3], x_goal_0[2], weight_goal_0, radius_body_base_link
+//   stat [Ss][4][B]: x[3], radius          dyn [Sd][7][B]: x[2], xdot[2], xddot[2], radius
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kActThreads)
+    point_action_kernel(T eps, T sigma, T s2, const T* __restrict__ rec, int Ss, const T* __restrict__ stat, int Sd,
+                        const T* __restrict__ dyn, T* __restrict__ action, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    auto ld = [&](int f) { return rec[(long long)f * B + b]; };
+    const T qx = ld(0), qy = ld(1), vx = ld(3), vy = ld(4), vth = ld(5);
+    const T gx = ld(6), gy = ld(7), wg = ld(8), rb = ld(9);
+    T m00 = T(0.2), m01 = T(0), m11 = T(0.2), f0 = T(0), f1 = T(0), num = T(0);
+    for (int o = 0; o < Ss + Sd; ++o) {
+        T dx, dy, dz, wx, wy, ax = T(0), ay = T(0), rho;
+        if (o < Ss) {
+            const T* p = stat + (long long)o * 4 * B + b;
+            dx = qx - p[0]; dy = qy - p[B]; dz = T(0.05) - p[2 * B];
+            wx = vx; wy = vy;
+            rho = p[3 * B] + rb;
+        } else {
+            const T* p = dyn + (long long)(o - Ss) * 7 * B + b;
+            dx = qx - p[0]; dy = qy - p[B]; dz = T(0);
+            wx = vx - p[2 * B]; wy = vy - p[3 * B];
+            ax = p[4 * B]; ay = p[5 * B];
+            rho = p[6 * B] + rb;
+        }
+        const T n2 = dx * dx + dy * dy + dz * dz;
+        const T in1 = Mth<T>::rsqrt(n2), n = n2 * in1;
+        const T t = n - rho, nr = n * rho, u = Mth<T>::rcp(nr * t);
+        const T gs = u * t, ix = (u * nr) * rho;         // 1/(n rho), 1/x
+        const T dw = dx * wx + dy * wy, ww = wx * wx + wy * wy;
+        const T xd = dw * gs;
+        const T kappa = (ww - dw * dw * (in1 * in1)) * gs;
+        const T s = xd < T(0) ? T(1) : (xd > T(0) ? T(0) : T(0.5)); // 1 - heaviside(xdot)
+        const T Ml = T(2) * s * ix * ix;
+        const T fel = T(-2) * s * xd * xd * ix * ix * ix;
+        const T fl = Ml * (T(-2) * ix * xd * xd);
+        const T acc_o = (dx * ax + dy * ay) * gs;
+        const T fq = fl + Ml * (sigma * kappa - acc_o), feq = fel + Ml * (kappa - acc_o);
+        const T g0 = dx * gs, g1 = dy * gs;
+        f0 += g0 * fq; f1 += g1 * fq;
+        m00 += Ml * g0 * g0; m01 += Ml * g0 * g1; m11 += Ml * g1 * g1;
+        num += (g0 * vx + g1 * vy) * (fq - feq);
+    }
+    const T xg0 = qx - gx, xg1 = qy - gy;
+    const T ng = Mth<T>::sqrt(xg0 * xg0 + xg1 * xg1);
+    T dpsi, mm;
+    attractor_scalars(ng, wg, dpsi, mm);
+    const T ff0 = f0 + mm * dpsi * xg0 * Mth<T>::rcp(ng), ff1 = f1 + mm * dpsi * xg1 * Mth<T>::rcp(ng);
+    auto solve2 = [&](T a00, T a01, T a11, T b0, T b1, T& h0, T& h1) {
+        a00 += eps; a11 += eps;
+        const T idet = Mth<T>::rcp(a00 * a11 - a01 * a01);
+        h0 = (a11 * b0 - a01 * b1) * idet;
+        h1 = (a00 * b1 - a01 * b0) * idet;
+    };
+    T hg0, hg1, hf0, hf1;
+    solve2(m00, m01, m11, f0, f1, hg0, hg1);
+    solve2(m00 + mm, m01, m11 + mm, ff0, ff1, hf0, hf1);
+    const T qMq = m00 * vx * vx + T(2) * m01 * vx * vy + m11 * vy * vy + T(0.2) * vth * vth;
+    const T qq = vx * vx + vy * vy + vth * vth;
+    const T a_geom = -num * Mth<T>::rcp(eps + qMq);
+    const T iden = Mth<T>::rcp(eps + s2 * qq);
+    const T a_ex0 = -s2 * (vx * hg0 + vy * hg1) * iden, a_exf = -s2 * (vx * hf0 + vy * hf1) * iden;
+    const T eta = T(0.5) * (Mth<T>::tanh(T(-0.45) * qq - T(0.5)) + T(1));
+    const T a_ex = eta * a_ex0 + (T(1) - eta) * a_exf;
+    const T beta = T(0.5) * (Mth<T>::tanh(T(-0.5) * (ng - T(0.02))) + T(1)) * T(6.5) + T(0.01) +
+                   Mth<T>::max(T(0), a_geom - a_ex);
+    const T damp = a_ex + beta;
+    action[b] = -hf0 - damp * vx;
+    action[B + b] = -hf1 - damp * vy;
+    action[2 * B + b] = -damp * vth;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FMA peak micro-benchmark: the roofline denominator for the compute-bound rollout (MEASURED_PEAKS.json
 // holds HBM and bf16 tensor peaks only).  8 independent FMA chains per thread.
 // ------------------------------------------------------------------------------------------------
@@ -1268,6 +1347,48 @@ extern "C" int mrf_obstacles_dev_f32(mrf_handle_t h, int n_per_link, const doubl
                                      const float* qdot, float* obst, float* spheres_x, float* spheres_v, int64_t B,
                                      void* stream) {
     return obstacles_dev<float>(h, n_per_link, offsets, vel_mode, q, qdot, obst, spheres_x, spheres_v, B, stream);
+}
+
+template <typename T>
+static int point_action_dev(mrf_handle_t h, const T* rec, int Ss, const T* stat, int Sd, const T* dyn, T* action, int64_t B,
+                            void* stream) {
+    if (!h || !rec || !action || (Ss > 0 && !stat) || (Sd > 0 && !dyn)) return fail(MRF_EINVAL, "mrf_point_action: null argument");
+    if (B <= 0 || Ss < 0 || Sd < 0) return fail(MRF_EINVAL, "mrf_point_action: bad sizes");
+    MRF_CUDA(cudaSetDevice(h->device));
+    point_action_kernel<T><<<(unsigned)((B + kActThreads - 1) / kActThreads), kActThreads, 0, (cudaStream_t)stream>>>(
+        (T)h->cfg.eps, (T)h->cfg.jdot_sign, (T)(2.0 * h->cfg.exec_scale), rec, Ss, stat, Sd, dyn, action, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+extern "C" int mrf_point_action_dev_f64(mrf_handle_t h, const double* rec, int Ss, const double* stat, int Sd,
+                                        const double* dyn, double* action, int64_t B, void* stream) {
+    return point_action_dev<double>(h, rec, Ss, stat, Sd, dyn, action, B, stream);
+}
+extern "C" int mrf_point_action_dev_f32(mrf_handle_t h, const float* rec, int Ss, const float* stat, int Sd,
+                                        const float* dyn, float* action, int64_t B, void* stream) {
+    return point_action_dev<float>(h, rec, Ss, stat, Sd, dyn, action, B, stream);
+}
+// host variant: rec [B][10], stat [B][Ss][4], dyn [B][Sd][7] -> action [B][3]
+extern "C" int mrf_point_action_host_f64(mrf_handle_t h, const double* rec, int Ss, const double* stat, int Sd,
+                                         const double* dyn, double* action, int64_t B) {
+    if (!h || !rec || !action || (Ss > 0 && !stat) || (Sd > 0 && !dyn)) return fail(MRF_EINVAL, "mrf_point_action_host: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_point_action_host: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    int rc = upload_soa<double>(h, rec, B, 10, 0, 1);
+    if (rc) return rc;
+    if (Ss > 0) { rc = upload_soa<double>(h, stat, B, Ss * 4, 2, 3); if (rc) return rc; }
+    if (Sd > 0) { rc = upload_soa<double>(h, dyn, B, Sd * 7, 4, 5); if (rc) return rc; }
+    rc = stage_reserve(h, 6, sizeof(double) * (size_t)B * 3);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = point_action_dev<double>(h, (const double*)h->stage[1], Ss, (const double*)h->stage[3], Sd,
+                                  (const double*)h->stage[5], (double*)h->stage[6], B, h->stream);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    rc = download_aos<double>(h, action, B, 3, 6, 7);
+    if (rc) return rc;
+    return finish_timed(h);
 }
 
 template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {

@@ -147,6 +147,53 @@ def set_planner_panda(degrees_of_freedom: int = 7, nr_obst=0, nr_obst_dyn=1, col
     return PandaFabricPlanner(mount, nr_obst, nr_obst_dyn, list(collision_links_nr), i_robot, device, dtype=dtype), PandaGoal()
 
 
+class PointFabricPlanner:
+    """compute_action drop-in for set_planner_point (examples/example_pointmasses_static.py:102-129,
+    examples/example_pointmasses_dynamic.py:102-131): 3-dof point robot, mode 'acc'."""
+
+    def __init__(self, n_obstacles: int, n_dyn_obstacles: int = 0, device: int = 0):
+        self.n_obst, self.n_dyn = int(n_obstacles), int(n_dyn_obstacles)
+        self.fab = Fabrics(config=default_config(1), device=device)
+
+    def _pack(self, kw: dict):
+        rec = np.zeros((1, 10))
+        rec[0, 0:3] = _vec(kw["q"], 3)
+        rec[0, 3:6] = _vec(kw["qdot"], 3)
+        rec[0, 6:8] = _vec(kw["x_goal_0"], 2)
+        rec[0, 8] = float(np.asarray(kw["weight_goal_0"]).reshape(-1)[0])
+        rec[0, 9] = float(np.asarray(kw["radius_body_base_link"]).reshape(-1)[0])
+        stat = np.zeros((1, self.n_obst, 4))
+        for i in range(self.n_obst):
+            x = kw[f"x_obst_{i}"] if f"x_obst_{i}" in kw else kw["x_obsts"][i]
+            r = kw[f"radius_obst_{i}"] if f"radius_obst_{i}" in kw else kw["radius_obsts"][i]
+            stat[0, i, 0:3] = _vec(x, 3)
+            stat[0, i, 3] = float(np.asarray(r).reshape(-1)[0])
+        dyn = np.zeros((1, self.n_dyn, 7))
+        for i in range(self.n_dyn):
+            get = lambda single, plural: kw[f"{single}_{i}"] if f"{single}_{i}" in kw else kw[plural][i]
+            dyn[0, i, 0:2] = _vec(get("x_obst_dynamic", "x_obsts_dynamic"))[0:2]
+            dyn[0, i, 2:4] = _vec(get("xdot_obst_dynamic", "xdot_obsts_dynamic"))[0:2]
+            dyn[0, i, 4:6] = _vec(get("xddot_obst_dynamic", "xddot_obsts_dynamic"))[0:2]
+            dyn[0, i, 6] = float(np.asarray(get("radius_obst_dynamic", "radius_obsts_dynamic")).reshape(-1)[0])
+        return rec, stat, dyn
+
+    def compute_action(self, **kwargs) -> np.ndarray:
+        rec, stat, dyn = self._pack(kwargs)
+        act = np.empty((1, 3))
+        check(lib().mrf_point_action_host_f64(self.fab.handle.ptr, hptr(rec), self.n_obst, hptr(stat) if self.n_obst else None,
+                                              self.n_dyn, hptr(dyn) if self.n_dyn else None, hptr(act), 1),
+              "mrf_point_action_host")
+        a = act[0]
+        if np.linalg.norm(a) < 1e-6:
+            a = a * 0.0
+        return a
+
+
+def set_planner_point(goal=None, n_obstacles: int = 2, n_dyn_obstacles: int = 0, device: int = 0):
+    """Same role as the reference's set_planner_point (the URDF and the geometry strings are compiled in)."""
+    return PointFabricPlanner(n_obstacles, n_dyn_obstacles, device)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class ForwardFabricsPlanner:
     """Coupled joint-space Rollout Fabrics (forward_planner_Jointspace.py)."""

@@ -471,6 +471,77 @@ void mrfo_spheres(const mrfo_config* c, int robot, const double* q, const double
         }
 }
 
+/* Point-mass planner of examples/example_pointmasses_static.py:102-129 / _dynamic.py:102-131: 3 dof (x, y, theta),
+ * collision link base_link at fk = (x, y, 0.05) (pointRobot1.urdf:91-113), collision_geometry "-2/x xdot^2",
+ * collision_finsler "1/x^2 (1 - heaviside(xdot)) xdot^2", one 2-D attractor on (x, y), no limits, mode 'acc'.
+ * static spheres xs [Ss][3], rs [Ss]; dynamic spheres (2-D) xd, vd, ad [Sd][2], rd [Sd]. */
+int mrfo_point_action(const mrfo_config* c, const double* q, const double* qd, const double* goal, double w_goal,
+                      double r_body, int Ss, const double* xs, const double* rs, int Sd, const double* xd,
+                      const double* vd, const double* ad, const double* rd, double* action) {
+    const double sigma = c->jdot_sign, e = c->eps;
+    double M[2][2] = {{0.2, 0.0}, {0.0, 0.2}}, f[2] = {0, 0}, num = 0; /* theta decouples: M33 = 0.2, f3 = 0 */
+    for (int o = 0; o < Ss + Sd; o++) {
+        const int dyn = o >= Ss;
+        const int k = dyn ? o - Ss : o;
+        double d[3], w[3], ao[3] = {0, 0, 0}, rho;
+        if (!dyn) {
+            d[0] = q[0] - xs[3 * k]; d[1] = q[1] - xs[3 * k + 1]; d[2] = 0.05 - xs[3 * k + 2];
+            w[0] = qd[0]; w[1] = qd[1]; w[2] = 0.0;
+            rho = rs[k] + r_body;
+        } else {
+            d[0] = q[0] - xd[2 * k]; d[1] = q[1] - xd[2 * k + 1]; d[2] = 0.0;
+            w[0] = qd[0] - vd[2 * k]; w[1] = qd[1] - vd[2 * k + 1]; w[2] = 0.0;
+            ao[0] = ad[2 * k]; ao[1] = ad[2 * k + 1];
+            rho = rd[k] + r_body;
+        }
+        double n = sqrt(dot3(d, d)), x = n / rho - 1.0, g[3] = {d[0] / (n * rho), d[1] / (n * rho), d[2] / (n * rho)};
+        double xdot = dot3(g, w), dw = dot3(d, w);
+        double kappa = (dot3(w, w) - dw * dw / (n * n)) / (n * rho);
+        double s = xdot < 0 ? 1.0 : (xdot > 0 ? 0.0 : 0.5);     /* 1 - heaviside(xdot), heaviside(0) = 0.5 */
+        double Ml = 2.0 * s / (x * x), fel = -2.0 * s * xdot * xdot / (x * x * x), h = -2.0 / x * xdot * xdot;
+        double fl = Ml * h, acc_o = dot3(g, ao);
+        double fq = fl + Ml * (sigma * kappa - acc_o), feq = fel + Ml * (kappa - acc_o);
+        double gv = g[0] * qd[0] + g[1] * qd[1]; /* J^T g . qdot */
+        for (int a = 0; a < 2; a++) {
+            f[a] += g[a] * fq;
+            for (int b = 0; b < 2; b++) M[a][b] += Ml * g[a] * g[b];
+        }
+        num += gv * (fq - feq);
+    }
+    double Mf[2][2] = {{M[0][0], M[0][1]}, {M[1][0], M[1][1]}}, ff[2] = {f[0], f[1]};
+    double xg[2] = {q[0] - goal[0], q[1] - goal[1]}, n = sqrt(xg[0] * xg[0] + xg[1] * xg[1]);
+    double dpsi = 5.0 * w_goal * tanh(10.0 * n), m2 = 2.0 * (1.7 * exp(-0.5625 * n * n) + 0.3);
+    for (int a = 0; a < 2; a++) {
+        ff[a] += m2 * dpsi * xg[a] / n;
+        Mf[a][a] += m2;
+    }
+    double hg[3], hf[3];
+    for (int sys = 0; sys < 2; sys++) {
+        double (*A)[2] = sys ? Mf : M;
+        double* b = sys ? ff : f;
+        double* hh = sys ? hf : hg;
+        double a00 = A[0][0] + e, a11 = A[1][1] + e, a01 = A[0][1], det = a00 * a11 - a01 * a01;
+        hh[0] = (a11 * b[0] - a01 * b[1]) / det;
+        hh[1] = (a00 * b[1] - a01 * b[0]) / det;
+        hh[2] = 0.0;
+    }
+    double qMq = 0.2 * qd[2] * qd[2], qq = 0, qhg = 0, qhf = 0;
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) qMq += qd[a] * M[a][b] * qd[b];
+    for (int a = 0; a < 3; a++) {
+        qq += qd[a] * qd[a];
+        qhg += qd[a] * hg[a];
+        qhf += qd[a] * hf[a];
+    }
+    double a_geom = -num / (e + qMq), s2 = 2.0 * c->exec_scale, den = e + s2 * qq;
+    double a_ex0 = -s2 * qhg / den, a_exf = -s2 * qhf / den;
+    double eta = 0.5 * (tanh(-0.9 * (1.0 - 1.0 / 2.0) * qq - 0.5) + 1.0);
+    double a_ex = eta * a_ex0 + (1.0 - eta) * a_exf;
+    double beta = 0.5 * (tanh(-0.5 * (n - 0.02)) + 1.0) * 6.5 + 0.01 + fmax(0.0, a_geom - a_ex);
+    for (int a = 0; a < 3; a++) action[a] = -hf[a] - (a_ex + beta) * qd[a]; /* mode 'acc' */
+    return 0;
+}
+
 int mrfo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -82,6 +82,11 @@ void mrfo_endeffector(const mrfo_config* c, int robot, const double* q, const do
 void mrfo_spheres(const mrfo_config* c, int robot, const double* q, const double* qd, int n, const double* off,
                   double* x, double* v_origin, double* v_sphere);
 
+/* Point-mass planner (examples/example_pointmasses_static.py:102-129, _dynamic.py:102-131), mode 'acc'. */
+int mrfo_point_action(const mrfo_config* c, const double* q, const double* qd, const double* goal, double w_goal,
+                      double r_body, int Ss, const double* xs, const double* rs, int Sd, const double* xd,
+                      const double* vd, const double* ad, const double* rd, double* action);
+
 int mrfo_max_threads(void);
 
 #ifdef __cplusplus

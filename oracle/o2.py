@@ -55,6 +55,7 @@ def lib():
         _lib.mrfo_rollout_jointspace_batch.argtypes = [cp, d, C.c_long, C.c_int, d, d, d, d, C.c_int]
         _lib.mrfo_action_batch.argtypes = [cp, C.c_int, d, C.c_long, C.c_int, d, d, d, d, d, C.c_int]
         _lib.mrfo_spheres.argtypes = [cp, C.c_int, d, d, C.c_int, d, d, d, d]
+        _lib.mrfo_point_action.argtypes = [cp, d, d, d, C.c_double, C.c_double, C.c_int, d, d, C.c_int, d, d, d, d, d]
         _lib.mrfo_max_threads.restype = C.c_int
     return _lib
 
@@ -192,6 +193,17 @@ def obstacle_lists(cfg, q, qd, off, vel_mode=0, static_or_dyn=1):
             o[:, 9] = np.repeat(np.array(cfg.r_robots[j][:]), n)
             rows.append(o)
         out.append(np.concatenate(rows))
+    return out
+
+
+def point_action(cfg, q, qd, goal, w_goal, r_body, xs=(), rs=(), xd=(), vd=(), ad=(), rd=()):
+    """Point-mass fabric action (mode 'acc'); static spheres xs (Ss,3), rs; dynamic spheres xd, vd, ad (Sd,2), rd."""
+    q, qd, goal = _c(q), _c(qd), _c(goal)
+    xs, rs = _c(xs).reshape(-1, 3), _c(rs).reshape(-1)
+    xd, vd, ad, rd = _c(xd).reshape(-1, 2), _c(vd).reshape(-1, 2), _c(ad).reshape(-1, 2), _c(rd).reshape(-1)
+    out = np.zeros(3)
+    lib().mrfo_point_action(C.byref(cfg), _p(q), _p(qd), _p(goal), float(w_goal), float(r_body), len(rs), _p(xs), _p(rs),
+                            len(rd), _p(xd), _p(vd), _p(ad), _p(rd), _p(out))
     return out
 
 

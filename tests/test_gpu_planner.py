@@ -195,3 +195,57 @@ def test_batched_deadlock_from_rollout_flags_identical(built):
         assert np.abs(got - exp_goals)[okb].max() < tol
         assert np.array_equal(w.T.double().cpu().numpy()[okb], exp_w[okb])
     fab.close()
+
+
+def test_point_mass_planner_config_c1(built):
+    """BASELINE config C1: the 4-point-mass examples through the drop-in planner, against the O1 golden actions and
+    (batched, random states) against oracle O2."""
+    import torch
+    g = np.load(os.path.join(GOLD, "fabric_golden.npz"))
+    pos, vel, goals, obst = g["pm_pos"], g["pm_vel"], g["pm_goals"], g["pm_obst"]
+    pl_s = P.set_planner_point(None, n_obstacles=9)
+    pl_d = P.set_planner_point(None, n_obstacles=6, n_dyn_obstacles=3)
+    for i in range(4):
+        others = [j for j in range(4) if j != i]
+        a = pl_s.compute_action(q=pos[i], qdot=vel[i], x_goal_0=goals[i], weight_goal_0=1.0,
+                                x_obsts=list(obst) + [pos[j] for j in others], radius_obsts=[1.0] * 6 + [0.2] * 3,
+                                radius_body_base_link=np.array(0.2))
+        assert np.abs(a - g["pm_static"][i]).max() < 1e-10
+        kw = dict(q=pos[i], qdot=vel[i], x_goal_0=goals[i], weight_goal_0=1.0, x_obsts=list(obst), radius_obsts=[1.0] * 6,
+                  radius_body_base_link=np.array(0.2))
+        for k, j in enumerate(others):                       # per-index spellings, example_pointmasses_dynamic.py:199-211
+            kw[f"x_obst_dynamic_{k}"], kw[f"xdot_obst_dynamic_{k}"] = pos[j][0:2], vel[j][0:2]
+            kw[f"xddot_obst_dynamic_{k}"], kw[f"radius_obst_dynamic_{k}"] = np.array([0, 0]), np.array(0.2)
+        a = pl_d.compute_action(**kw)
+        assert np.abs(a - g["pm_dyn"][i]).max() < 1e-10
+    # batched device entry vs O2
+    rng = np.random.default_rng(8)
+    B, Ss, Sd = 300, 6, 3
+    rec = np.zeros((B, 10))
+    rec[:, 0:2] = rng.uniform(-3, 3, (B, 2))
+    rec[:, 3:6] = rng.uniform(-1, 1, (B, 3))
+    rec[:, 6:8] = rng.uniform(-3, 3, (B, 2))
+    rec[:, 8], rec[:, 9] = 1.0, 0.2
+    stat = np.zeros((B, Ss, 4))
+    ang = rng.uniform(0, 2 * np.pi, (B, Ss))
+    rad = rng.uniform(2.0, 4.0, (B, Ss))                    # keep clear of the robot: normalised clearance >= 0.6
+    stat[:, :, 0] = rec[:, None, 0] + rad * np.cos(ang)
+    stat[:, :, 1] = rec[:, None, 1] + rad * np.sin(ang)
+    stat[:, :, 3] = 1.0
+    dyn = np.zeros((B, Sd, 7))
+    ang = rng.uniform(0, 2 * np.pi, (B, Sd))
+    dyn[:, :, 0] = rec[:, None, 0] + 1.5 * np.cos(ang)
+    dyn[:, :, 1] = rec[:, None, 1] + 1.5 * np.sin(ang)
+    dyn[:, :, 2:6] = rng.uniform(-0.5, 0.5, (B, Sd, 4))
+    dyn[:, :, 6] = 0.2
+    fab = pl_s.fab
+    for dt, tol in ((torch.float64, 1e-9), (torch.float32, 2e-3)):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(np.moveaxis(a, 0, -1))).to("cuda:0", dtype=dt)
+        act = fab.point_action_dev(t(rec), t(stat), t(dyn))
+        torch.cuda.synchronize()
+        got = act.T.double().cpu().numpy()
+        ocfg = o2.default_config(2)
+        for b in range(B):
+            ref = o2.point_action(ocfg, rec[b, 0:3], rec[b, 3:6], rec[b, 6:8], 1.0, 0.2, stat[b, :, 0:3], stat[b, :, 3],
+                                  dyn[b, :, 0:2], dyn[b, :, 2:4], dyn[b, :, 4:6], dyn[b, :, 6])
+            assert np.abs(got[b] - ref).max() < tol * max(1.0, np.abs(ref).max())

@@ -163,3 +163,17 @@ def test_sphere_offsets_and_sphere_kinematics(built):
             assert np.array_equal(vo[l * 2 + s], vl[l])
     x1, _, _ = o2.spheres(cfg, 2, q, qd, np.zeros((8, 1, 3)))
     assert np.abs(x1 - xl).max() < 1e-15                                             # zero offsets = link origins
+
+
+def test_point_mass_o2_matches_o1_golden(gold):
+    """BASELINE config C1 (4 point masses): closed-form O2 against the O1 golden actions, static and dynamic variants
+    (examples/example_pointmasses_static.py:191-199, examples/example_pointmasses_dynamic.py:192-212)."""
+    cfg = o2.default_config(2)
+    pos, vel, goals, obst = gold["pm_pos"], gold["pm_vel"], gold["pm_goals"], gold["pm_obst"]
+    for i in range(4):
+        others = [j for j in range(4) if j != i]
+        a = o2.point_action(cfg, pos[i], vel[i], goals[i], 1.0, 0.2, np.concatenate([obst, pos[others]]), [1.0] * 6 + [0.2] * 3)
+        assert np.abs(a - gold["pm_static"][i]).max() < 1e-12
+        a = o2.point_action(cfg, pos[i], vel[i], goals[i], 1.0, 0.2, obst, [1.0] * 6, pos[others][:, 0:2],
+                            vel[others][:, 0:2], np.zeros((3, 2)), [0.2] * 3)
+        assert np.abs(a - gold["pm_dyn"][i]).max() < 1e-12
