@@ -56,3 +56,43 @@ def oracle_actions(rec, obst, robot_first=0, **cfgkw):
             except FloatingPointError:
                 pass
     return out
+
+
+def oracle_episode(rec, T, N, rollout=True, resolve=True, estimate=False, n_per_link=1):
+    """CPU restatement of the closed control loop (examples/example_pandas_Jointspace.py:280-458) for ONE scenario with
+    the reach-task protocol of multi_robot_fabrics_b200.episodes: oracle O2 + the deadlock restatement."""
+    from oracle.deadlock_ref import DeadlockOracle
+    R = rec.shape[0]
+    cfg = o2.default_config(R)
+    off = o2.sphere_offsets_ref(n_per_link)
+    vlim = np.array([2.175] * 4 + [2.61] * 3)
+    q, qd = rec[:, 0:7].copy(), rec[:, 7:14].copy()
+    goal0, w0 = rec[:, 14:17].copy(), rec[:, 17].copy()
+    dl, tdo, n_flags, done_at = DeadlockOracle(R), 1000, 0, -1
+    for t in range(T):
+        qd = np.clip(qd, -vlim, vlim)
+        goals, weights = [g.copy() for g in goal0], list(w0)
+        xee = [o2.kinematics(cfg, i, q[i], qd[i])[0][7] for i in range(R)]
+        if rollout:
+            if estimate:
+                x, v = o2.endeffector(cfg, 1, q[1], qd[1])
+                goals[1] = x + 0.2 * v
+            r = rec.copy()
+            r[:, 0:7], r[:, 7:14], r[:, 14:17], r[:, 17], r[:, 21] = q, qd, np.array(goals), weights, 10.0
+            avg, _ = o2.rollout_jointspace_avg(cfg, r, N)
+            if resolve:
+                goals, weights, tdo, flag = dl.step(xee, goals, weights, t, tdo, float(sum(avg[0]) / R), [0] * R)
+                n_flags += int(flag)
+        lists = o2.obstacle_lists(cfg, q, qd, off, vel_mode=0)
+        act = np.zeros((R, 7))
+        for i in range(R):
+            r = rec[i].copy()
+            r[0:7], r[7:14], r[14:17], r[17], r[21] = q[i], qd[i], goals[i], weights[i], 20.0
+            o = lists[i]
+            act[i] = o2.action(cfg, i, r, o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+        a = np.clip(act, -vlim, vlim)
+        qd = a
+        q = q + 0.01 * a
+        if done_at < 0 and all(np.linalg.norm(xee[i] - goal0[i]) < 0.05 for i in range(R)):
+            done_at = t
+    return q, n_flags, done_at

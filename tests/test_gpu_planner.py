@@ -14,7 +14,7 @@ from multi_robot_fabrics_b200.api import Fabrics
 from oracle import o2
 from oracle.deadlock_ref import DeadlockOracle
 
-from helpers import oracle_rollout, random_obstacles
+from helpers import oracle_episode, oracle_rollout, random_obstacles
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MOUNT = {"z_table": 0.65, "mount_positions": [np.array([0.0, 0.0, 0.65]), np.array([1.0, 0.0, 0.65]),
@@ -249,3 +249,32 @@ def test_point_mass_planner_config_c1(built):
             ref = o2.point_action(ocfg, rec[b, 0:3], rec[b, 3:6], rec[b, 6:8], 1.0, 0.2, stat[b, :, 0:3], stat[b, :, 3],
                                   dyn[b, :, 0:2], dyn[b, :, 2:4], dyn[b, :, 4:6], dyn[b, :, 6])
             assert np.abs(got[b] - ref).max() < tol * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("R,kw", [(2, dict(rollout_fabrics=True, resolve_deadlocks=True, estimate_goal=True)),
+                                  (3, dict(rollout_fabrics=True, resolve_deadlocks=True, estimate_goal=False)),
+                                  (2, dict(rollout_fabrics=False))])
+def test_closed_loop_episodes_match_cpu_loop(built, R, kw):
+    """the batched closed control loop (rollout -> deadlock -> obstacle staging -> action -> kinematic
+    step, captured in a CUDA graph) reproduces the same loop run on the CPU oracle, scenario by scenario."""
+    from multi_robot_fabrics_b200.episodes import BatchedEpisodes
+    B, T, N = 12, 25, 5
+    rec = m.scenarios.generate(B, R, seed=71)
+    rec[:, :, 7:14] *= 0.2
+    rec[1::2, 1, 14:17] = rec[1::2, 0, 14:17] + [0.05, 0.0, 0.02]      # half of the scenarios: nearly the same goal
+    ep = BatchedEpisodes(rec, n_horizon=N, dtype="f64", n_obst_per_link=2, **kw).run(T)
+    res = ep.results()
+    n_cmp = 0
+    for b in range(B):
+        try:
+            q, n_flags, done_at = oracle_episode(rec[b], T, N, rollout=kw.get("rollout_fabrics", True),
+                                                 resolve=kw.get("resolve_deadlocks", True),
+                                                 estimate=kw.get("estimate_goal", False), n_per_link=2)
+        except FloatingPointError:
+            continue
+        if not np.isfinite(q).all():
+            continue
+        n_cmp += 1
+        assert np.abs(res["q"][b] - q).max() < 1e-7, b
+        assert res["deadlock_steps"][b] == n_flags and res["steps_to_success"][b] == done_at
+    assert n_cmp >= B - 3 and res["steps"] == T
