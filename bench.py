@@ -148,16 +148,64 @@ def reference_arm(a):
 
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons DURING the timed region.  Polls NVML in-process every few ms (nvidia_ml_py)
+    so that even a 20 ms region is sampled; falls back to an `nvidia-smi -lms` subprocess if NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device_index: int):
         self.idx = device_index
-        self.rows = []
+        self.rows = []          # (sm_mhz, power_w, reasons_mask)
+        self.max_mhz = None
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, pw, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def _read(self):
+        names = {5: 0x8, 6: 0x40, 7: 0x20, 8: 0x4}
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                mask = 0
+                for col, bit in names.items():
+                    if r[col].lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[1]), float(r[3]), mask))
+                self.max_mhz = float(r[2])
+            except Exception:
+                continue
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
@@ -166,32 +214,27 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        self.stop_flag = True
+        if self.nvml is not None:
+            self.t.join(timeout=1.0)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                pw.append(float(r[3]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.proc.wait(timeout=5)
             except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML / nvidia-smi"]}
+        sm = [r[0] for r in self.rows]
+        pw = [r[1] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        reasons = sorted(v for k, v in self.REASONS.items() if mask & k)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons,
+                "source": "nvml in-process poll" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 def ours(a):
