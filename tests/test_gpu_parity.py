@@ -284,3 +284,42 @@ def test_mrdf_control_step_configs_c2_c4(fabs, R, n):
             n_ok += 1
             assert np.abs(got[b, i] - ref).max() < F64_RTOL * max(1.0, np.abs(ref).max())
     assert n_ok > 0.7 * B * R
+
+
+def test_single_robot_rollout(fabs):
+    """n_robots = 1: no inter-robot leaves, only plane / limit / attractor leaves (throughput kernel)."""
+    R, N, B = 1, 20, 40
+    rec = m.scenarios.generate(B, R, seed=81)
+    fab = get_fab(fabs, R)
+    out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    qN, qdN, avg, xee, goal, ok = oracle_rollout(rec, R, N)
+    assert ok.sum() > 0.9 * B
+    assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
+    assert np.abs(out["x_ee"] - xee).max() < 1e-12
+
+
+@pytest.mark.parametrize("kernel", ["throughput", "cooperative"])
+def test_four_robot_rollout_custom_mount(fabs, kernel):
+    """n_robots = MRF_MAX_ROBOTS = 4 with a caller-supplied mount for the fourth arm (MrfConfig.mount)."""
+    from multi_robot_fabrics_b200 import scenarios as sc
+    R, N, B = 4, 10, 24
+    old = sc.MOUNT_XYZ[3].copy()
+    sc.MOUNT_XYZ[3] = [0.3, -0.6, 0.65]
+    try:
+        rec = sc.generate(B, R, seed=82)
+        mounts = [sc.mount_matrix(r) for r in range(R)]
+    finally:
+        sc.MOUNT_XYZ[3] = old
+    fab = Fabrics(R, device=0, mount=mounts)
+    fab.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
+    out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    fab.close()
+    ocfg = o2.default_config(R)
+    for r in range(R):
+        for k, v in enumerate(mounts[r].reshape(16)):
+            ocfg.mount[r][k] = v
+    qN, qdN, avg, _ = o2.rollout_jointspace(ocfg, rec, N)
+    ok = np.isfinite(qdN).all(axis=(1, 2, 3)) & (np.abs(qdN).max(axis=(1, 2, 3)) < 3)
+    assert ok.sum() > 0.8 * B
+    assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
+    assert np.abs(out["avg_vel"] - avg)[ok].max() < F64_RTOL
