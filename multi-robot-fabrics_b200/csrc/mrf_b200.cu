@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
+    // (a double-buffered point table with one barrier per step was measured 2 % slower: more shared memory per CTA
+    //  and non-immediate offsets; the barrier stall is load imbalance between the robots' warps, not barrier count)
     T* kin = reinterpret_cast<T*>(smem_raw);
     T* prm = kin + kKin * NT;
     const long long b = (long long)blockIdx.x * kTile + lane;
@@ -543,6 +545,18 @@ __global__ void __launch_bounds__(kActThreads)
 // FMA peak micro-benchmark: the roofline denominator for the compute-bound rollout (MEASURED_PEAKS.json
 // holds HBM and bf16 tensor peaks only).  8 independent FMA chains per thread.
 // ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma2_peak_kernel(float* out, int iters, float b, float c) {
+    float a0 = threadIdx.x * 1e-3f;
+    float2 p0 = make_float2(a0, a0 + 1), p1 = make_float2(a0 + 2, a0 + 3), p2 = make_float2(a0 + 4, a0 + 5),
+           p3 = make_float2(a0 + 6, a0 + 7);
+    const float2 bb = make_float2(b, b), cc = make_float2(c, c);
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        p0 = __ffma2_rn(p0, bb, cc); p1 = __ffma2_rn(p1, bb, cc); p2 = __ffma2_rn(p2, bb, cc); p3 = __ffma2_rn(p3, bb, cc);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
+}
+
 template <typename T> __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T b, T c) {
     T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
     T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
@@ -1409,6 +1423,19 @@ template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {
         MRF_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
+    }
+    if (sizeof(T) == 4) { // the FP32 pipe peak is reached with packed FFMA2 (scalar FFMA is issue-limited to ~93 %)
+        for (int rep = 0; rep < 6; ++rep) {
+            MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+            fma2_peak_kernel<<<blocks, threads, 0, h->stream>>>((float*)h->stage[0], iters, 0.999f, 1e-3f);
+            MRF_CUDA(cudaGetLastError());
+            MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+            MRF_CUDA(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            MRF_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
     }
     *tflops = best;
     return MRF_OK;

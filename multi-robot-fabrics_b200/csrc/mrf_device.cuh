@@ -255,6 +255,65 @@ MRF_HD void chain_forward(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// P2<T>: two independent values processed together.  For float on sm_100a the arithmetic maps to the packed
+// FP32x2 instructions FFMA2 / FMUL2 / FADD2 (__ffma2_rn ...): one issue slot for two FMAs.  The rollout kernel is
+// issue-bound (ncu: 76 % issue slots busy at 59 % FMA-pipe utilisation), so evaluating two sphere leaves per
+// instruction stream removes ~30 % of its issued instructions; measured on B200 (tools/micro/ffma2_probe.cu):
+// FFMA2 reaches the same pipe peak as scalar FFMA (74 TFLOP/s) with half the issue slots.  For double (and on the
+// host) the pair is two scalars.
+// ------------------------------------------------------------------------------------------------
+#if !defined(__CUDACC__)
+struct float2 {
+    float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#endif
+template <typename T> struct P2;
+template <> struct P2<float> {
+    float2 v;
+};
+template <> struct P2<double> {
+    double a, b;
+};
+MRF_HD P2<float> pmk(float a, float b) { return P2<float>{make_float2(a, b)}; }
+MRF_HD P2<double> pmk(double a, double b) { return P2<double>{a, b}; }
+MRF_HD P2<float> psplat(float a) { return pmk(a, a); }
+MRF_HD P2<double> psplat(double a) { return pmk(a, a); }
+MRF_HD float plo(P2<float> x) { return x.v.x; }
+MRF_HD float phi(P2<float> x) { return x.v.y; }
+MRF_HD double plo(P2<double> x) { return x.a; }
+MRF_HD double phi(P2<double> x) { return x.b; }
+MRF_HD P2<float> pmul(P2<float> x, P2<float> y) {
+#if defined(__CUDA_ARCH__)
+    return P2<float>{__fmul2_rn(x.v, y.v)};
+#else
+    return pmk(x.v.x * y.v.x, x.v.y * y.v.y);
+#endif
+}
+MRF_HD P2<float> padd(P2<float> x, P2<float> y) {
+#if defined(__CUDA_ARCH__)
+    return P2<float>{__fadd2_rn(x.v, y.v)};
+#else
+    return pmk(x.v.x + y.v.x, x.v.y + y.v.y);
+#endif
+}
+MRF_HD P2<float> pfma(P2<float> x, P2<float> y, P2<float> z) {
+#if defined(__CUDA_ARCH__)
+    return P2<float>{__ffma2_rn(x.v, y.v, z.v)};
+#else
+    return pmk(x.v.x * y.v.x + z.v.x, x.v.y * y.v.y + z.v.y);
+#endif
+}
+MRF_HD P2<double> pmul(P2<double> x, P2<double> y) { return pmk(x.a * y.a, x.b * y.b); }
+MRF_HD P2<double> padd(P2<double> x, P2<double> y) { return pmk(x.a + y.a, x.b + y.b); }
+MRF_HD P2<double> pfma(P2<double> x, P2<double> y, P2<double> z) { return pmk(x.a * y.a + z.a, x.b * y.b + z.b); }
+template <typename T> MRF_HD P2<T> prsqrt(P2<T> x) { return pmk(Mth<T>::rsqrt(plo(x)), Mth<T>::rsqrt(phi(x))); }
+template <typename T> MRF_HD P2<T> prcp(P2<T> x) { return pmk(Mth<T>::rcp(plo(x)), Mth<T>::rcp(phi(x))); }
+template <typename T> MRF_HD P2<T> pdot(const V3<P2<T>>& a, const V3<P2<T>>& b) {
+    return pfma(a.z, b.z, pfma(a.y, b.y, pmul(a.x, b.x)));
+}
+
+// ------------------------------------------------------------------------------------------------
 // accumulators
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Sym3 {
@@ -309,6 +368,56 @@ MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> co
     acc.A.xx += Md.x * d.x; acc.A.xy += Md.x * d.y; acc.A.xz += Md.x * d.z;
     acc.A.yy += Md.y * d.y; acc.A.yz += Md.y * d.z; acc.A.zz += Md.z * d.z;
     acc.b = acc.b + d * (gs * fq);
+}
+
+// Two sphere leaves of the same ego point at once (obstacle points A and B packed in P2): same algebra as
+// sphere_leaf, every operation on pairs.
+template <typename T> struct PointAcc2 {
+    Sym3<P2<T>> A;
+    V3<P2<T>> b;
+    P2<T> num;
+};
+template <typename T> MRF_HD void acc2_zero(PointAcc2<T>& a) {
+    const P2<T> z = psplat(T(0));
+    a.A = Sym3<P2<T>>{z, z, z, z, z, z};
+    a.b = V3<P2<T>>{z, z, z};
+    a.num = z;
+}
+template <typename T>
+MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>& cc, const V3<P2<T>>& xo,
+                         const V3<P2<T>>& vo, const V3<P2<T>>& co, T vref, T aref, P2<T> rho, P2<T> wt, T sigma,
+                         PointAcc2<T>& acc) {
+    const P2<T> m1 = psplat(T(-1)), nvref = psplat(-vref);
+    V3<P2<T>> d{pfma(xo.x, m1, p.x), pfma(xo.y, m1, p.y), pfma(xo.z, m1, p.z)};
+    V3<P2<T>> w{pfma(vo.x, nvref, v.x), pfma(vo.y, nvref, v.y), pfma(vo.z, nvref, v.z)};
+    P2<T> n2 = pdot(d, d);
+    P2<T> in1 = prsqrt(n2);
+    P2<T> n = pmul(n2, in1);
+    P2<T> t = pfma(rho, m1, n);                 // n - rho
+    P2<T> nr = pmul(n, rho);
+    P2<T> u = prcp(pmul(nr, t));
+    P2<T> gs = pmul(u, t);                      // 1/(n rho)
+    P2<T> ix = pmul(pmul(u, nr), rho);          // 1/x
+    P2<T> dw = pdot(d, w), dc = pdot(d, cc), da = pdot(d, co), dv = pdot(d, v), ww = pdot(w, w);
+    P2<T> in2 = pmul(in1, in1);
+    P2<T> inner = padd(pfma(pmul(pmul(dw, dw), m1), in2, ww), dc);   // (kappa + g.c)/gs
+    P2<T> xd = pmul(dw, gs);
+    P2<T> ix2 = pmul(ix, ix), ix4 = pmul(ix2, ix2);
+    P2<T> hx = pmul(pmul(xd, xd), ix4);
+    P2<T> Ml = pmul(pmul(psplat(T(0.02)), wt), ix4);
+    P2<T> fl = pmul(Ml, pmul(psplat(T(-0.5)), hx));
+    P2<T> fel = pmul(pmul(psplat(T(-0.04)), wt), pmul(hx, ix));
+    P2<T> Mg = pmul(Ml, gs);
+    P2<T> s1 = pfma(psplat(sigma), inner, pmul(psplat(-aref), da));
+    P2<T> fq = pfma(Mg, s1, fl);
+    P2<T> e1 = pfma(pmul(Mg, psplat(sigma - T(1))), inner, pfma(fel, m1, fl));
+    acc.num = pfma(pmul(dv, gs), e1, acc.num);
+    P2<T> k = pmul(Mg, gs);
+    V3<P2<T>> Md{pmul(d.x, k), pmul(d.y, k), pmul(d.z, k)};
+    acc.A.xx = pfma(Md.x, d.x, acc.A.xx); acc.A.xy = pfma(Md.x, d.y, acc.A.xy); acc.A.xz = pfma(Md.x, d.z, acc.A.xz);
+    acc.A.yy = pfma(Md.y, d.y, acc.A.yy); acc.A.yz = pfma(Md.y, d.z, acc.A.yz); acc.A.zz = pfma(Md.z, d.z, acc.A.zz);
+    P2<T> gf = pmul(gs, fq);
+    acc.b.x = pfma(d.x, gf, acc.b.x); acc.b.y = pfma(d.y, gf, acc.b.y); acc.b.z = pfma(d.z, gf, acc.b.z);
 }
 
 // Plane leaf (geometry_plane_constraint "10*(1/(1+exp(-10x))-1) xdot^2", example_pandas_Jointspace.py:87;
@@ -461,13 +570,32 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 T rb2 = prm[(P_RB + rb_first + 1) * NT + tid];
                 if (rb2 == rb) we = T(2); else passes = 2;
             }
+            PointAcc2<T> acc2;
+            acc2_zero(acc2);
+            const V3<P2<T>> p2{psplat(p.x), psplat(p.y), psplat(p.z)}, v2{psplat(v.x), psplat(v.y), psplat(v.z)},
+                c2{psplat(cc.x), psplat(cc.y), psplat(cc.z)};
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
-                src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
-                    sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
-                });
+                if (sizeof(T) == 4) {
+                    // FP32: sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2)
+                    src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
+                        sphere_leaf2(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)),
+                                     pmul(wo, psplat(we)), sigma, acc2);
+                    });
+                } else {
+                    // FP64: no packed instructions exist and pairing doubles the live registers -> one leaf at a time
+                    src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
+                        sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
+                    });
+                }
                 plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
             }
+            acc.A.xx += plo(acc2.A.xx) + phi(acc2.A.xx); acc.A.xy += plo(acc2.A.xy) + phi(acc2.A.xy);
+            acc.A.xz += plo(acc2.A.xz) + phi(acc2.A.xz); acc.A.yy += plo(acc2.A.yy) + phi(acc2.A.yy);
+            acc.A.yz += plo(acc2.A.yz) + phi(acc2.A.yz); acc.A.zz += plo(acc2.A.zz) + phi(acc2.A.zz);
+            acc.b.x += plo(acc2.b.x) + phi(acc2.b.x); acc.b.y += plo(acc2.b.y) + phi(acc2.b.y);
+            acc.b.z += plo(acc2.b.z) + phi(acc2.b.z);
+            num += plo(acc2.num) + phi(acc2.num);
             V3<T> Jc[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j)
@@ -587,6 +715,19 @@ template <typename T> struct SmemSrc {
               cfg.ent_rad[r][k], cfg.ent_w[r][k]);
         }
     }
+    // pairs of entries; an odd tail is paired with itself at weight 0
+    template <typename F> MRF_HD void each2(F f) const {
+        const int ne = cfg.ent_n[r];
+        for (int k = 0; k < ne; k += 2) {
+            const int k1 = k + 1 < ne ? k + 1 : k;
+            const T* a = kin + cfg.ent_src[r][k] * 9 * NT + cfg.ent_rob[r][k] * kTile + lane;
+            const T* b = kin + cfg.ent_src[r][k1] * 9 * NT + cfg.ent_rob[r][k1] * kTile + lane;
+            f(V3<P2<T>>{pmk(a[0], b[0]), pmk(a[NT], b[NT]), pmk(a[2 * NT], b[2 * NT])},
+              V3<P2<T>>{pmk(a[3 * NT], b[3 * NT]), pmk(a[4 * NT], b[4 * NT]), pmk(a[5 * NT], b[5 * NT])},
+              V3<P2<T>>{pmk(a[6 * NT], b[6 * NT]), pmk(a[7 * NT], b[7 * NT]), pmk(a[8 * NT], b[8 * NT])},
+              pmk(cfg.ent_rad[r][k], cfg.ent_rad[r][k1]), pmk(cfg.ent_w[r][k], k1 == k ? T(0) : cfg.ent_w[r][k1]));
+        }
+    }
 };
 
 // same, specialised to the reference's set-up in which every robot sphere has the same radius
@@ -608,6 +749,24 @@ template <typename T, int R> struct SmemSrcUniform {
             for (int pt = 0; pt < kPts; ++pt, b += 9 * NT) {
                 f(mk(b[0], b[NT], b[2 * NT]), mk(b[3 * NT], b[4 * NT], b[5 * NT]), mk(b[6 * NT], b[7 * NT], b[8 * NT]),
                   ro, (pt == 2 || pt == 5) ? T(2) : T(1));
+            }
+        }
+    }
+    // point pairs (link3, link4), (link5==6 [x2], link7), (link8, link1==2 [x2]) of every other robot
+    template <typename F> MRF_HD void each2(F f) const {
+        constexpr int NT = kTile * R;
+        const P2<T> ro2 = psplat(ro);
+#pragma unroll 1
+        for (int j = 0; j < R; ++j) {
+            if (j == r) continue;
+            const T* a = kin + j * kTile + lane;
+#pragma unroll
+            for (int pp = 0; pp < kPts / 2; ++pp, a += 18 * NT) { // 3 independent packed leaves in flight (ILP)
+                const T* b = a + 9 * NT;
+                f(V3<P2<T>>{pmk(a[0], b[0]), pmk(a[NT], b[NT]), pmk(a[2 * NT], b[2 * NT])},
+                  V3<P2<T>>{pmk(a[3 * NT], b[3 * NT]), pmk(a[4 * NT], b[4 * NT]), pmk(a[5 * NT], b[5 * NT])},
+                  V3<P2<T>>{pmk(a[6 * NT], b[6 * NT]), pmk(a[7 * NT], b[7 * NT]), pmk(a[8 * NT], b[8 * NT])}, ro2,
+                  pmk(pp == 1 ? T(2) : T(1), pp == 2 ? T(2) : T(1)));
             }
         }
     }
@@ -634,6 +793,24 @@ template <typename T, bool CART> struct GlobalSrc {
                 ao = mk(b[6 * stride], b[7 * stride], b[8 * stride]);
             }
             f(xo, vo, ao, b[9 * stride], T(1));
+        }
+    }
+    template <typename F> MRF_HD void each2(F f) const {
+        for (int o = 0; o < S; o += 2) {
+            const int o1 = o + 1 < S ? o + 1 : o;
+            const T* a = obst + (long long)o * MRF_OBST * stride + off;
+            const T* b = obst + (long long)o1 * MRF_OBST * stride + off;
+            V3<P2<T>> xo{pmk(a[0], b[0]), pmk(a[stride], b[stride]), pmk(a[2 * stride], b[2 * stride])};
+            V3<P2<T>> vo{pmk(a[3 * stride], b[3 * stride]), pmk(a[4 * stride], b[4 * stride]), pmk(a[5 * stride], b[5 * stride])};
+            V3<P2<T>> ao;
+            if (CART) {
+                const P2<T> tk2 = psplat(tk);
+                xo = V3<P2<T>>{pfma(vo.x, tk2, xo.x), pfma(vo.y, tk2, xo.y), pfma(vo.z, tk2, xo.z)};
+                ao = V3<P2<T>>{psplat(T(0)), psplat(T(0)), psplat(T(0))};
+            } else {
+                ao = V3<P2<T>>{pmk(a[6 * stride], b[6 * stride]), pmk(a[7 * stride], b[7 * stride]), pmk(a[8 * stride], b[8 * stride])};
+            }
+            f(xo, vo, ao, pmk(a[9 * stride], b[9 * stride]), pmk(T(1), o1 == o ? T(0) : T(1)));
         }
     }
 };
