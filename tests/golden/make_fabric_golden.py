@@ -132,6 +132,26 @@ def main():
     out["pm_obst"], out["pm_static"], out["pm_dyn"] = obstacles_pos, np.array(pm_static), np.array(pm_dyn)
     print("point-mass static", np.array(pm_static))
 
+    # ---- coupled rollout, 3 Pandas, N = 2, STATIC_OR_DYN_FABRICS = 0 and unequal sphere radii (appended last so the
+    #      random stream of the cases above is unchanged) ---------------------------------------------------------------
+    R, N = 3, 2
+    recs = np.stack([rand_rec(), rand_rec(), rand_rec()])
+    recs[0, 0:7] = [1.1, -0.3, 0.0, -2.2, 0.0, 1.9, 0.8]          # near the reference's 3-robot pos0
+    recs[1, 0:7] = [1.13, 0.2, 0.12, -1.65, 0.0, 1.86, 0.7]
+    recs[2, 0:7] = [-0.47, -0.25, -0.4, -2.1, -0.1, 1.85, 0.37]
+    recs[:, o2.RB:o2.RB + 6] = [0.08, 0.07, 0.09, 0.06, 0.08, 0.1]
+    rr = [[0.08, 0.06, 0.08, 0.08, 0.07, 0.09, 0.08, 0.08], [0.05, 0.05, 0.08, 0.1, 0.08, 0.08, 0.06, 0.08],
+          [0.08] * 8]
+    planners = [o1.make_panda_planner(mounts[r], n_dyn=16) for r in range(R)]
+    for sd in (1, 0):
+        qN, qdN, avg = o1.jointspace_rollout(planners, mounts[:R], [recs[r, 0:7] for r in range(R)],
+                                             [recs[r, 7:14] for r in range(R)],
+                                             [o2.record_to_params(recs[r]) for r in range(R)], N, r_robots=rr,
+                                             static_or_dyn=sd)
+        out[f"ro3_sd{sd}_qN"], out[f"ro3_sd{sd}_qdN"], out[f"ro3_sd{sd}_avg"] = qN, qdN, avg
+        print("3-robot rollout sd", sd, avg)
+    out["ro3_rec"], out["ro3_rr"], out["ro3_N"] = recs, np.array(rr), np.array(N)
+
     np.savez_compressed(os.path.join(HERE, "fabric_golden.npz"), **out)
     print("wrote fabric_golden.npz")
 

@@ -323,3 +323,71 @@ def test_four_robot_rollout_custom_mount(fabs, kernel):
     assert ok.sum() > 0.8 * B
     assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
     assert np.abs(out["avg_vel"] - avg)[ok].max() < F64_RTOL
+
+
+def test_kernels_against_committed_golden_vectors(fabs):
+    """The CUDA kernels against tests/golden/fabric_golden.npz directly (vectors derived by oracle O1, autodiff)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fabric_golden.npz"))
+    # single actions (robots 0..2, S = 0..8, vel / acc mode, grasp planner, unequal radii, zero velocity)
+    for c in range(int(g["n_act"])):
+        p = f"act{c}_"
+        kw = dict(mode=int(g[p + "mode"]), has_collision_links=0 if int(g[p + "grasp"]) else 1)
+        fab = get_fab(fabs, 3, **kw)
+        obst = g[p + "obst"]
+        act = fab.action_host(g[p + "rec"][None, None], obst[None, None] if len(obst) else None,
+                              robot_first=int(g[p + "robot"]), dtype="f64")[0, 0]
+        assert np.abs(act - g[p + "action"]).max() < 1e-10 * max(1.0, np.abs(g[p + "action"]).max()), c
+    # coupled rollouts: 2 Pandas, and 3 Pandas with unequal radii in dynamic and static mode, both kernels
+    for coop in (0, 1 << 20):
+        fab = get_fab(fabs, 2)
+        fab.handle.set_coop_max_batch(coop)
+        out = fab.rollout_host(g["ro_rec"][None], int(g["ro_N"]), dtype="f64", trajectories=True)
+        fab.handle.set_coop_max_batch(512)
+        assert np.abs(out["qN"][0] - g["ro_qN"]).max() < 1e-11 and np.abs(out["qdN"][0] - g["ro_qdN"]).max() < 1e-10
+        assert np.abs(out["avg_vel"][0] - g["ro_avg"]).max() < 1e-10
+        for sd in (1, 0):
+            fab3 = Fabrics(3, device=0, static_or_dyn=sd, r_robots=g["ro3_rr"].tolist())
+            fab3.handle.set_coop_max_batch(coop)
+            out = fab3.rollout_host(g["ro3_rec"][None], int(g["ro3_N"]), dtype="f64", trajectories=True)
+            fab3.close()
+            assert np.abs(out["qdN"][0] - g[f"ro3_sd{sd}_qdN"]).max() < 1e-10
+            assert np.abs(out["avg_vel"][0] - g[f"ro3_sd{sd}_avg"]).max() < 1e-10
+    # Cartesian rollout and link kinematics
+    fab = get_fab(fabs, 2)
+    avg, qN, qdN = fab.rollout_cart_host(0, g["cart_rec"][None], g["cart_obst"][None], 2, dtype="f64")
+    assert np.abs(qN[0] - g["cart_qN"]).max() < 1e-11 and np.abs(qdN[0] - g["cart_qdN"]).max() < 1e-10
+    assert abs(avg[0] - float(g["cart_avg"])) < 1e-10
+    fab3 = get_fab(fabs, 3)
+    q = np.zeros((1, 3, 7)); qd = np.zeros((1, 3, 7))
+    q[0, 1], qd[0, 1] = g["kin_rec"][0:7], g["kin_rec"][7:14]
+    x, v, a = fab3.kinematics_host(q, qd)
+    assert np.abs(x[0, 1] - g["kin_xva"][:, 0]).max() < 1e-13 and np.abs(v[0, 1] - g["kin_xva"][:, 1]).max() < 1e-13
+    assert np.abs(a[0, 1] - g["kin_xva"][:, 2]).max() < 1e-12
+
+
+def test_error_paths_fail_loudly(fabs):
+    """Bad calls return an error code with a message instead of computing something else."""
+    import ctypes as C
+    import torch
+    from multi_robot_fabrics_b200 import _lib
+    fab = Fabrics(2, device=0, mode=0)                       # 'acc' planner: joint-space rollouts are undefined
+    rec = m.scenarios.generate(4, 2, seed=1)
+    with pytest.raises(_lib.MrfError, match="vel"):
+        fab.rollout_host(rec, 5)
+    fab.close()
+    fab = get_fab(fabs, 2)
+    L = _lib.lib()
+    assert L.mrf_rollout_host_f64(fab.handle.ptr, None, 5, None, None, None, None, None, 4) == -1
+    assert b"null" in L.mrf_last_error()
+    d = torch.zeros((44, 2, 4), dtype=torch.float64, device="cuda:0")
+    assert L.mrf_rollout_dev_f64(fab.handle.ptr, C.c_void_p(d.data_ptr()), 0, None, None, None, None, None, 4, None) == -1
+    assert L.mrf_action_dev_f64(fab.handle.ptr, 1, 2, C.c_void_p(d.data_ptr()), 0, None, C.c_void_p(d.data_ptr()), 4, None) == -1
+    with pytest.raises(_lib.MrfError):
+        fab.rollout_dev(torch.zeros((44, 3, 4), dtype=torch.float64, device="cuda:0"), 5)     # wrong robot count
+    with pytest.raises(_lib.MrfError):
+        fab.rollout_dev(torch.zeros((44, 2, 4), dtype=torch.float16, device="cuda:0"), 5)     # unsupported dtype
+    bad = _lib.default_config(2)
+    bad.estimate_goal, bad.estimate_robot = 1, 5
+    with pytest.raises(_lib.MrfError, match="estimate_robot"):
+        m.Handle(bad)

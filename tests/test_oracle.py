@@ -70,6 +70,20 @@ def test_o2_rollouts_match_o1_golden(gold):
     assert abs(cavg - float(gold["cart_avg"])) < 1e-11
 
 
+def test_o2_three_robot_rollout_matches_o1_golden(gold):
+    """3 Pandas, unequal sphere radii, dynamic and static (STATIC_OR_DYN_FABRICS = 0) fabrics."""
+    N = int(gold["ro3_N"])
+    for sd in (1, 0):
+        cfg = o2.default_config(3, static_or_dyn=sd)
+        for r in range(3):
+            for l in range(8):
+                cfg.r_robots[r][l] = float(gold["ro3_rr"][r][l])
+        qN, qdN, avg, _ = o2.rollout_jointspace(cfg, gold["ro3_rec"], N)
+        assert np.abs(qN - gold[f"ro3_sd{sd}_qN"]).max() < 1e-12
+        assert np.abs(qdN - gold[f"ro3_sd{sd}_qdN"]).max() < 1e-10
+        assert np.abs(avg - gold[f"ro3_sd{sd}_avg"]).max() < 1e-10
+
+
 def test_o1_live_matches_o2_small(built):
     """One live O1 evaluation (slow path, torch autodiff) so the generator of the golden file stays exercised."""
     from oracle import o1_fabrics as o1
