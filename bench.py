@@ -281,12 +281,11 @@ def ours(a):
     gathered = torch.empty((world, R + 1, B), dtype=tdt, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    d_work = d_rec.clone()        # the deadlock step mutates goals / weights in place, like the reference's lists
+
     def step():
         fab.rollout_dev(d_rec, H, avg_vel=avg, x_ee=xee, goal_est=gest)
-        goals.copy_(d_rec[14:17].permute(1, 0, 2))                    # caller's goal list (robot 1 gets the estimate)
-        goals[1].copy_(gest)
-        weights.copy_(d_rec[17])
-        fab.deadlock_dev(xee, goals, weights, sm_state, tstep, tdo, st_int, st_goal, avg_vel=avg, flag=flag)
+        fab.deadlock_rec_dev(xee, d_work, sm_state, tstep, tdo, st_int, st_goal, goal_est=gest, avg_vel=avg, flag=flag)
         if world > 1:
             result[:R].copy_(avg)
             result[R].copy_(flag)
@@ -313,10 +312,7 @@ def ours(a):
         kev[i][0].record()
         fab.rollout_dev(d_rec, H, avg_vel=avg, x_ee=xee, goal_est=gest)
         kev[i][1].record()
-        goals.copy_(d_rec[14:17].permute(1, 0, 2))
-        goals[1].copy_(gest)
-        weights.copy_(d_rec[17])
-        fab.deadlock_dev(xee, goals, weights, sm_state, tstep, tdo, st_int, st_goal, avg_vel=avg, flag=flag)
+        fab.deadlock_rec_dev(xee, d_work, sm_state, tstep, tdo, st_int, st_goal, goal_est=gest, avg_vel=avg, flag=flag)
         if world > 1:
             result[:R].copy_(avg)
             result[R].copy_(flag)

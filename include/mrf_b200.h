@@ -169,6 +169,19 @@ int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* goals, float*
                          int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
                          void* stream);
 
+/* The same step applied IN PLACE to the record tensor rec [MRF_REC][R][B] that mrf_rollout_dev / mrf_action_dev read: the
+ * goals are rows MRF_G0..MRF_G0+2 and the weights row MRF_W0 -- the reference likewise mutates the caller's goal /
+ * weight lists that compute_action then receives (example_pandas_Jointspace.py:379-380,423).  If goal_est [3][B] is
+ * given and MrfConfig.estimate_goal is set, robot `estimate_robot`'s goal is first replaced by it (:346-348). */
+int mrf_deadlock_rec_dev_f64(mrf_handle_t h, const double* x_ee, double* rec, const double* goal_est, const double* avg_vel,
+                             const double* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                             int32_t* time_deadlock_out, int32_t* st_int, double* st_goal, int32_t* flag, int64_t B,
+                             void* stream);
+int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, const float* goal_est, const float* avg_vel,
+                             const float* avg_sum, const int32_t* sm_state, const int32_t* time_step,
+                             int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
+                             void* stream);
+
 /* ------------------------------- host-pointer entries (AoS) -----------------------------------
  *   rec [B][R][MRF_REC]   obst [B][R][S][MRF_OBST]   action [B][R][MRF_DOF]
  *   avg_vel [B][R]  x_ee [B][R][3]  goal_est [B][3]  qN,qdN [B][R][N][MRF_DOF]  (nullable outputs skipped) */

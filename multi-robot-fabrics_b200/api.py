@@ -217,6 +217,24 @@ class Fabrics:
         return flag
 
 
+def _deadlock_rec_dev(self, x_ee, rec, sm_state, time_step, time_deadlock_out, st_int, st_goal, goal_est=None, avg_vel=None,
+                      avg_sum=None, flag=None):
+    """deadlock_checking in place on the record tensor (goal rows 14..16, weight row 17); see mrf_deadlock_rec_dev."""
+    import torch
+    p = self._prec(rec)
+    B = rec.shape[-1]
+    if flag is None:
+        flag = torch.empty((B,), dtype=torch.int32, device=rec.device)
+    fn = getattr(lib(), f"mrf_deadlock_rec_dev_{p}")
+    check(fn(self.handle.ptr, self._tp(x_ee), self._tp(rec), self._tp(goal_est), self._tp(avg_vel), self._tp(avg_sum),
+             self._tp(sm_state), self._tp(time_step), self._tp(time_deadlock_out), self._tp(st_int), self._tp(st_goal),
+             self._tp(flag), B, self._stream()), "mrf_deadlock_rec_dev")
+    return flag
+
+
+Fabrics.deadlock_rec_dev = _deadlock_rec_dev
+
+
 def to_soa(rec):
     """(B,R,F) array-of-records -> (F,R,B) structure-of-arrays (numpy or torch)."""
     if isinstance(rec, np.ndarray):

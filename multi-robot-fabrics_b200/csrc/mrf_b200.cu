@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(kActThreads)
 // deadlock heuristic, one thread per scenario (deadlock_prevention.py:50-118)
 // ------------------------------------------------------------------------------------------------
 struct DlCfg {
+    // goal element (robot i, component k, scenario b) at goals[i * g_sr + k * g_sc + b]; weight at weights[i * w_sr + b]
+    long long g_sr, g_sc, w_sr;
+    int est_robot; // >= 0: goals of this robot are first overwritten by goal_est (RF-CV), -1: off
     int R, time_wait, time_gate;
     double avg_vel_constant, dist_constant, w_follower, w_leader, goal_scale, dist_endeff, backoff;
 };
@@ -259,10 +262,13 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
                                 const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
                                 const int* __restrict__ sm_state,
                                 const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
-                                T* __restrict__ st_goal, int* __restrict__ flag, long long B) {
+                                T* __restrict__ st_goal, int* __restrict__ flag, const T* __restrict__ goal_est,
+                                long long B) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int R = c.R;
+    if (c.est_robot >= 0 && goal_est != nullptr) // goal_pandas[1] = estimate (example_pandas_Jointspace.py:346-348)
+        for (int k = 0; k < 3; ++k) goals[c.est_robot * c.g_sr + k * c.g_sc + b] = goal_est[(long long)k * B + b];
     // the reference does this arithmetic in float64 whatever the planner precision
     double x[MRF_MAX_ROBOTS][3], g[MRF_MAX_ROBOTS][3], dist_goal[MRF_MAX_ROBOTS];
     int st[MRF_MAX_ROBOTS];
@@ -270,7 +276,7 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
     for (int i = 0; i < R; ++i) {
         for (int k = 0; k < 3; ++k) {
             x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
-            g[i][k] = (double)goals[((long long)i * 3 + k) * B + b];
+            g[i][k] = (double)goals[i * c.g_sr + k * c.g_sc + b];
         }
         dist_goal[i] = np_norm3(__dsub_rn(x[i][0], g[i][0]), __dsub_rn(x[i][1], g[i][1]), __dsub_rn(x[i][2], g[i][2]));
         st[i] = sm_state[(long long)i * B + b];
@@ -333,9 +339,9 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
         t_out = t_out + 1;
     }
     if (apply) {
-        weights[(long long)i_leader * B + b] = (T)c.w_leader;
-        weights[(long long)i_follower * B + b] = (T)c.w_follower;
-        for (int k = 0; k < 3; ++k) goals[((long long)i_follower * 3 + k) * B + b] = (T)g0[k];
+        weights[i_leader * c.w_sr + b] = (T)c.w_leader;
+        weights[i_follower * c.w_sr + b] = (T)c.w_follower;
+        for (int k = 0; k < 3; ++k) goals[i_follower * c.g_sr + k * c.g_sc + b] = (T)g0[k];
     }
     tdo[b] = t_out;
     st_int[0 * B + b] = i_leader;
@@ -841,7 +847,7 @@ static int kinematics_dev(mrf_handle_t h, const T* q, const T* qd, T* x, T* v, T
 template <typename T>
 static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const T* avg_sum,
                         const int32_t* sm_state, const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal,
-                        int32_t* flag, int64_t B, void* stream) {
+                        int32_t* flag, int64_t B, void* stream, bool rec_layout = false, const T* goal_est = nullptr) {
     if (!h || !x_ee || !goals || !weights || !sm_state || !time_step || !tdo || !st_int || !st_goal)
         return fail(MRF_EINVAL, "mrf_deadlock: null argument");
     if ((avg_vel == nullptr) == (avg_sum == nullptr))
@@ -849,10 +855,13 @@ static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, con
     if (B <= 0) return fail(MRF_EINVAL, "mrf_deadlock: B must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
     const MrfConfig& c = h->cfg;
-    DlCfg d{c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
+    const long long Rl = c.n_robots;
+    DlCfg d{rec_layout ? (long long)B : 3 * (long long)B, rec_layout ? Rl * B : (long long)B, (long long)B,
+            (rec_layout && c.estimate_goal && goal_est && c.estimate_robot < c.n_robots) ? c.estimate_robot : -1,
+            c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
             c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
     deadlock_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, (long long)B);
+        d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, goal_est, (long long)B);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;
@@ -903,6 +912,31 @@ extern "C" int mrf_deadlock_dev_f32(mrf_handle_t h, const float* x_ee, float* go
                                     void* stream) {
     return deadlock_dev<float>(h, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
                              st_goal, flag, B, stream);
+}
+
+// deadlock step operating in place on the SoA record tensor: goals = rows MRF_G0..+2, weights = row MRF_W0
+template <typename T>
+static int deadlock_rec_dev(mrf_handle_t h, const T* x_ee, T* rec, const T* goal_est, const T* avg_vel, const T* avg_sum,
+                            const int32_t* sm_state, const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal,
+                            int32_t* flag, int64_t B, void* stream) {
+    if (!h || !rec) return fail(MRF_EINVAL, "mrf_deadlock_rec: null argument");
+    const long long RB = (long long)h->cfg.n_robots * B;
+    return deadlock_dev<T>(h, x_ee, rec + MRF_G0 * RB, rec + MRF_W0 * RB, avg_vel, avg_sum, sm_state, time_step, tdo, st_int,
+                           st_goal, flag, B, stream, true, goal_est);
+}
+extern "C" int mrf_deadlock_rec_dev_f64(mrf_handle_t h, const double* x_ee, double* rec, const double* goal_est,
+                                        const double* avg_vel, const double* avg_sum, const int32_t* sm_state,
+                                        const int32_t* time_step, int32_t* time_deadlock_out, int32_t* st_int,
+                                        double* st_goal, int32_t* flag, int64_t B, void* stream) {
+    return deadlock_rec_dev<double>(h, x_ee, rec, goal_est, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
+                                    st_goal, flag, B, stream);
+}
+extern "C" int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, const float* goal_est,
+                                        const float* avg_vel, const float* avg_sum, const int32_t* sm_state,
+                                        const int32_t* time_step, int32_t* time_deadlock_out, int32_t* st_int,
+                                        float* st_goal, int32_t* flag, int64_t B, void* stream) {
+    return deadlock_rec_dev<float>(h, x_ee, rec, goal_est, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
+                                   st_goal, flag, B, stream);
 }
 
 // ---------------------------------- host-pointer entries ----------------------------------------

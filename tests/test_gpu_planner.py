@@ -278,3 +278,40 @@ def test_closed_loop_episodes_match_cpu_loop(built, R, kw):
         assert np.abs(res["q"][b] - q).max() < 1e-7, b
         assert res["deadlock_steps"][b] == n_flags and res["steps_to_success"][b] == done_at
     assert n_cmp >= B - 3 and res["steps"] == T
+
+
+def test_deadlock_in_place_on_record_tensor(built):
+    """mrf_deadlock_rec_dev (goals / weights rows of the SoA record tensor, RF-CV estimate applied first) equals the
+    separate-array entry."""
+    import torch
+    from multi_robot_fabrics_b200.api import to_soa
+    R, N, B = 3, 10, 300
+    rec = m.scenarios.generate(B, R, seed=55)
+    rec[:, :, 7:14] *= 0.1
+    fab = Fabrics(R, device=0, estimate_goal=1)
+    dev = "cuda:0"
+    for dt in (torch.float64, torch.float32):
+        d_rec = torch.from_numpy(to_soa(rec)).to(dev, dtype=dt)
+        a = torch.empty((R, B), dtype=dt, device=dev)
+        x = torch.empty((R, 3, B), dtype=dt, device=dev)
+        ge = torch.empty((3, B), dtype=dt, device=dev)
+        fab.rollout_dev(d_rec, N, avg_vel=a, x_ee=x, goal_est=ge)
+        x[1, :, ::2] = x[0, :, ::2] + 0.03                     # near-contact hands in every other scenario
+        sm = torch.zeros((R, B), dtype=torch.int32, device=dev)
+        ts = torch.full((B,), 50, dtype=torch.int32, device=dev)
+        mk = lambda: (torch.full((B,), 1000, dtype=torch.int32, device=dev),
+                      torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous(),
+                      torch.zeros((3, B), dtype=dt, device=dev))
+        goals = d_rec[14:17].permute(1, 0, 2).contiguous()
+        goals[1] = ge
+        w = d_rec[17].clone()
+        tdo1, si1, sg1 = mk()
+        f1 = fab.deadlock_dev(x, goals, w, sm, ts, tdo1, si1, sg1, avg_vel=a)
+        work = d_rec.clone()
+        tdo2, si2, sg2 = mk()
+        f2 = fab.deadlock_rec_dev(x, work, sm, ts, tdo2, si2, sg2, goal_est=ge, avg_vel=a)
+        torch.cuda.synchronize()
+        assert torch.equal(f1, f2) and f1.sum() > 20 and torch.equal(tdo1, tdo2) and torch.equal(si1, si2)
+        assert torch.equal(work[14:17].permute(1, 0, 2), goals) and torch.equal(work[17], w)
+        assert torch.equal(work[0:14], d_rec[0:14]) and torch.equal(work[18:], d_rec[18:])
+    fab.close()
