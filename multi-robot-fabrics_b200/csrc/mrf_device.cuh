@@ -495,6 +495,43 @@ template <typename T> MRF_HD void chol_solve6(T (&M)[6][6], T eps, const T* b, T
     }
 }
 
+// The geometry and the forced system factored together as pairs (lo = G, hi = F): one dependent chain instead of two,
+// packed FP32x2 arithmetic on sm_100a.
+template <typename T> MRF_HD void chol_solve6_pair(P2<T> (&M)[6][6], T eps, const P2<T>* b, P2<T>* x) {
+    P2<T> inv[6];
+    const P2<T> m1 = psplat(T(-1)), e2 = psplat(eps);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        P2<T> s = padd(M[j][j], e2);
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = pfma(pmul(M[k][j], m1), M[k][j], s);
+        P2<T> r = prsqrt(s);
+        inv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            P2<T> t = M[j][i];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = pfma(pmul(M[k][j], m1), M[k][i], t);
+            M[j][i] = pmul(t, r);
+        }
+    }
+    P2<T> y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        P2<T> s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = pfma(pmul(M[k][i], m1), y[k], s);
+        y[i] = pmul(s, inv[i]);
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        P2<T> s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s = pfma(pmul(M[i][k], m1), x[k], s);
+        x[i] = pmul(s, inv[i]);
+    }
+}
+
 template <typename T> MRF_HD void attractor_scalars(T n, T w, T& dpsi, T& m2) {
     // attractor_potential 5(|x| + 0.1 log(1 + exp(-20|x|))): d/d|x| = 5 tanh(10|x|);
     // attractor_metric (1.7 exp(-(0.75|x|)^2) + 0.3) I, L = xdot^T m xdot -> M = 2 m I
@@ -524,22 +561,20 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     T num = T(0); // qdot . (f_g - f_e,g)
 
     // ---- joint-limit leaves (limit_geometry "-0.1/x xdot^2", limit_finsler "0.1/x s xdot^2") ----
+    // lower and upper leaf of a joint as one pair (x = q - lo | hi - q, xdot = qd | -qd):
+    //   M = 0.2 s/x,  f = M h = -0.02 s xdot^2/x^2,  f - f_e = 0.08 s xdot^2/x^2
 #pragma unroll
     for (int i = 0; i < kDof; ++i) {
-#pragma unroll
-        for (int up = 0; up < 2; ++up) {
-            T x = up ? cfg.lim[i][1] - q[i] : q[i] - cfg.lim[i][0];
-            T xd = up ? -qd[i] : qd[i];
-            T s = xd > T(0) ? T(0) : (xd < T(0) ? T(1) : T(0.5));
-            T ix = Mth<T>::rcp(x);
-            T xd2 = xd * xd;
-            T Ml = T(0.2) * s * ix;
-            T fl = Ml * (T(-0.1) * xd2 * ix);
-            T fel = T(-0.1) * s * xd2 * ix * ix;
-            if (i < 6) G.M[i][i] += Ml; else G.m7 += Ml;
-            G.f[i] += up ? -fl : fl;
-            num += xd * (fl - fel);
-        }
+        const P2<T> x2 = pmk(q[i] - cfg.lim[i][0], cfg.lim[i][1] - q[i]);
+        const T sl = qd[i] > T(0) ? T(0) : (qd[i] < T(0) ? T(1) : T(0.5)); // lower side switch; upper = 1 - sl
+        const P2<T> ix = prcp(x2);
+        const P2<T> t = pmul(pmk(sl, T(1) - sl), ix);                          // s/x
+        const P2<T> u = pmul(pmul(psplat(qd[i] * qd[i]), ix), t);              // s xdot^2/x^2
+        const T Ml = T(0.2) * (plo(t) + phi(t));
+        if (i < 6) G.M[i][i] += Ml; else G.m7 += Ml;
+        const T du = plo(u) - phi(u);                                           // lower pushes +, upper -
+        G.f[i] += T(-0.02) * du;
+        num += qd[i] * (T(0.08) * du);
     }
 
     V3<T> org[6];
@@ -670,9 +705,25 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
 
     // ---- solves and speed-control damper ----
     T hg[kDof], hf[kDof];
-    chol_solve6(G.M, e, G.f, hg);
+    if (sizeof(T) == 4) {
+        P2<T> M2[6][6], b2[6], x2[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            b2[j] = pmk(G.f[j], F.f[j]);
+#pragma unroll
+            for (int i = 0; i <= j; ++i) M2[i][j] = pmk(G.M[i][j], F.M[i][j]);
+        }
+        chol_solve6_pair(M2, e, b2, x2);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            hg[j] = plo(x2[j]);
+            hf[j] = phi(x2[j]);
+        }
+    } else {
+        chol_solve6(G.M, e, G.f, hg);
+        chol_solve6(F.M, e, F.f, hf);
+    }
     hg[6] = G.f[6] * Mth<T>::rcp(G.m7 + e);
-    chol_solve6(F.M, e, F.f, hf);
     hf[6] = F.f[6] * Mth<T>::rcp(F.m7 + e);
     T qq = T(0), qhg = T(0), qhf = T(0);
 #pragma unroll
