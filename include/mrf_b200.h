@@ -182,6 +182,20 @@ int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, cons
                              int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
                              void* stream);
 
+/* Batched pick-and-place state machine step: StateMachine.get_state_machine_panda and
+ * get_gripper_action_panda, multi_robot_fabrics/others_planner/state_machine.py:70-84,133-214.
+ *   nr_blocks: HOST pointer, blocks per robot [R]
+ *   x_ee, goal_block, start_goal [R][3][B] (in);  q_grip [R][2][B] (in)
+ *   goal, above [R][3][B] and weight [R][B] (in/out: get_goal_robot(), goal_above_block, get_weight_goal0())
+ *   st [6][R][B] (in/out): state_machine_panda (initial 1), nr_blocks_success, nr_blocks_failed, time_gripping,
+ *                          gripper closed (0/1), stop_time;   grip_action [R][2][B] (out, nullable) */
+int mrf_fsm_dev_f64(mrf_handle_t h, const int32_t* nr_blocks, const double* x_ee, const double* q_grip,
+                    const double* goal_block, const double* start_goal, double* goal, double* above, double* weight,
+                    int32_t* st, double* grip_action, int64_t B, void* stream);
+int mrf_fsm_dev_f32(mrf_handle_t h, const int32_t* nr_blocks, const float* x_ee, const float* q_grip,
+                    const float* goal_block, const float* start_goal, float* goal, float* above, float* weight, int32_t* st,
+                    float* grip_action, int64_t B, void* stream);
+
 /* ------------------------------- host-pointer entries (AoS) -----------------------------------
  *   rec [B][R][MRF_REC]   obst [B][R][S][MRF_OBST]   action [B][R][MRF_DOF]
  *   avg_vel [B][R]  x_ee [B][R][3]  goal_est [B][3]  qN,qdN [B][R][N][MRF_DOF]  (nullable outputs skipped) */

@@ -46,7 +46,7 @@ EXPORTS = [
     "mrf_version", "mrf_last_error", "mrf_config_default", "mrf_create", "mrf_destroy", "mrf_device_count",
     "mrf_action_dev_f64", "mrf_action_dev_f32", "mrf_rollout_dev_f64", "mrf_rollout_dev_f32",
     "mrf_rollout_cart_dev_f64", "mrf_rollout_cart_dev_f32", "mrf_kinematics_dev_f64", "mrf_kinematics_dev_f32",
-    "mrf_deadlock_dev_f64", "mrf_deadlock_dev_f32", "mrf_deadlock_rec_dev_f64", "mrf_deadlock_rec_dev_f32", "mrf_obstacles_dev_f64", "mrf_obstacles_dev_f32", "mrf_point_action_dev_f64", "mrf_point_action_dev_f32",
+    "mrf_deadlock_dev_f64", "mrf_deadlock_dev_f32", "mrf_deadlock_rec_dev_f64", "mrf_deadlock_rec_dev_f32", "mrf_fsm_dev_f64", "mrf_fsm_dev_f32", "mrf_obstacles_dev_f64", "mrf_obstacles_dev_f32", "mrf_point_action_dev_f64", "mrf_point_action_dev_f32",
     "mrf_point_action_host_f64", "mrf_action_host_f64", "mrf_action_host_f32",
     "mrf_rollout_host_f64", "mrf_rollout_host_f32", "mrf_rollout_cart_host_f64", "mrf_rollout_cart_host_f32",
     "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak", "mrf_set_coop_max_batch",
@@ -79,6 +79,7 @@ def lib():
         getattr(L, f"mrf_kinematics_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_deadlock_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_deadlock_rec_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        getattr(L, f"mrf_fsm_dev_{p}").argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_obstacles_dev_{p}").argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_action_host_{p}").argtypes = [vp, i32, i32, vp, i32, vp, vp, i64]
         getattr(L, f"mrf_rollout_host_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i64]

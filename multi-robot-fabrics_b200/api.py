@@ -235,6 +235,20 @@ def _deadlock_rec_dev(self, x_ee, rec, sm_state, time_step, time_deadlock_out, s
 Fabrics.deadlock_rec_dev = _deadlock_rec_dev
 
 
+def _fsm_dev(self, nr_blocks, x_ee, q_grip, goal_block, start_goal, goal, above, weight, st, grip_action=None):
+    """Batched pick-and-place state machine step (state_machine.py:133-214); goal/above/weight/st updated in place."""
+    p = self._prec(x_ee)
+    B = x_ee.shape[-1]
+    nb = np.ascontiguousarray(nr_blocks, dtype=np.int32)
+    fn = getattr(lib(), f"mrf_fsm_dev_{p}")
+    check(fn(self.handle.ptr, hptr(nb), self._tp(x_ee), self._tp(q_grip), self._tp(goal_block), self._tp(start_goal),
+             self._tp(goal), self._tp(above), self._tp(weight), self._tp(st), self._tp(grip_action), B, self._stream()),
+          "mrf_fsm_dev")
+
+
+Fabrics.fsm_dev = _fsm_dev
+
+
 def to_soa(rec):
     """(B,R,F) array-of-records -> (F,R,B) structure-of-arrays (numpy or torch)."""
     if isinstance(rec, np.ndarray):

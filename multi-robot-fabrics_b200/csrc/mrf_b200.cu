@@ -548,6 +548,92 @@ __global__ void __launch_bounds__(kActThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// pick-and-place state machine, one thread per (robot, scenario):
+// StateMachine.get_state_machine_panda + get_gripper_action_panda
+// (multi_robot_fabrics/others_planner/state_machine.py:70-84,133-214).  Distances are float64 with numpy's rounding
+// (np_norm3) so the threshold tests agree with the reference bit for bit.
+//   x_ee, goal_block, start_goal, goal (in/out), above (in/out)  [R][3][B];  q_grip, grip_action [R][2][B]
+//   weight [R][B] (in/out);  st [6][R][B] in/out: state, nr_success, nr_failed, time_gripping, gripper_closed, stop_time
+// ------------------------------------------------------------------------------------------------
+struct FsmCfg {
+    int R;
+    int nr_blocks[MRF_MAX_ROBOTS];
+};
+template <typename T>
+__global__ void fsm_kernel(FsmCfg c, const T* __restrict__ x_ee, const T* __restrict__ q_grip,
+                           const T* __restrict__ goal_block, const T* __restrict__ start_goal, T* __restrict__ goal,
+                           T* __restrict__ above, T* __restrict__ weight, int* __restrict__ st, T* __restrict__ grip_action,
+                           long long B) {
+    const long long total = (long long)c.R * B;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int r = (int)(idx / B);
+    const long long b = idx - (long long)r * B;
+    auto v3 = [&](const T* p, int k) { return (double)p[((long long)r * 3 + k) * B + b]; };
+    const double x[3] = {v3(x_ee, 0), v3(x_ee, 1), v3(x_ee, 2)};
+    const double gb[3] = {v3(goal_block, 0), v3(goal_block, 1), v3(goal_block, 2)};
+    const double sg[3] = {v3(start_goal, 0), v3(start_goal, 1), v3(start_goal, 2)};
+    double g[3] = {v3(goal, 0), v3(goal, 1), v3(goal, 2)};
+    double ab[3] = {v3(above, 0), v3(above, 1), v3(above, 2)};
+    const double qg0 = (double)q_grip[((long long)r * 2 + 0) * B + b], qg1 = (double)q_grip[((long long)r * 2 + 1) * B + b];
+    int state = st[0 * total + idx], n_ok = st[1 * total + idx], n_fail = st[2 * total + idx], t_grip = st[3 * total + idx];
+    int closed = st[4 * total + idx], stop = st[5 * total + idx];
+    double w = (double)weight[idx];
+    const double pre[3] = {gb[0], gb[1], __dadd_rn(gb[2], 0.1)};                                   // :134-135
+    auto norm2 = [](double a, double bb) { return __dsqrt_rn(__fma_rn(bb, bb, __dmul_rn(a, a))); };
+    const double d_start = np_norm3(__dsub_rn(x[0], sg[0]), __dsub_rn(x[1], sg[1]), __dsub_rn(x[2], sg[2]));
+    const double d_pre = norm2(__dsub_rn(x[0], pre[0]), __dsub_rn(x[1], pre[1]));
+    const double d_block = np_norm3(__dsub_rn(x[0], gb[0]), __dsub_rn(x[1], gb[1]), __dsub_rn(x[2], gb[2]));
+    const double d_open = norm2(__dsub_rn(qg0, 0.04), __dsub_rn(qg1, 0.04));
+    if (n_ok > c.nr_blocks[r] - 1) {                                                               // :141-142
+        state = 10;
+    } else if (gb[2] < 0.6) {                                                                      // :143-147
+        n_ok += 1; n_fail += 1; state = 0;
+    }
+    const int s = state;
+    if (s == 0) {                                                                                  // :150-155
+        g[0] = sg[0]; g[1] = sg[1]; g[2] = sg[2]; closed = 0;
+        if (d_start < 0.05) state = 1;
+    } else if (s == 1) {                                                                           // :158-162
+        g[0] = pre[0]; g[1] = pre[1]; g[2] = pre[2];
+        if (d_pre < 0.013) state = 2;
+    } else if (s == 2) {                                                                           // :164-170
+        g[0] = gb[0]; g[1] = gb[1]; g[2] = gb[2];
+        if (d_block < 0.013) { closed = 1; w = 0.0; state = 3; }
+    } else if (s == 3) {                                                                           // :172-181
+        g[0] = gb[0]; g[1] = gb[1]; g[2] = gb[2];
+        ab[0] = gb[0]; ab[1] = gb[1]; ab[2] = __dadd_rn(gb[2], 0.15);
+        t_grip += 1;
+        if ((double)t_grip > 0.3 / 0.01) { t_grip = 0; g[0] = sg[0]; g[1] = sg[1]; g[2] = sg[2]; w = 2.0; state = 12; }
+    } else if (s == 12) {                                                                          // :183-186
+        g[0] = ab[0]; g[1] = ab[1]; g[2] = ab[2];
+        if (norm2(__dsub_rn(x[0], g[0]), __dsub_rn(x[1], g[1])) < 0.04) state = 4;
+    } else if (s == 4) {                                                                           // :188-194
+        g[0] = sg[0]; g[1] = sg[1]; g[2] = sg[2];
+        if (d_start < 0.15) { state = 5; closed = 0; }
+    } else if (s == 5) {                                                                           // :196-200
+        if (d_open < 0.005) { state = 0; n_ok += 1; g[0] = sg[0]; g[1] = sg[1]; g[2] = sg[2]; }
+    } else if (s == 10) {                                                                          // :202-206
+        stop = 1;
+    }
+    // gripper action (:70-84)
+    double a0 = 0.0, a1 = 0.0;
+    if (closed) { a0 = -0.05; a1 = -0.05; }
+    else if (d_open > 0.005) { a0 = qg0 > 0.04 ? -0.4 : 0.4; a1 = qg1 > 0.04 ? -0.4 : 0.4; }
+    for (int k = 0; k < 3; ++k) {
+        goal[((long long)r * 3 + k) * B + b] = (T)g[k];
+        above[((long long)r * 3 + k) * B + b] = (T)ab[k];
+    }
+    weight[idx] = (T)w;
+    st[0 * total + idx] = state; st[1 * total + idx] = n_ok; st[2 * total + idx] = n_fail; st[3 * total + idx] = t_grip;
+    st[4 * total + idx] = closed; st[5 * total + idx] = stop;
+    if (grip_action) {
+        grip_action[((long long)r * 2 + 0) * B + b] = (T)a0;
+        grip_action[((long long)r * 2 + 1) * B + b] = (T)a1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // FMA peak micro-benchmark: the roofline denominator for the compute-bound rollout (MEASURED_PEAKS.json
 // holds HBM and bf16 tensor peaks only).  8 independent FMA chains per thread.
 // ------------------------------------------------------------------------------------------------
@@ -1437,6 +1523,35 @@ extern "C" int mrf_point_action_host_f64(mrf_handle_t h, const double* rec, int 
     rc = download_aos<double>(h, action, B, 3, 6, 7);
     if (rc) return rc;
     return finish_timed(h);
+}
+
+template <typename T>
+static int fsm_dev(mrf_handle_t h, const int32_t* nr_blocks, const T* x_ee, const T* q_grip, const T* goal_block,
+                   const T* start_goal, T* goal, T* above, T* weight, int32_t* st, T* grip_action, int64_t B, void* stream) {
+    if (!h || !nr_blocks || !x_ee || !q_grip || !goal_block || !start_goal || !goal || !above || !weight || !st)
+        return fail(MRF_EINVAL, "mrf_fsm: null argument");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_fsm: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    FsmCfg c;
+    c.R = h->cfg.n_robots;
+    for (int r = 0; r < MRF_MAX_ROBOTS; ++r) c.nr_blocks[r] = r < c.R ? nr_blocks[r] : 0;
+    const long long total = (long long)c.R * B;
+    fsm_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(c, x_ee, q_grip, goal_block, start_goal,
+                                                                                      goal, above, weight, st, grip_action,
+                                                                                      (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+extern "C" int mrf_fsm_dev_f64(mrf_handle_t h, const int32_t* nr_blocks, const double* x_ee, const double* q_grip,
+                               const double* goal_block, const double* start_goal, double* goal, double* above,
+                               double* weight, int32_t* st, double* grip_action, int64_t B, void* stream) {
+    return fsm_dev<double>(h, nr_blocks, x_ee, q_grip, goal_block, start_goal, goal, above, weight, st, grip_action, B, stream);
+}
+extern "C" int mrf_fsm_dev_f32(mrf_handle_t h, const int32_t* nr_blocks, const float* x_ee, const float* q_grip,
+                               const float* goal_block, const float* start_goal, float* goal, float* above, float* weight,
+                               int32_t* st, float* grip_action, int64_t B, void* stream) {
+    return fsm_dev<float>(h, nr_blocks, x_ee, q_grip, goal_block, start_goal, goal, above, weight, st, grip_action, B, stream);
 }
 
 template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {

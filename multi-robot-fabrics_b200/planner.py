@@ -437,3 +437,64 @@ class deadlockprevention:  # noqa: N801 (the reference's class name)
             if w[0, i] != float(np.asarray(goal_weights[i]).reshape(-1)[0]):
                 goal_weights[i] = w[0, i]
         return goal_robots, goal_weights, int(tdo[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class StateMachine:
+    """state_machine.py drop-in (Panda branch): the decision logic runs in the CUDA fsm kernel with B = 1.
+    `fk_fun_ee(q)` may be any callable returning the hand position (the reference passes a CasADi function)."""
+
+    def __init__(self, start_goal, nr_robots, nr_blocks, fk_fun_ee, robot_types, device: int = 0):
+        import torch
+        self.torch = torch
+        self.fk_fun_ee = fk_fun_ee
+        self.nr_blocks_panda = nr_blocks
+        self.start_goal = np.asarray(start_goal, dtype=np.float64).reshape(3)
+        self.fab = Fabrics(config=default_config(1), device=device)
+        dev = f"cuda:{device}"
+        t = lambda a, dt=torch.float64: torch.tensor(a, dtype=dt, device=dev)
+        self._start = t(self.start_goal).reshape(1, 3, 1)
+        self._goal = self._start.clone()
+        self._above = torch.zeros((1, 3, 1), dtype=torch.float64, device=dev)
+        self._weight = t([[2.0]])
+        self._st = t([[[1]], [[0]], [[0]], [[0]], [[0]], [[0]]], torch.int32)
+        self._grip = torch.zeros((1, 2, 1), dtype=torch.float64, device=dev)
+        self._dev = dev
+
+    def get_state_machine_panda(self, q_robot, q_robot_gripper, goal_block, robot_type="panda"):
+        t = self.torch
+        x = np.asarray(self.fk_fun_ee(q_robot), dtype=np.float64).reshape(3)
+        mk = lambda a, n: t.tensor(np.asarray(a, dtype=np.float64).reshape(1, n, 1), dtype=t.float64, device=self._dev)
+        self.fab.fsm_dev([int(self.nr_blocks_panda)], mk(x, 3), mk(q_robot_gripper, 2), mk(goal_block, 3), self._start,
+                         self._goal, self._above, self._weight, self._st, self._grip)
+        t.cuda.synchronize()
+        return int(self._st[0, 0, 0])
+
+    @property
+    def state_machine_panda(self):
+        return int(self._st[0, 0, 0])
+
+    def get_goal_robot(self):
+        return self._goal[0, :, 0].cpu().numpy()
+
+    def get_weight_goal0(self):
+        w = float(self._weight[0, 0])
+        return int(w) if w == int(w) else w
+
+    def get_nr_blocks_picked(self):
+        return int(self._st[1, 0, 0])
+
+    def get_success_rate(self):
+        return (int(self._st[1, 0, 0]) - int(self._st[2, 0, 0])) / self.nr_blocks_panda
+
+    def get_gripper_action_panda(self, q_panda_gripper):
+        """The action computed with the last get_state_machine_panda call's gripper state (same q as the reference's
+        call order, example_pandas_Jointspace.py:301,447)."""
+        q = np.asarray(q_panda_gripper, dtype=np.float64).reshape(2)
+        closed = int(self._st[4, 0, 0])
+        a = np.zeros(2)
+        if closed:
+            a[:] = -0.05
+        elif np.linalg.norm(q - np.array([0.04, 0.04])) > 0.005:
+            a = np.where(q > 0.04, -0.4, 0.4)
+        return a

@@ -315,3 +315,41 @@ def test_deadlock_in_place_on_record_tensor(built):
         assert torch.equal(work[14:17].permute(1, 0, 2), goals) and torch.equal(work[17], w)
         assert torch.equal(work[0:14], d_rec[0:14]) and torch.equal(work[18:], d_rec[18:])
     fab.close()
+
+
+def test_fsm_kernel_matches_reference_golden(built):
+    """The batched state-machine kernel replays the reference class's own sequences (all 8 cases as one batch): state,
+    goal, weight and gripper action identical at every step; plus the StateMachine drop-in class on one case."""
+    import torch
+    g = np.load(os.path.join(GOLD, "fsm_golden.npz"))
+    C_ = int(g["n_cases"])
+    T = len(g["c0_x"])
+    dev = "cuda:0"
+    for nb in sorted(set(int(g[f"c{c}_nr_blocks"]) for c in range(C_))):
+        cases = [c for c in range(C_) if int(g[f"c{c}_nr_blocks"]) == nb]
+        B = len(cases)
+        fab = Fabrics(1, device=0)
+        col = lambda key, t: torch.tensor(np.stack([g[f"c{c}_{key}"][t] for c in cases], axis=-1)[None], dtype=torch.float64, device=dev)
+        start = torch.tensor(np.stack([g[f"c{c}_start"] for c in cases], axis=-1)[None], dtype=torch.float64, device=dev)
+        goal, above = start.clone(), torch.zeros_like(start)
+        weight = torch.full((1, B), 2.0, dtype=torch.float64, device=dev)
+        st = torch.zeros((6, 1, B), dtype=torch.int32, device=dev)
+        st[0] = 1
+        grip = torch.zeros((1, 2, B), dtype=torch.float64, device=dev)
+        for t in range(T):
+            fab.fsm_dev([nb], col("x", t), col("qg", t), col("gb", t), start, goal, above, weight, st, grip)
+            exp_state = np.array([g[f"c{c}_state"][t] for c in cases])
+            assert np.array_equal(st[0, 0].cpu().numpy(), exp_state), t
+            assert np.array_equal(goal[0].cpu().numpy().T, np.stack([g[f"c{c}_goal"][t] for c in cases]))
+            assert np.array_equal(weight[0].cpu().numpy(), np.array([g[f"c{c}_weight"][t] for c in cases]))
+            assert np.array_equal(grip[0].cpu().numpy().T, np.stack([g[f"c{c}_grip"][t] for c in cases]))
+        fab.close()
+    # drop-in class
+    holder = {}
+    sm = P.StateMachine(g["c0_start"], 2, int(g["c0_nr_blocks"]), lambda q: holder["x"], ["panda", "panda"])
+    for t in range(0, 300):
+        holder["x"] = g["c0_x"][t]
+        s = sm.get_state_machine_panda(np.zeros(7), g["c0_qg"][t], g["c0_gb"][t], "panda")
+        assert s == g["c0_state"][t] and np.array_equal(sm.get_goal_robot(), g["c0_goal"][t])
+        assert sm.get_weight_goal0() == g["c0_weight"][t]
+        assert np.array_equal(sm.get_gripper_action_panda(g["c0_qg"][t]), g["c0_grip"][t])

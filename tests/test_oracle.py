@@ -191,3 +191,19 @@ def test_point_mass_o2_matches_o1_golden(gold):
         a = o2.point_action(cfg, pos[i], vel[i], goals[i], 1.0, 0.2, obst, [1.0] * 6, pos[others][:, 0:2],
                             vel[others][:, 0:2], np.zeros((3, 2)), [0.2] * 3)
         assert np.abs(a - gold["pm_dyn"][i]).max() < 1e-12
+
+
+def test_fsm_restatement_matches_reference_golden():
+    """the state-machine restatement replays sequences produced by the reference's own class."""
+    from oracle.fsm_ref import FsmOracle
+    g = np.load(os.path.join(GOLD, "fsm_golden.npz"))
+    seen = set()
+    for c in range(int(g["n_cases"])):
+        p = f"c{c}_"
+        o = FsmOracle(g[p + "start"], int(g[p + "nr_blocks"]))
+        for t in range(len(g[p + "x"])):
+            st = o.step(g[p + "x"][t], g[p + "qg"][t], g[p + "gb"][t])
+            seen.add(st)
+            assert st == g[p + "state"][t] and np.array_equal(o.goal, g[p + "goal"][t]) and o.weight == g[p + "weight"][t]
+            assert np.array_equal(o.gripper_action(g[p + "qg"][t]), g[p + "grip"][t])
+    assert seen == {0, 1, 2, 3, 4, 5, 10, 12}
