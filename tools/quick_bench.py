@@ -29,6 +29,21 @@ def main():
             rs = B * 3 * N / (best * 1e-3)
             print(json.dumps(dict(kernel="rollout", dtype=name, B=B, N=N, ms_best=best, ms_med=med, robot_steps_per_s=rs,
                                   tflops_alg=rs * 13.4e3 / 1e12)))
+    # executed action with staged obstacles (configs C2 / C4 shapes: n = 4 spheres per link)
+    for Rr, Bb in ((2, 65536), (3, 65536)):
+        fabr = Fabrics(Rr)
+        recr = np.tile(m.scenarios.generate(4096, Rr, seed=1, weight_goal_1=20.0), (Bb // 4096, 1, 1))
+        dr = torch.from_numpy(to_soa(recr)).to("cuda:0", dtype=torch.float32)
+        q, qd = dr[0:7].contiguous(), dr[7:14].contiguous()
+        obst = fabr.obstacles_dev(q, qd, n_per_link=4, vel_mode=0)
+        act = torch.empty((7, Rr, Bb), dtype=torch.float32, device="cuda:0")
+        t_ob, _ = timeit(lambda: fabr.obstacles_dev(q, qd, n_per_link=4, vel_mode=0, obst=obst))
+        t_ac, _ = timeit(lambda: fabr.action_dev(dr, obst, action=act))
+        S = obst.shape[0]
+        print(json.dumps(dict(kernel="obstacles+action", robots=Rr, B=Bb, S=S, ms_obstacles=t_ob, ms_action=t_ac,
+                              actions_per_s=Bb * Rr / (t_ac * 1e-3), tflops_alg=Bb * Rr / (t_ac * 1e-3) * (5700 + 480 * S) / 1e12,
+                              obst_GBps=obst.numel() * 4 / (t_ob * 1e-3) / 1e9)))
+        fabr.close()
     # single-scenario latency
     d1 = torch.from_numpy(to_soa(base[:1])).to("cuda:0", dtype=torch.float32)
     avg1 = torch.empty((3, 1), dtype=torch.float32, device="cuda:0")
