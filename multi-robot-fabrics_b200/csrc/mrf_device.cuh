@@ -590,6 +590,37 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     if (cfg.has_coll) {
         const V3<T> nh = mk(prm[(P_NH + 0) * NT + tid], prm[(P_NH + 1) * NT + tid], prm[(P_NH + 2) * NT + tid]);
         const T dn = prm[P_DN * NT + tid];
+        // Obstacle-major accumulation for sources that stream the spheres from global memory (executed action,
+        // Cartesian rollout): every sphere is loaded ONCE and evaluated against the six ego links as three packed
+        // pairs (link3|link4, link5|link6, link7|link8) -- the ego-major loop below would re-read the list five times
+        // (measured: the S = 64 action was bound by that traffic).  FP32 only (pairs in registers).
+        constexpr bool kObstMajor = Src::kObstacleMajor && sizeof(T) == 4;
+        PointAcc2<T> om[3];
+        if (kObstMajor) {
+            V3<P2<T>> pp[3], vv[3], cp[3];
+            P2<T> rbp[3];
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+                const int ea = ps == 0 ? 0 : (ps == 1 ? 2 : 3), eb = ps == 0 ? 1 : (ps == 1 ? 2 : 4);
+                V3<T> pa = kin_load(kin, NT, tid, ea, 0), pb = kin_load(kin, NT, tid, eb, 0);
+                V3<T> va = kin_load(kin, NT, tid, ea, 3), vb = kin_load(kin, NT, tid, eb, 3);
+                V3<T> ca = kin_load(kin, NT, tid, ea, 6), cb = kin_load(kin, NT, tid, eb, 6);
+                pp[ps] = V3<P2<T>>{pmk(pa.x, pb.x), pmk(pa.y, pb.y), pmk(pa.z, pb.z)};
+                vv[ps] = V3<P2<T>>{pmk(va.x, vb.x), pmk(va.y, vb.y), pmk(va.z, vb.z)};
+                cp[ps] = V3<P2<T>>{pmk(ca.x, cb.x), pmk(ca.y, cb.y), pmk(ca.z, cb.z)};
+                rbp[ps] = pmk(prm[(P_RB + 2 * ps) * NT + tid], prm[(P_RB + 2 * ps + 1) * NT + tid]);
+                acc2_zero(om[ps]);
+            }
+            src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
+                const V3<P2<T>> xo2{psplat(xo.x), psplat(xo.y), psplat(xo.z)}, vo2{psplat(vo.x), psplat(vo.y), psplat(vo.z)},
+                    co2{psplat(co.x), psplat(co.y), psplat(co.z)};
+                const P2<T> ro2 = psplat(ro), wo2 = psplat(wo);
+#pragma unroll
+                for (int ps = 0; ps < 3; ++ps)
+                    sphere_leaf2(pp[ps], vv[ps], cp[ps], xo2, vo2, co2, src.vref, src.aref, padd(ro2, rbp[ps]), wo2, sigma,
+                                 om[ps]);
+            });
+        }
 #pragma unroll 1
         for (int e = 0; e < kEgo; ++e) {
             const int K = e < 3 ? e + 2 : 6;           // link3: 2, link4: 3, link5/6: 4, link7: 6, link8: 6 joints
@@ -607,11 +638,26 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             }
             PointAcc2<T> acc2;
             acc2_zero(acc2);
+            if (kObstMajor) {
+                // pick this point's accumulators from the pair slots: link3 = slot0.lo, link4 = slot0.hi,
+                // link5 + link6 = slot1.lo + slot1.hi (same point), link7 = slot2.lo, link8 = slot2.hi
+                auto pick = [&](const P2<T>& s0, const P2<T>& s1, const P2<T>& s2) {
+                    return e == 0 ? plo(s0) : e == 1 ? phi(s0) : e == 2 ? plo(s1) + phi(s1) : e == 3 ? plo(s2) : phi(s2);
+                };
+                acc.A.xx = pick(om[0].A.xx, om[1].A.xx, om[2].A.xx); acc.A.xy = pick(om[0].A.xy, om[1].A.xy, om[2].A.xy);
+                acc.A.xz = pick(om[0].A.xz, om[1].A.xz, om[2].A.xz); acc.A.yy = pick(om[0].A.yy, om[1].A.yy, om[2].A.yy);
+                acc.A.yz = pick(om[0].A.yz, om[1].A.yz, om[2].A.yz); acc.A.zz = pick(om[0].A.zz, om[1].A.zz, om[2].A.zz);
+                acc.b.x = pick(om[0].b.x, om[1].b.x, om[2].b.x); acc.b.y = pick(om[0].b.y, om[1].b.y, om[2].b.y);
+                acc.b.z = pick(om[0].b.z, om[1].b.z, om[2].b.z);
+                num += pick(om[0].num, om[1].num, om[2].num);
+            }
             const V3<P2<T>> p2{psplat(p.x), psplat(p.y), psplat(p.z)}, v2{psplat(v.x), psplat(v.y), psplat(v.z)},
                 c2{psplat(cc.x), psplat(cc.y), psplat(cc.z)};
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
-                if (sizeof(T) == 4) {
+                if (kObstMajor) {
+                    // sphere leaves already accumulated above
+                } else if (sizeof(T) == 4) {
                     // FP32: sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2)
                     src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
                         sphere_leaf2(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)),
@@ -753,6 +799,7 @@ constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane e
 // ------------------------------------------------------------------------------------------------
 // other robots of the same scenario, read from the CTA's shared kinematics table (generic: table driven, any radii)
 template <typename T> struct SmemSrc {
+    static constexpr bool kObstacleMajor = false; // shared-memory points: re-reading per ego point is cheap
     const DevCfg<T>& cfg;
     const T* kin;
     int NT, lane, r;
@@ -785,6 +832,7 @@ template <typename T> struct SmemSrc {
 // (parameters_manipulators.py:23,37-43): no table look-ups, the six distinct points of each other robot are unrolled
 // with their multiplicities (link3, link4, link5==6 [x2], link7, link8, link1==2 [x2]) as compile-time constants.
 template <typename T, int R> struct SmemSrcUniform {
+    static constexpr bool kObstacleMajor = false;
     const T* kin;
     int lane, r;
     T vref, aref, ro;
@@ -825,25 +873,36 @@ template <typename T, int R> struct SmemSrcUniform {
 
 // caller-supplied spheres in global memory, SoA [S][MRF_OBST][stride]; tk > 0 extrapolates x + tk * xdot
 template <typename T, bool CART> struct GlobalSrc {
+    static constexpr bool kObstacleMajor = true; // global-memory spheres: load each once (see fabric_action)
     const T* obst;
     long long stride, off;
     int S;
     T tk;
     T vref, aref;
     template <typename F> MRF_HD void each(F f) const {
-#pragma unroll 2
+        // software-pipelined: the ten scalars of sphere o+1 are in flight while sphere o is evaluated (the obstacle-major
+        // action loop has only ~2 warps per scheduler to hide global-memory latency with)
+        if (S <= 0) return;
+        T cur[MRF_OBST], nxt[MRF_OBST];
+        const T* b = obst + off;
+#pragma unroll
+        for (int c = 0; c < MRF_OBST; ++c) cur[c] = b[c * stride];
         for (int o = 0; o < S; ++o) {
-            const T* b = obst + (long long)o * MRF_OBST * stride + off;
-            V3<T> xo = mk(b[0], b[stride], b[2 * stride]);
-            V3<T> vo = mk(b[3 * stride], b[4 * stride], b[5 * stride]);
+            const T* bn = obst + (long long)(o + 1 < S ? o + 1 : o) * MRF_OBST * stride + off;
+#pragma unroll
+            for (int c = 0; c < MRF_OBST; ++c) nxt[c] = bn[c * stride];
+            V3<T> xo = mk(cur[0], cur[1], cur[2]);
+            V3<T> vo = mk(cur[3], cur[4], cur[5]);
             V3<T> ao;
             if (CART) {
                 xo = xo + vo * tk;
                 ao = mk(T(0), T(0), T(0));
             } else {
-                ao = mk(b[6 * stride], b[7 * stride], b[8 * stride]);
+                ao = mk(cur[6], cur[7], cur[8]);
             }
-            f(xo, vo, ao, b[9 * stride], T(1));
+            f(xo, vo, ao, cur[9], T(1));
+#pragma unroll
+            for (int c = 0; c < MRF_OBST; ++c) cur[c] = nxt[c];
         }
     }
     template <typename F> MRF_HD void each2(F f) const {
