@@ -704,8 +704,8 @@ struct MrfHandle_ {
     int device;
     DevCfg<float> c32;
     DevCfg<double> c64;
-    cudaStream_t stream, s_copy, s_chunk[4];
-    cudaEvent_t ev0, ev1, ev_up[8], ev_free, ev_chunk[4];
+    cudaStream_t stream, s_copy, s_chunk[8];
+    cudaEvent_t ev0, ev1, ev_up[8], ev_free, ev_chunk[8];
     void* stage[8];
     size_t stage_bytes[8];
     long long launches;
@@ -797,7 +797,7 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     MRF_CUDA(cudaEventCreate(&h->ev1));
     for (int i = 0; i < 8; ++i) MRF_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
     MRF_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         MRF_CUDA(cudaStreamCreateWithFlags(&h->s_chunk[i], cudaStreamNonBlocking));
         MRF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     }
@@ -814,7 +814,7 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     cudaEventDestroy(h->ev1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_up[i]);
     cudaEventDestroy(h->ev_free);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         cudaEventDestroy(h->ev_chunk[i]);
         cudaStreamDestroy(h->s_chunk[i]);
     }
@@ -1099,7 +1099,7 @@ static int upload_records(mrf_handle_t h, const T* rec, long long B, int R, int 
 // overlaps the transpose + rollout + result read-back of chunk c (compute stream).
 template <typename T>
 static int rollout_host_pipelined(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B) {
-    const int R = h->cfg.n_robots, C = 4;
+    const int R = h->cfg.n_robots, C = B >= 32768 ? 8 : 4;
     const long long Bc = (((B + C - 1) / C) + 31) / 32 * 32; // chunk size, multiple of the CTA tile
     const size_t rec_elems = (size_t)B * R * MRF_REC;
     int rc = stage_reserve(h, 0, sizeof(T) * rec_elems);   // AoS records
