@@ -399,3 +399,28 @@ def test_error_paths_fail_loudly(fabs):
     bad.estimate_goal, bad.estimate_robot = 1, 5
     with pytest.raises(_lib.MrfError, match="estimate_robot"):
         m.Handle(bad)
+
+
+def test_assumption_knobs_on_the_gpu(fabs):
+    """jdot_sign / exec_scale / eps / jdot_ref_sign are MrfConfig fields: the kernels follow the oracle for the
+    alternative conventions too (rollout and action, both rollout kernels)."""
+    R, N, B = 2, 8, 24
+    kn = dict(jdot_sign=1.0, exec_scale=0.5, eps=1e-5, jdot_ref_sign=1.0)
+    rec = m.scenarios.generate(B, R, seed=91)
+    ocfg = o2.default_config(R, **kn)
+    qN, qdN, avg, _ = o2.rollout_jointspace(ocfg, rec, N)
+    ok = np.isfinite(qdN).all(axis=(1, 2, 3)) & (np.abs(qdN).max(axis=(1, 2, 3)) < 3)
+    fab = Fabrics(R, device=0, **kn)
+    for coop in (0, 1 << 20):
+        fab.handle.set_coop_max_batch(coop)
+        out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+        assert np.abs(out["qdN"] - qdN)[ok].max() / np.abs(qdN[ok]).max() < F64_RTOL
+    rng = np.random.default_rng(3)
+    obst = random_obstacles(rng, B, R, 6, rec)
+    act = fab.action_host(rec, obst, dtype="f64")
+    ref = oracle_actions(rec, obst, **kn)
+    okb = np.isfinite(ref).all(axis=(1, 2))
+    assert np.abs(act - ref)[okb].max() / np.abs(ref[okb]).max() < F64_RTOL
+    fab.close()
+    dflt = oracle_actions(rec, obst)
+    assert np.abs(dflt - ref)[okb].max() > 1e-6

@@ -207,3 +207,24 @@ def test_fsm_restatement_matches_reference_golden():
             assert st == g[p + "state"][t] and np.array_equal(o.goal, g[p + "goal"][t]) and o.weight == g[p + "weight"][t]
             assert np.array_equal(o.gripper_action(g[p + "qg"][t]), g[p + "grip"][t])
     assert seen == {0, 1, 2, 3, 4, 5, 10, 12}
+
+
+def test_assumption_knobs_agree_between_o1_and_o2(built):
+    """The recalled fabrics internals are knobs in every implementation.  With the alternative
+    settings (Jdot sign +1, ExecutionLagrangian 0.5 qd.qd, eps 1e-5) the autodiff oracle and the closed form still agree,
+    so if a real fabrics install ever shows a different convention, flipping the knob restores parity."""
+    from oracle import o1_fabrics as o1
+    rec = o2.make_record([0.9, 0.2, 0.1, -1.6, 0.2, 1.8, 0.5], [0.3, -0.2, 0.4, 0.1, -0.3, 0.2, 0.1], [0.5, 0.1, 1.0])
+    obst = np.array([[0.6, 0.2, 1.2, 0.1, -0.2, 0.05, 0.3, 0.1, -0.2, 0.08], [0.2, -0.3, 1.3, 0.0, 0.1, 0.0, 0.0, 0.0, 0.0, 0.1]])
+    kn = dict(jdot_sign=1.0, exec_scale=0.5, eps=1e-5)
+    cfg = o2.default_config(2, **kn)
+    pl = o1.make_panda_planner(o2.mount_of(cfg, 0), n_dyn=2, config=o1.panda_config(jdot_sign=1.0, exec_energy_scale=0.5, eps=1e-5))
+    p = o2.record_to_params(rec)
+    for i in range(2):
+        p.update({f"x_obst_dynamic_{i}": obst[i, 0:3], f"xdot_obst_dynamic_{i}": obst[i, 3:6],
+                  f"xddot_obst_dynamic_{i}": obst[i, 6:9], f"radius_obst_dynamic_{i}": obst[i, 9]})
+    a1, _ = pl.action_raw(rec[0:7], rec[7:14], p)
+    a2 = o2.action(cfg, 0, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
+    assert np.abs(a1 - a2).max() < 1e-11
+    base = o2.action(o2.default_config(2), 0, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
+    assert np.abs(a2 - base).max() > 1e-6
