@@ -353,3 +353,55 @@ def test_fsm_kernel_matches_reference_golden(built):
         assert s == g["c0_state"][t] and np.array_equal(sm.get_goal_robot(), g["c0_goal"][t])
         assert sm.get_weight_goal0() == g["c0_weight"][t]
         assert np.array_equal(sm.get_gripper_action_panda(g["c0_qg"][t]), g["c0_grip"][t])
+
+
+def test_utils_kinematics_dropins(built):
+    """UtilsKinematics / utils_apply_fk drop-ins used the way example_pandas_Jointspace.py:324-343 and
+    example_pandas_cartesian.py:361-418 use the CasADi functions."""
+    from multi_robot_fabrics_b200 import utils as U
+    R = 2
+    rng = np.random.default_rng(5)
+    planners = [P.set_planner_panda(7, 0, 8 * (R - 1), LINKS, "panda", MOUNT, i)[0] for i in range(R)]
+    cfg = o2.default_config(R, jdot_ref_sign=-1.0)
+    links = [[f"panda_link{k + 1}" for k in range(8)]] * R
+    uk = U.UtilsKinematics()
+    fk = uk.define_forward_kinematics(planners, [LINKS] * R, links)
+    ee = uk.define_symbolic_endeffector(planners)
+    q = rng.uniform(-1, 1, (R, 7)) + np.array([0, 0, 0, -1.5, 0, 1.8, 0])
+    qd = rng.uniform(-1, 1, (R, 7))
+    for i in range(R):
+        x, v, c, J = o2.kinematics(cfg, i, q[i], qd[i])
+        for z in range(8):
+            np.testing.assert_allclose(fk["fk_fun"][i][z](q[i]).full().transpose()[0], x[z], atol=1e-12)
+            jac = fk["jac_fun"][i][z](q[i])
+            np.testing.assert_allclose(jac.full(), J[z], atol=1e-12)
+            np.testing.assert_allclose((jac @ qd[i]).full().transpose()[0], v[z], atol=1e-12)
+            # utils.py:28,37: Jdot_sign (-1) times d(J qd)/dq qd
+            np.testing.assert_allclose((fk["jac_dot_fun"][i][z](q[i], qd[i]) @ qd[i]).full().transpose()[0], -c[z],
+                                       atol=1e-11)
+    x_ee, v_ee = U.compute_endeffector(list(q), list(qd), ee, nr_robots=R)
+    for i in range(R):
+        xo, vo = o2.endeffector(cfg, i, q[i], qd[i], use_jqd=True)
+        np.testing.assert_allclose(x_ee[i], xo, atol=1e-12)
+        np.testing.assert_allclose(v_ee[i], vo, atol=1e-12)
+    # collision-sphere functions + compute_x_obsts_dyn_0 (n_obst_per_link = 2)
+    n = 2
+    off = o2.sphere_offsets_ref(n)
+    T = [[[np.block([[np.eye(3), off[l, s].reshape(3, 1)], [np.zeros((1, 3)), np.ones((1, 1))]]) for s in range(n)]
+          for l in range(8)] for _ in range(R)]
+    mounts = [planners[i].mount for i in range(R)]
+    sph = uk.define_symbolic_collision_link_poses({"URDF_file_panda": "unused"}, links, T, n_obst_per_link=n,
+                                                  mount_transform=mounts)
+    env = {}
+    for i in range(R):
+        xs, _, vs = o2.spheres(cfg, i, q[i], qd[i], off)
+        np.testing.assert_allclose(sph[i]["fk_fun"](np.append(q[i], 0)).full().T, xs, atol=1e-12)
+        np.testing.assert_allclose(sph[i]["vel_fun"](np.append(q[i], 0), np.append(qd[i], 0)).full().T, vs, atol=1e-12)
+        for k in range(8 * n):
+            env[(f"robot_{i}", k)] = xs[k]
+    xd, vd, per = U.compute_x_obsts_dyn_0(list(q), list(qd), x_collision_sphere_poses=env, nr_robots=R,
+                                          fk_dict_spheres=sph, nr_dyn_obsts=[8 * n] * R)
+    ref = o2.obstacle_lists(cfg, q, qd, off, vel_mode=1)
+    for i in range(R):
+        np.testing.assert_allclose(np.array(xd[i]), ref[i][:, 0:3], atol=1e-12)
+        np.testing.assert_allclose(np.array(vd[i]).reshape(-1, 3), ref[i][:, 3:6], atol=1e-12)
