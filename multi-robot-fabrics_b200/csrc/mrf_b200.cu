@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     // (a double-buffered point table with one barrier per step was measured 2 % slower: more shared memory per CTA
     //  and non-immediate offsets; the barrier stall is load imbalance between the robots' warps, not barrier count)
     T* kin = reinterpret_cast<T*>(smem_raw);
-    T* prm = kin + kKin * NT;
+    T* prm = kin + kKinRows<T> * NT;
     const long long b = (long long)blockIdx.x * kTile + lane;
     const bool live = b < B;
     const long long bb = live ? b : B - 1; // idle lanes shadow the last scenario so barriers stay uniform
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kActThreads)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, tid = threadIdx.x;
     T* kin = reinterpret_cast<T*>(smem_raw);
-    T* prm = kin + kKin * NT;
+    T* prm = kin + kKinRows<T> * NT;
     const long long total = (long long)n_rob * B;
     long long idx = (long long)blockIdx.x * NT + tid;
     const bool live = idx < total;
@@ -864,7 +864,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         h->launches += 1;
         return MRF_OK;
     }
-    const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * NT;
+    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * NT;
     const long long grid = (B + kTile - 1) / kTile;
     int rc = MRF_OK;
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
@@ -902,7 +902,7 @@ static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, 
         return fail(MRF_EINVAL, "mrf_action: bad sizes");
     if (CART && (N <= 0 || h->cfg.mode != 1)) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0 and mode 'vel'");
     MRF_CUDA(cudaSetDevice(h->device));
-    const size_t smem = sizeof(T) * (size_t)(kKin + P_N) * kActThreads;
+    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * kActThreads;
     int rc = set_smem(action_kernel<T, CART>, smem);
     if (rc) return rc;
     const long long total = (long long)n_rob * B;
@@ -919,7 +919,7 @@ static int kinematics_dev(mrf_handle_t h, const T* q, const T* qd, T* x, T* v, T
     if (!h || !q || !qd) return fail(MRF_EINVAL, "mrf_kinematics: null argument");
     if (B <= 0) return fail(MRF_EINVAL, "mrf_kinematics: B must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
-    const size_t smem = sizeof(T) * (size_t)kKin * kActThreads;
+    const size_t smem = sizeof(T) * (size_t)kKinRows<T> * kActThreads;
     int rc = set_smem(kinematics_kernel<T>, smem);
     if (rc) return rc;
     const long long total = (long long)h->cfg.n_robots * B;

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(32 * R, 1)
     rollout_coop_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                         T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN,
                         long long B) {
-    __shared__ T kin[kKin * R];
+    __shared__ T kin[kKinRows<T> * R];
     __shared__ T prm[P_N * R];
     __shared__ CoopState<T> sts[R];
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;

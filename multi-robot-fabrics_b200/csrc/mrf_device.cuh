@@ -34,7 +34,12 @@ template <int N> struct Int {
 constexpr int kDof = 7;
 constexpr int kEgo = 5;        // distinct moving link points: link3, link4, link5(==link6), link7, link8
 constexpr int kPts = kEgo + 1; // + the constant point link1 == link2 (slot 5), so readers need no special case
-constexpr int kKin = kPts * 9; // x, v, c per point
+// x, v, c per point; then, for FP64 only, the six joint axes of the thread's own robot.  They are needed only at the
+// pullbacks; keeping them out of the register file across the leaf loops removes the FP64 kernel's spills (36
+// registers; measured +2.7 %), while for FP32 (18 registers, no spills) the extra shared-memory reads cost 1.3 %.
+constexpr int kZ = kPts * 9;
+template <typename T> constexpr bool kAxesInSmem = sizeof(T) == 8;
+template <typename T> constexpr int kKinRows = kPts * 9 + (kAxesInSmem<T> ? 18 : 0);
 constexpr int kMaxEnt = 8 * (MRF_MAX_ROBOTS - 1); // sphere entries one robot sees (all links of all other robots)
 // parameter block (per thread, shared memory)
 enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P_NH = 19, P_DN = 22, P_RB = 23, P_N = 29 };
@@ -173,6 +178,14 @@ template <typename T> struct DevCfg {
 template <typename T> struct Chain {
     V3<T> z[6]; // world axes of joints 1..6 (joint 7 moves no collision point)
 };
+// axis j of the thread's robot / origin of joint j+1 (joints 1,2 at link1; 3 at link3; 4 at link4; 5,6 at link5)
+template <typename T> MRF_HD V3<T> axis_of(const Chain<T>& ch, const T* kin, int NT, int tid, int j) {
+    if (kAxesInSmem<T>) {
+        const T* k = kin + (kZ + 3 * j) * NT + tid;
+        return V3<T>{k[0], k[NT], k[2 * NT]};
+    }
+    return ch.z[j];
+}
 
 // ------------------------------------------------------------------------------------------------
 // chain_forward: Panda FK with velocity / acceleration propagation (qdd = 0).
@@ -252,6 +265,13 @@ MRF_HD void chain_forward(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     (void)fr_joint<T, 1>(f, q[6], qd[6]);
     fr_advance(f, f.n * T(0.107));                                   // fixed joint8 (0,0,0.107); hand == link8
     kin_store(kin, NT, tid, 4, f);                                   // link8
+    if (kAxesInSmem<T>) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            T* k = kin + (kZ + 3 * j) * NT + tid;
+            k[0] = ch.z[j].x; k[NT] = ch.z[j].y; k[2 * NT] = ch.z[j].z;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,9 +464,10 @@ MRF_HD void plane_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> nh, T dn, T rb, T wt, T
 
 // Jacobian columns of a point p that rides on joints 1..K: z_j x (p - o_j).  Joint origins: o_1 = o_2 = link1,
 // o_3 = link3, o_4 = link4, o_5 = o_6 = link5.
-template <typename T, int K> MRF_HD void jac_cols(const Chain<T>& ch, V3<T> p, const V3<T>* org, V3<T>* Jc) {
+template <typename T, int K, typename Org>
+MRF_HD void jac_cols(const Chain<T>& ch, const T* kin, int NT, int tid, V3<T> p, const Org& org, V3<T>* Jc) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) Jc[j] = cross(ch.z[j], p - org[j]);
+    for (int j = 0; j < K; ++j) Jc[j] = cross(axis_of(ch, kin, NT, tid, j), p - org(j));
 }
 
 template <typename T, int K> MRF_HD void pullback(const V3<T>* Jc, const PointAcc<T>& acc, Spec<T>& S) {
@@ -577,13 +598,21 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         num += qd[i] * (T(0.08) * du);
     }
 
-    V3<T> org[6];
-    org[0] = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
-    org[1] = org[0];
-    org[2] = kin_load(kin, NT, tid, 0, 0);
-    org[3] = kin_load(kin, NT, tid, 1, 0);
-    org[4] = kin_load(kin, NT, tid, 2, 0);
-    org[5] = org[4];
+    // joint origins: FP64 re-reads them from the point table where a Jacobian column is formed (not held across the
+    // leaves); FP32 keeps them in registers
+    V3<T> org_[6];
+    if (!kAxesInSmem<T>) {
+        org_[0] = mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]);
+        org_[1] = org_[0];
+        org_[2] = kin_load(kin, NT, tid, 0, 0);
+        org_[3] = kin_load(kin, NT, tid, 1, 0);
+        org_[4] = kin_load(kin, NT, tid, 2, 0);
+        org_[5] = org_[4];
+    }
+    auto org = [&](int j) -> V3<T> {
+        if (!kAxesInSmem<T>) return org_[j];
+        return j < 2 ? mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]) : kin_load(kin, NT, tid, j < 4 ? j - 2 : 2, 0);
+    };
 
     // ---- collision leaves per distinct ego point (runtime loop: one copy of the leaf code keeps the kernel
     //      inside the instruction cache; the column count K of each point is warp-uniform) ----
@@ -680,7 +709,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             V3<T> Jc[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j)
-                if (j < K) Jc[j] = cross(ch.z[j], p - org[j]);
+                if (j < K) Jc[j] = cross(axis_of(ch, kin, NT, tid, j), p - org(j));
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 if (j < K) {
@@ -732,9 +761,9 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         attractor_scalars(n1, prm[P_W1 * NT + tid], dpsi1, m1);
         V3<T> t1 = (x1 * (dpsi1 * Mth<T>::rcp(n1)) + rot(c8 - c7) * sigma) * m1;
         V3<T> J8[6], Jr[6];
-        jac_cols<T, 6>(ch, p8, org, J8);
+        jac_cols<T, 6>(ch, kin, NT, tid, p8, org, J8);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) Jr[j] = rot(cross(ch.z[j], d87));
+        for (int j = 0; j < 6; ++j) Jr[j] = rot(cross(axis_of(ch, kin, NT, tid, j), d87));
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             F.f[j] += dot(J8[j], t0) + dot(Jr[j], t1);

@@ -16,7 +16,7 @@ static int rollout(const MrfConfig* mc, const double* rec, int N, double* avg, d
     DevCfg<T> cfg;
     fill_devcfg(*mc, cfg);
     const int R = cfg.n_robots, NT = kTile * R;
-    std::vector<T> kin((size_t)kKin * NT), prm((size_t)P_N * NT), q((size_t)NT * 7), qd((size_t)NT * 7), acc(NT);
+    std::vector<T> kin((size_t)kKinRows<T> * NT), prm((size_t)P_N * NT), q((size_t)NT * 7), qd((size_t)NT * 7), acc(NT);
     std::vector<Chain<T>> ch(NT);
     for (long long t0 = 0; t0 < B; t0 += kTile) {
         for (int tid = 0; tid < NT; ++tid) {
@@ -92,7 +92,7 @@ static int action(const MrfConfig* mc, int robot, const double* rec, int S, cons
     DevCfg<T> cfg;
     fill_devcfg(*mc, cfg);
     const int NT = 1;
-    std::vector<T> kin(kKin), prm(P_N), ob((size_t)S * MRF_OBST + 1);
+    std::vector<T> kin(kKinRows<T>), prm(P_N), ob((size_t)S * MRF_OBST + 1);
     for (long long b = 0; b < B; ++b) {
         auto ld = [&](int f) { return (T)rec[b * MRF_REC + f]; };
         T q[7], qd[7];
