@@ -12,8 +12,11 @@ horizon step (FK/J/Jdot qdot, leaves, pullback, solve, integrator update, avg-ve
 
   value     whole-job robot-steps/s with the scenario records already resident in HBM (CUDA events per step on the
             launching stream; L2 flushed between timed steps; max over ranks).
-  e2e       the same metric through the host-pointer C-ABI call (mrf_rollout_host_f32): every step copies the records
-            from pinned host memory, transposes, runs the kernels and reads avg_vel / x_ee / goal_est back.
+  e2e       the same metric through the host-pointer C-ABI call (mrf_rollout_host_f32) on page-locked host buffers:
+            every step the rollout kernel reads the records in the caller's record order straight from host memory
+            over PCIe (tile by tile, overlapped with the horizons of earlier tiles) and writes avg_vel / x_ee /
+            goal_est straight back -- what the reference's get_velocity_rollouts hands its Python caller; the
+            host-side deadlock heuristic that consumes them is not in this number (0.9 % of the device step).
   roofline  the kernel is compute-bound on the FP32 CUDA-core pipe (arithmetic intensity > 200 FLOP/B, no tensor
             cores): achieved = robot-steps/s x F(S=16) = 13.4 kFLOP over the FMA peak measured in this
             run by the library's micro-benchmark (MEASURED_PEAKS.json holds HBM / bf16 peaks only); the HBM view is
@@ -429,7 +432,7 @@ def ours(a):
             "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype, "data": "synthetic", "config": config_dict(a),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timing": "host wall clock around the synchronous mrf_rollout_host call, max over ranks"},
+                    "timing": "host wall clock around the synchronous mrf_rollout_host call (kernel reads the page-locked records in place and writes the results back; rollout only, the deadlock heuristic consumes its host outputs), max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "single_rollout_us": {"device_events_median": statistics.median(lat), "wall_back_to_back": lat_wall,
                                   "shape": "1 scenario x 3 Pandas x H20"},

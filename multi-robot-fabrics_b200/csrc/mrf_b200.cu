@@ -39,10 +39,21 @@ namespace mrf {
 #ifndef MRF_ROLLOUT_MINBLOCKS
 #define MRF_ROLLOUT_MINBLOCKS 4
 #endif
-template <typename T, int R, bool UNIFORM>
-__global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : 1)
+#ifndef MRF_ROLLOUT_MINBLOCKS_F64
+#define MRF_ROLLOUT_MINBLOCKS_F64 1
+#endif
+// Host-record mode (AOS): `rec` holds the caller's own records rec[B][R][44] (the reference's argument order), normally
+// in PAGE-LOCKED HOST memory that the kernel reads over PCIe.  A tile's records are one contiguous block, fetched with
+// coalesced 16-byte loads into the (not yet used) point table; results go back in the matching layout (avg[B][R],
+// x_ee[B][R][3], goal[B][3]).  No staging copy, no transpose kernel: the CTA scheduler overlaps the host reads of later
+// tiles with the horizons of earlier ones.  Tiles are handed out by an atomic ticket and admitted to the bus in ticket
+// order, `window` tiles at a time (sync[0] = tickets, sync[1] = tiles loaded): without that every CTA of a wave would
+// share the bus, all would start -- and later finish -- together, and each wave would stall for its whole transfer.
+template <typename T, int R, bool UNIFORM, bool AOS>
+__global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : MRF_ROLLOUT_MINBLOCKS_F64)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
-                   T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B) {
+                   T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
+                   unsigned* __restrict__ sync, unsigned window) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
@@ -50,10 +61,36 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     //  and non-immediate offsets; the barrier stall is load imbalance between the robots' warps, not barrier count)
     T* kin = reinterpret_cast<T*>(smem_raw);
     T* prm = kin + kKinRows<T> * NT;
-    const long long b = (long long)blockIdx.x * kTile + lane;
+    unsigned tile = blockIdx.x;
+    if (AOS) {
+        unsigned* tk = reinterpret_cast<unsigned*>(prm);
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&sync[0], 1u);
+            while (*reinterpret_cast<volatile unsigned*>(&sync[1]) + window <= t) __nanosleep(100);
+            *tk = t;
+        }
+        __syncthreads();
+        tile = *tk;
+    }
+    const long long b = (long long)tile * kTile + lane;
     const bool live = b < B;
     const long long bb = live ? b : B - 1; // idle lanes shadow the last scenario so barriers stay uniform
-    auto ld = [&](int f) { return rec[((long long)f * R + r) * B + bb]; };
+    const T* ld_base = rec + (long long)r * B + bb;
+    long long ld_stride = (long long)R * B;
+    if (AOS) {
+        const long long first = (long long)tile * kTile;
+        const int nb = (int)(B - first < kTile ? B - first : kTile);
+        const int nvec = nb * R * MRF_REC * (int)sizeof(T) / 16; // MRF_REC * sizeof(T) is a multiple of 16
+        const int4* src = reinterpret_cast<const int4*>(rec + first * R * MRF_REC);
+        int4* dst = reinterpret_cast<int4*>(kin);
+        for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (tid == 0) atomicAdd(&sync[1], 1u);
+        ld_base = kin + ((live ? lane : nb - 1) * R + r) * MRF_REC;
+        ld_stride = 1;
+    }
+    auto ld = [&](int f) { return AOS ? ld_base[f] : rec[((long long)f * R + r) * B + bb]; };
+    (void)ld_stride;
 
     T q[kDof], qd[kDof];
 #pragma unroll
@@ -81,9 +118,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
             // constant-velocity goal estimate of one robot (:346-348)
             V3<T> p8 = kin_load(kin, NT, tid, 4, 0);
             if (x_ee != nullptr && live) {
-                x_ee[((long long)r * 3 + 0) * B + b] = p8.x;
-                x_ee[((long long)r * 3 + 1) * B + b] = p8.y;
-                x_ee[((long long)r * 3 + 2) * B + b] = p8.z;
+                T* o = AOS ? x_ee + (b * R + r) * 3 : x_ee + (long long)r * 3 * B + b;
+                const long long st = AOS ? 1 : B;
+                o[0] = p8.x;
+                o[st] = p8.y;
+                o[2 * st] = p8.z;
             }
             if (r == cfg.estimate_robot) {
                 V3<T> g = mk(prm[(P_G0 + 0) * NT + tid], prm[(P_G0 + 1) * NT + tid], prm[(P_G0 + 2) * NT + tid]);
@@ -97,9 +136,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
                     prm[(P_G0 + 2) * NT + tid] = g.z;
                 }
                 if (goal_est != nullptr && live) {
-                    goal_est[0 * B + b] = g.x;
-                    goal_est[1 * B + b] = g.y;
-                    goal_est[2 * B + b] = g.z;
+                    T* o = AOS ? goal_est + b * 3 : goal_est + b;
+                    const long long st = AOS ? 1 : B;
+                    o[0] = g.x;
+                    o[st] = g.y;
+                    o[2 * st] = g.z;
                 }
             }
             continue;
@@ -129,7 +170,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         }
     }
     // compute_velocity_average (:102-116): mean SQUARE joint velocity over the horizon
-    if (avg_vel != nullptr && live) avg_vel[(long long)r * B + b] = acc / (T(N) * T(kDof));
+    if (avg_vel != nullptr && live) avg_vel[AOS ? b * R + r : (long long)r * B + b] = acc / (T(N) * T(kDof));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -711,6 +752,9 @@ struct MrfHandle_ {
     long long launches;
     double last_ms;
     long long coop_max_batch; // batches up to this size use the cooperative low-latency rollout kernel
+    int zero_copy;            // page-locked host records are read by the kernel directly (MRF_ZERO_COPY=0 disables)
+    int zc_window;            // tiles admitted to the bus at a time in that mode
+    unsigned* d_sync;         // its ticket / loaded counters
 };
 
 extern "C" int mrf_version(void) { return 100; }
@@ -789,6 +833,12 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->device = device;
     h->coop_max_batch = 512;
     if (const char* e = getenv("MRF_COOP_MAX_BATCH")) h->coop_max_batch = atoll(e);
+    h->zero_copy = 1;
+    if (const char* e = getenv("MRF_ZERO_COPY")) h->zero_copy = atoi(e);
+    h->zc_window = 32;
+    if (const char* e = getenv("MRF_ZC_WINDOW")) h->zc_window = atoi(e) > 0 ? atoi(e) : 32;
+    h->d_sync = nullptr;
+    if (cudaMalloc(&h->d_sync, 2 * sizeof(unsigned)) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -810,6 +860,7 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->d_sync) cudaFree(h->d_sync);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_up[i]);
@@ -844,7 +895,7 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------- device-pointer entries --------------------------------------
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
-                       void* stream) {
+                       void* stream, bool aos = false) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -852,7 +903,8 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
                                       "(forward_planner_Jointspace.py:197-201,233)");
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
-    if (R >= 2 && B <= h->coop_max_batch) {
+    if (aos && (qN || qdN)) return fail(MRF_EINVAL, "mrf_rollout: record-order input has no trajectory output");
+    if (!aos && R >= 2 && B <= h->coop_max_batch) {
         // few scenarios: latency matters, not throughput -> one CTA per scenario, one warp per robot (mrf_coop.cuh)
         switch (R) {
             case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
@@ -867,20 +919,22 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * NT;
     const long long grid = (B + kTile - 1) / kTile;
     int rc = MRF_OK;
+#define MRF_LAUNCH_ROLLOUT_K(RR, UU, AA)                                                                             \
+    {                                                                                                                \
+        rc = set_smem(rollout_kernel<T, RR, UU, AA>, smem);                                                          \
+        if (rc) return rc;                                                                                           \
+        rollout_kernel<T, RR, UU, AA><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                           \
+            devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync, (unsigned)h->zc_window); \
+    }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
         if (devcfg<T>(h).uniform_obst) {                                                                             \
-            rc = set_smem(rollout_kernel<T, RR, true>, smem);                                                        \
-            if (rc) return rc;                                                                                       \
-            rollout_kernel<T, RR, true><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                         \
-                devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B);                               \
+            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, true, true) else MRF_LAUNCH_ROLLOUT_K(RR, true, false)                 \
         } else {                                                                                                     \
-            rc = set_smem(rollout_kernel<T, RR, false>, smem);                                                       \
-            if (rc) return rc;                                                                                       \
-            rollout_kernel<T, RR, false><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                        \
-                devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B);                               \
+            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, false, true) else MRF_LAUNCH_ROLLOUT_K(RR, false, false)               \
         }                                                                                                            \
         break;
+    if (aos) MRF_CUDA(cudaMemsetAsync(h->d_sync, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
     switch (R) {
         MRF_LAUNCH_ROLLOUT(1)
         MRF_LAUNCH_ROLLOUT(2)
@@ -888,6 +942,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         MRF_LAUNCH_ROLLOUT(4)
         default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
     }
+#undef MRF_LAUNCH_ROLLOUT_K
 #undef MRF_LAUNCH_ROLLOUT
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -1160,13 +1215,63 @@ static int rollout_host_pipelined(mrf_handle_t h, const T* rec, int N, T* avg_ve
     return finish_timed(h);
 }
 
+// Device view of a host pointer when it is page-locked (cudaHostAlloc / cudaHostRegister: torch pinned tensors), else
+// nullptr.  With unified addressing the kernel can read and write such memory directly over PCIe.
+static void* pinned_view(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return (a.type == cudaMemoryTypeHost && ((uintptr_t)a.devicePointer & 15) == 0) ? a.devicePointer : nullptr;
+}
+
+// Page-locked records: ONE kernel launch reads the caller's records straight from host memory (record order, coalesced
+// 16-byte loads per tile) and writes avg / x_ee / goal straight back -- the CTA scheduler overlaps the PCIe reads of
+// later tiles with the horizons of earlier ones, so there is no staging copy, no transpose and no chunk pipeline.
+// Results whose host buffer is not page-locked go through a device buffer and one copy.
+template <typename T>
+static int rollout_host_zerocopy(mrf_handle_t h, const T* rec_view, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B) {
+    const int R = h->cfg.n_robots;
+    struct Out { T* host; T* dev; size_t n; bool direct; } outs[3] = {{avg_vel, nullptr, (size_t)B * R, false},
+                                                                      {x_ee, nullptr, (size_t)B * 3 * R, false},
+                                                                      {goal_est, nullptr, (size_t)B * 3, false}};
+    size_t staged = 0;
+    for (auto& o : outs) {
+        if (!o.host) continue;
+        o.dev = (T*)pinned_view(o.host);
+        o.direct = o.dev != nullptr;
+        if (!o.direct) staged += o.n;
+    }
+    if (staged) {
+        int rc = stage_reserve(h, 5, sizeof(T) * staged);
+        if (rc) return rc;
+        T* p = (T*)h->stage[5];
+        for (auto& o : outs)
+            if (o.host && !o.direct) { o.dev = p; p += o.n; }
+    }
+    MRF_CUDA(cudaEventRecord(h->ev0, h->stream));
+    int rc = rollout_dev<T>(h, rec_view, N, outs[0].dev, outs[1].dev, outs[2].dev, nullptr, nullptr, B, h->stream, true);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev1, h->stream));
+    for (auto& o : outs)
+        if (o.host && !o.direct)
+            MRF_CUDA(cudaMemcpyAsync(o.host, o.dev, sizeof(T) * o.n, cudaMemcpyDeviceToHost, h->stream));
+    return finish_timed(h);
+}
+
 template <typename T>
 static int rollout_host(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout_host: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout_host: B and N must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots;
-    if (!qN && !qdN && B >= 8192) return rollout_host_pipelined<T>(h, rec, N, avg_vel, x_ee, goal_est, B);
+    if (!qN && !qdN && B >= 8192) {
+        if (h->zero_copy)
+            if (const T* view = (const T*)pinned_view(rec)) return rollout_host_zerocopy<T>(h, view, N, avg_vel, x_ee, goal_est, B);
+        return rollout_host_pipelined<T>(h, rec, N, avg_vel, x_ee, goal_est, B);
+    }
     int rc = upload_records<T>(h, rec, B, R, 0, 1, 2);
     if (rc) return rc;
     const T* d_rec = (const T*)h->stage[R == 1 ? 1 : 2];
