@@ -198,7 +198,11 @@ int mrf_fsm_dev_f32(mrf_handle_t h, const int32_t* nr_blocks, const float* x_ee,
 
 /* ------------------------------- host-pointer entries (AoS) -----------------------------------
  *   rec [B][R][MRF_REC]   obst [B][R][S][MRF_OBST]   action [B][R][MRF_DOF]
- *   avg_vel [B][R]  x_ee [B][R][3]  goal_est [B][3]  qN,qdN [B][R][N][MRF_DOF]  (nullable outputs skipped) */
+ *   avg_vel [B][R]  x_ee [B][R][3]  goal_est [B][3]  qN,qdN [B][R][N][MRF_DOF]  (nullable outputs skipped)
+ *   mrf_rollout_host_*: when `rec` is page-locked (cudaHostAlloc / cudaHostRegister, 16-byte aligned), B >= 8192 and no
+ *   trajectories are requested, the kernel reads the records in place over PCIe and writes page-locked results in
+ *   place (one launch); pageable buffers take a chunk-pipelined staged path with identical results.  Environment:
+ *   MRF_ZERO_COPY=0 forces the staged path, MRF_ZC_WINDOW=<tiles admitted to the bus at a time, default 32>. */
 int mrf_action_host_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S, const double* obst,
                         double* action, int64_t B);
 int mrf_action_host_f32(mrf_handle_t h, int robot_first, int n_rob, const float* rec, int S, const float* obst,
