@@ -178,8 +178,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
 // ------------------------------------------------------------------------------------------------
 constexpr int kActThreads = 128;
 
+#ifndef MRF_ACTION_MINBLOCKS
+#define MRF_ACTION_MINBLOCKS 1
+#endif
 template <typename T, bool CART>
-__global__ void __launch_bounds__(kActThreads)
+__global__ void __launch_bounds__(kActThreads, sizeof(T) == 4 ? MRF_ACTION_MINBLOCKS : 1)
     action_kernel(const __grid_constant__ DevCfg<T> cfg, int robot_first, int n_rob, const T* __restrict__ rec, int S,
                   const T* __restrict__ obst, int N, T* __restrict__ out, T* __restrict__ qN, T* __restrict__ qdN,
                   long long B) {
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kActThreads)
     }
     load_params<T>(ld, prm, NT, tid);
     Chain<T> ch;
-    GlobalSrc<T, CART> src{obst, stride, idx, S, T(0), T(1), T(1)};
+    GlobalSrc<T, CART> src{obst, stride, idx, S, T(0), T(1), T(1), prm + P_N * NT, NT, tid};
     if (!CART) {
         T act[kDof];
         chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
@@ -957,7 +960,7 @@ static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, 
         return fail(MRF_EINVAL, "mrf_action: bad sizes");
     if (CART && (N <= 0 || h->cfg.mode != 1)) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0 and mode 'vel'");
     MRF_CUDA(cudaSetDevice(h->device));
-    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * kActThreads;
+    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N + kObstRing * MRF_OBST) * kActThreads;
     int rc = set_smem(action_kernel<T, CART>, smem);
     if (rc) return rc;
     const long long total = (long long)n_rob * B;

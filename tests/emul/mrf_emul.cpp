@@ -100,7 +100,7 @@ static int action(const MrfConfig* mc, int robot, const double* rec, int S, cons
         load_params<T>(ld, prm.data(), NT, 0);
         for (int o = 0; o < S * MRF_OBST; ++o) ob[o] = (T)obst[b * S * MRF_OBST + o]; // [o][c] with stride 1
         Chain<T> ch;
-        GlobalSrc<T, CART> src{ob.data(), 1, 0, S, T(0), T(1), T(1)};
+        GlobalSrc<T, CART> src{ob.data(), 1, 0, S, T(0), T(1), T(1), nullptr, 1, 0};
         T act[7];
         if (!CART) {
             chain_forward(cfg, robot, q, qd, ch, kin.data(), NT, 0);
