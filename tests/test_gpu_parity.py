@@ -448,3 +448,35 @@ def test_page_locked_host_records_are_read_in_place(built, dtype):
     for k in ("avg_vel", "x_ee", "goal_est"):
         assert np.array_equal(got[k].view(np.uint8), ref[k].view(np.uint8)), k
     fab.close()
+
+
+def test_degenerate_inputs_propagate_like_the_oracle(fabs):
+    """The reference has no guards (SURVEY 8b 'error conventions'): a joint on its limit is 1/0 in the limit leaf, a
+    joint beyond it or a penetrating sphere flips a leaf coordinate negative, a NaN input poisons the action.  The
+    CUDA path must return NaN actions exactly where the oracle does and agree everywhere else.  (Coincidences that
+    depend on the last bit of the forward kinematics -- goal exactly at the hand, sphere centre exactly on a link --
+    are not testable across two implementations of the chain.)"""
+    B, R, S = 8, 2, 3
+    rng = np.random.default_rng(77)
+    rec = m.scenarios.generate(B, R, seed=31, weight_goal_1=20.0)
+    obst = random_obstacles(rng, B, R, S, rec)
+    cfg = o2.default_config(R)
+    for r in range(R):
+        rec[1, r, 3] = float(cfg.limits[3][0])                # scenario 1: joint 4 on its lower limit -> 1/0
+        rec[2, r, 5] = float(cfg.limits[5][1]) + 0.05         # scenario 2: joint 6 beyond its upper limit (x < 0)
+        x, _, _, _ = o2.kinematics(cfg, r, rec[3, r, 0:7], rec[3, r, 7:14])
+        obst[3, r, 0, 0:3] = x[4] + np.array([0.03, -0.02, 0.04])   # scenario 3: sphere overlapping link5 (x < 0)
+        rec[4, r, 7:14] = 0.0                                 # scenario 4: robot at rest (sign switches at xdot = 0)
+        rec[5, r, 2] = np.nan                                 # scenario 5: NaN joint position
+        obst[6, r, 1, 3:6] = np.inf                           # scenario 6: infinite obstacle velocity
+    fab = get_fab(fabs, R)
+    ref = oracle_actions(rec, obst)
+    for dtype, tol in (("f64", 1e-9), ("f32", 2e-3)):
+        act = fab.action_host(rec, obst, dtype=dtype).astype(np.float64)
+        assert np.array_equal(np.isnan(act), np.isnan(ref)), dtype
+        okm = np.isfinite(ref)
+        assert np.isfinite(act[okm]).all()
+        if dtype == "f32":          # the overlapping-sphere rows are stiff (|action| ~ 1e3): FP32 is compared on the rest
+            okm &= (np.abs(ref) < 10).all(axis=2, keepdims=True)
+        assert np.abs(act - ref)[okm].max() / np.abs(ref[okm]).max() < tol, dtype
+    assert np.isnan(ref[1]).all() and np.isnan(ref[5]).all() and np.isfinite(ref[[0, 3, 4]]).all()
