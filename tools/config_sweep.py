@@ -24,3 +24,18 @@ for name, R, N in (("C3: 2 Pandas RF-CV H20", 2, 20), ("C4/C5: 3 Pandas RF-CV H5
         print(json.dumps(dict(config=name, dtype=nm, scenarios=B, ms=round(ms, 3), robot_steps_per_s=rs,
                               tflops_alg=rs * (5700 + 480 * S) / 1e12)))
     fab.close()
+# decoupled (Cartesian-example) rollouts: one robot against the other robots' constant-velocity spheres, n = 4 per link
+for name, R, N in (("FabricsRollouts, 2 Pandas, S = 32, H20", 2, 20), ("FabricsRollouts, 3 Pandas, S = 64, H50", 3, 50)):
+    rec = np.tile(m.scenarios.generate(4096, R, seed=3, weight_goal_1=20.0), (B // 4096, 1, 1))
+    fab = Fabrics(R)
+    for dt, nm in ((torch.float32, "f32"), (torch.float64, "f64")):
+        d = torch.from_numpy(to_soa(rec)).to("cuda:0", dtype=dt)
+        obst = fab.obstacles_dev(d[0:7].contiguous(), d[7:14].contiguous(), n_per_link=4, vel_mode=1)
+        o0, r0 = obst[:, :, 0, :].contiguous(), d[:, 0, :].contiguous()
+        a = torch.empty((B,), dtype=dt, device="cuda:0")
+        ms = timeit(lambda: fab.rollout_cart_dev(0, r0, o0, N, avg_vel=a), n=5, warm=2)
+        S = o0.shape[0]
+        rs = B * N / (ms * 1e-3)
+        print(json.dumps(dict(config=name, dtype=nm, scenarios=B, ms=round(ms, 3), robot_steps_per_s=rs,
+                              tflops_alg=rs * (5700 + 480 * S) / 1e12)))
+    fab.close()
