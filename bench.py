@@ -240,6 +240,20 @@ class ClockSampler:
                 "source": "nvml in-process poll" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
+def bind_to_gpu_socket(index: int) -> None:
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {i for i in range(n) if (words[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def ours(a):
     import torch
     import torch.distributed as dist
@@ -253,6 +267,12 @@ def ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if rank == 0:
         g.build()
+    # N > 1: keep each rank on the CPUs (and so, by first touch, the memory) of its GPU's socket -- the e2e kernel reads
+    # the page-locked records over PCIe, and a buffer on the far socket costs every rank bandwidth.  Restored before
+    # the CPU baseline so that leg still uses all host cores.
+    cpus_all = os.sched_getaffinity(0)
+    if world > 1:
+        bind_to_gpu_socket(local)
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -425,7 +445,8 @@ def ours(a):
     lat_wall = (time.perf_counter() - t0) / 200 * 1e6
 
     cpu = None
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:                  # the CPU leg is reported at N = 1 only
+        os.sched_setaffinity(0, cpus_all)
         cpu, _, _ = cpu_sample(H, a.cpu_seconds)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
