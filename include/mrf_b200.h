@@ -226,6 +226,50 @@ int mrf_deadlock_host_f64(mrf_handle_t h, const double* x_ee, double* goals, dou
                           const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
                           int32_t* st_int, double* st_goal, int32_t* flag, int64_t B);
 
+/* One closed-loop control step of B independent scenarios, entirely on the device -- the loop body of
+ * examples/example_pandas_Jointspace.py:280-458 with a kinematic environment (q += dt * clip(action), the urdfenvs 'vel'
+ * mode, :454) and a reach task (state-machine code 0; success = every hand within `epsilon` of its goal, :35):
+ *   clip qdot (:288) -> [rollout_fabrics: coupled rollouts with weight_goal_1 = w1_rollout (:352-376) -> RF-CV goal
+ *   (:346-348) -> resolve_deadlocks: deadlock_checking (:379-385)] -> other robots' collision spheres, n_per_link per
+ *   link, link-origin velocities (:400-412) -> executed action with weight_goal_1 = w1_action (:417-445) -> clip (:453),
+ *   integrate, metrics (first step at which the task is reached, minimum sphere clearance :461-470, deadlock steps).
+ * Seven kernel launches on `stream`; capture it in a CUDA graph and replay.  All pointers are device pointers of the
+ * entry's precision (T) unless typed; b fastest. */
+typedef struct MrfEpisode {
+    int32_t struct_size;        /* sizeof(MrfEpisode) */
+    int32_t n_horizon;          /* rollout horizon (rollout_fabrics) */
+    int32_t rollout_fabrics;    /* 0 = MRDF: no rollouts, no deadlock logic */
+    int32_t resolve_deadlocks;
+    int32_t n_per_link;         /* collision spheres per link seen by the executed action */
+    int32_t reserved0;
+    double epsilon;             /* reach tolerance (0.05) */
+    double w1_rollout, w1_action;   /* weight_goal_1: 10 in the rollouts (:43,364), 20 in the executed action (:427) */
+    double clearance_radius_sum;    /* subtracted from sphere-centre distances (0.16) */
+    double vel_limit[MRF_DOF];      /* :221 */
+    const double* offsets;      /* HOST pointer [8][n_per_link][3], link-frame sphere offsets */
+    void* rec;                  /* T [MRF_REC][R][B]: rows q, qdot are the live state; goal / weight rows are rewritten */
+    const void* goal0;          /* T [R][3][B] task goals */
+    const void* w0;             /* T [R][B] task weight_goal_0 */
+    void* avg_vel;              /* T [R][B]      (rollout_fabrics) */
+    void* x_ee;                 /* T [R][3][B]   hand positions at the measured state */
+    void* goal_est;             /* T [3][B]      (rollout_fabrics) */
+    void* obst;                 /* T [8 n (R-1)][MRF_OBST][R][B] */
+    void* spheres_x;            /* T [8 n][3][R][B] */
+    void* action;               /* T [MRF_DOF][R][B] */
+    void* kin_scratch;          /* T [3][8][3][R][B] (MRDF mode only) */
+    const int32_t* sm_state;    /* [R][B] state-machine codes (resolve_deadlocks) */
+    int32_t* time_step;         /* [B] in/out, incremented */
+    int32_t* time_deadlock_out; /* [B] in/out */
+    int32_t* st_int;            /* [4][B] in/out, see mrf_deadlock_dev */
+    void* st_goal;              /* T [3][B] in/out */
+    int32_t* flag;              /* [B] out: deadlock raised this step */
+    int32_t* done_at;           /* [B] in/out: first step index at which the task was reached (-1 = not yet) */
+    int32_t* deadlock_steps;    /* [B] in/out: += flag */
+    void* min_clearance;        /* T [B] in/out: running minimum */
+} MrfEpisode;
+int mrf_episode_step_dev_f64(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);
+int mrf_episode_step_dev_f32(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);
+
 /* mrf_rollout_* picks between two kernels computing the same recurrence: the cooperative low-latency kernel (one CTA
  * per scenario, one warp per robot) for B <= max_batch, the throughput kernel (one thread per scenario and robot)
  * above.  Default 512; 0 disables the cooperative kernel. */

@@ -38,6 +38,21 @@ class MrfConfig(C.Structure):
     ]
 
 
+class MrfEpisode(C.Structure):
+    """include/mrf_b200.h: state of mrf_episode_step_dev_* (device pointers as integers)."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_horizon", C.c_int32), ("rollout_fabrics", C.c_int32),
+        ("resolve_deadlocks", C.c_int32), ("n_per_link", C.c_int32), ("reserved0", C.c_int32),
+        ("epsilon", C.c_double), ("w1_rollout", C.c_double), ("w1_action", C.c_double),
+        ("clearance_radius_sum", C.c_double), ("vel_limit", C.c_double * DOF),
+        ("offsets", C.c_void_p), ("rec", C.c_void_p), ("goal0", C.c_void_p), ("w0", C.c_void_p), ("avg_vel", C.c_void_p),
+        ("x_ee", C.c_void_p), ("goal_est", C.c_void_p), ("obst", C.c_void_p), ("spheres_x", C.c_void_p),
+        ("action", C.c_void_p), ("kin_scratch", C.c_void_p), ("sm_state", C.c_void_p), ("time_step", C.c_void_p),
+        ("time_deadlock_out", C.c_void_p), ("st_int", C.c_void_p), ("st_goal", C.c_void_p), ("flag", C.c_void_p),
+        ("done_at", C.c_void_p), ("deadlock_steps", C.c_void_p), ("min_clearance", C.c_void_p),
+    ]
+
+
 _lib = None
 _F = {"f32": (C.c_float, np.float32), "f64": (C.c_double, np.float64)}
 
@@ -50,6 +65,7 @@ EXPORTS = [
     "mrf_point_action_host_f64", "mrf_action_host_f64", "mrf_action_host_f32",
     "mrf_rollout_host_f64", "mrf_rollout_host_f32", "mrf_rollout_cart_host_f64", "mrf_rollout_cart_host_f32",
     "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak", "mrf_set_coop_max_batch",
+    "mrf_episode_step_dev_f64", "mrf_episode_step_dev_f32",
 ]
 
 
@@ -90,6 +106,8 @@ def lib():
     L.mrf_kinematics_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, i64]
     L.mrf_deadlock_host_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]
     L.mrf_set_coop_max_batch.argtypes = [vp, i64]
+    L.mrf_episode_step_dev_f64.argtypes = [vp, C.POINTER(MrfEpisode), i64, vp]
+    L.mrf_episode_step_dev_f32.argtypes = [vp, C.POINTER(MrfEpisode), i64, vp]
     L.mrf_fma_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -1662,6 +1662,171 @@ extern "C" int mrf_fsm_dev_f32(mrf_handle_t h, const int32_t* nr_blocks, const f
     return fsm_dev<float>(h, nr_blocks, x_ee, q_grip, goal_block, start_goal, goal, above, weight, st, grip_action, B, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// closed-loop control step (examples/example_pandas_Jointspace.py:280-458) for B independent scenarios: the
+// bookkeeping between the rollout / deadlock / obstacle / action kernels as three small kernels, so one control step is
+// seven launches on one stream (CUDA-graph friendly) instead of ~45 framework launches
+// ------------------------------------------------------------------------------------------------
+struct EpLimits {
+    double v[MRF_DOF];
+};
+// :288 velocity clip of the measured state; goals / weights of this step start from the task's own (:352-368)
+template <typename T>
+__global__ void episode_pre_kernel(T* __restrict__ rec, const T* __restrict__ goal0, const T* __restrict__ w0, EpLimits lim,
+                                   T w1, int R, long long B) {
+    const long long RB = (long long)R * B, idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= RB) return;
+    const int r = (int)(idx / B);
+    const long long b = idx - (long long)r * B;
+#pragma unroll
+    for (int i = 0; i < MRF_DOF; ++i) {
+        T* p = rec + (MRF_QD + i) * RB + idx;
+        const T l = (T)lim.v[i], v = *p;
+        *p = v < -l ? -l : (v > l ? l : v); // NaN stays NaN, like np.clip
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rec[(MRF_G0 + c) * RB + idx] = goal0[((long long)r * 3 + c) * B + b];
+    rec[MRF_W0 * RB + idx] = w0[idx];
+    rec[MRF_W1 * RB + idx] = w1;
+}
+// between the rollouts and the executed action: RF-CV goal (when the deadlock kernel has not already applied it, :346-348)
+// and weight_goal_1 of the executed planner (:427)
+template <typename T>
+__global__ void episode_mid_kernel(T* __restrict__ rec, const T* __restrict__ goal_est, int est_robot, T w1, int R, long long B) {
+    const long long RB = (long long)R * B, idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= RB) return;
+    const int r = (int)(idx / B);
+    const long long b = idx - (long long)r * B;
+    rec[MRF_W1 * RB + idx] = w1;
+    if (goal_est != nullptr && r == est_robot) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rec[(MRF_G0 + c) * RB + idx] = goal_est[(long long)c * B + b];
+    }
+}
+// :453-470 clip the action, kinematic environment step (urdfenvs 'vel' mode stand-in), reach / clearance / deadlock metrics
+template <typename T>
+__global__ void episode_post_kernel(T* __restrict__ rec, const T* __restrict__ act, const T* __restrict__ x_ee, int xee_link_major,
+                                    const T* __restrict__ goal0, const T* __restrict__ sx, int S, const int32_t* __restrict__ flag,
+                                    EpLimits lim, T dt, T eps, T rsum, int32_t* __restrict__ tstep, int32_t* __restrict__ done_at,
+                                    int32_t* __restrict__ deadlock_steps, T* __restrict__ min_clear, int R, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long long RB = (long long)R * B;
+    bool reached = true;
+    for (int r = 0; r < R; ++r) {
+        const long long idx = (long long)r * B + b;
+#pragma unroll
+        for (int i = 0; i < MRF_DOF; ++i) {
+            const T l = (T)lim.v[i];
+            T a = act[(long long)i * RB + idx];
+            a = a < -l ? -l : (a > l ? l : a);
+            if (!(a - a == T(0))) a = T(0); // non-finite action: hold still
+            rec[(MRF_QD + i) * RB + idx] = a;
+            rec[(MRF_Q + i) * RB + idx] += a * dt;
+        }
+        T d2 = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const T x = xee_link_major ? x_ee[((long long)c * R + r) * B + b] : x_ee[((long long)r * 3 + c) * B + b];
+            const T d = x - goal0[((long long)r * 3 + c) * B + b];
+            d2 += d * d;
+        }
+        reached = reached && (Mth<T>::sqrt(d2) < eps);
+    }
+    const int32_t t = tstep[b];
+    if (reached && done_at[b] < 0) done_at[b] = t;
+    if (sx != nullptr) {
+        T mc = min_clear[b];
+        for (int ra = 0; ra < R; ++ra)
+            for (int rb = ra + 1; rb < R; ++rb)
+                for (int i = 0; i < S; ++i) {
+                    const T ax = sx[((long long)(i * 3 + 0) * R + ra) * B + b], ay = sx[((long long)(i * 3 + 1) * R + ra) * B + b],
+                            az = sx[((long long)(i * 3 + 2) * R + ra) * B + b];
+                    for (int j = 0; j < S; ++j) {
+                        const T dx = ax - sx[((long long)(j * 3 + 0) * R + rb) * B + b], dy = ay - sx[((long long)(j * 3 + 1) * R + rb) * B + b],
+                                dz = az - sx[((long long)(j * 3 + 2) * R + rb) * B + b];
+                        const T c = Mth<T>::sqrt(dx * dx + dy * dy + dz * dz) - rsum;
+                        mc = c < mc ? c : mc;
+                    }
+                }
+        min_clear[b] = mc;
+    }
+    if (flag != nullptr && deadlock_steps != nullptr) deadlock_steps[b] += flag[b];
+    tstep[b] = t + 1;
+}
+
+template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream) {
+    if (!h || !ep) return fail(MRF_EINVAL, "mrf_episode_step: null argument");
+    if (ep->struct_size != (int32_t)sizeof(MrfEpisode)) return fail(MRF_EINVAL, "mrf_episode_step: MrfEpisode size mismatch");
+    if (!ep->rec || !ep->goal0 || !ep->w0 || !ep->x_ee || (h->cfg.n_robots > 1 && !ep->obst) || !ep->spheres_x || !ep->action ||
+        !ep->offsets || !ep->time_step || !ep->done_at || !ep->min_clearance)
+        return fail(MRF_EINVAL, "mrf_episode_step: null state pointer");
+    if (ep->n_per_link < 1 || ep->n_per_link > MRF_MAX_SPHERES_PER_LINK) return fail(MRF_EINVAL, "mrf_episode_step: bad n_per_link");
+    if (ep->rollout_fabrics && (!ep->avg_vel || !ep->goal_est || ep->n_horizon <= 0))
+        return fail(MRF_EINVAL, "mrf_episode_step: rollouts need avg_vel, goal_est and n_horizon > 0");
+    if (ep->rollout_fabrics && ep->resolve_deadlocks &&
+        (!ep->sm_state || !ep->time_deadlock_out || !ep->st_int || !ep->st_goal || !ep->flag || !ep->deadlock_steps))
+        return fail(MRF_EINVAL, "mrf_episode_step: deadlock resolution needs its state arrays");
+    if (!ep->rollout_fabrics && !ep->kin_scratch) return fail(MRF_EINVAL, "mrf_episode_step: MRDF mode needs kin_scratch");
+    if (B <= 0) return fail(MRF_EINVAL, "mrf_episode_step: B must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const int R = h->cfg.n_robots;
+    const long long RB = (long long)R * B;
+    cudaStream_t st = (cudaStream_t)stream;
+    T* rec = (T*)ep->rec;
+    EpLimits lim;
+    for (int i = 0; i < MRF_DOF; ++i) lim.v[i] = ep->vel_limit[i];
+    const unsigned g_rb = (unsigned)((RB + 255) / 256), g_b = (unsigned)((B + 127) / 128);
+    const bool est = h->cfg.estimate_goal != 0 && R > 1;
+    episode_pre_kernel<T><<<g_rb, 256, 0, st>>>(rec, (const T*)ep->goal0, (const T*)ep->w0, lim,
+                                                (T)(ep->rollout_fabrics ? ep->w1_rollout : ep->w1_action), R, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    int rc;
+    const T* xee = (const T*)ep->x_ee;
+    int link_major = 0;
+    if (ep->rollout_fabrics) {
+        rc = rollout_dev<T>(h, rec, ep->n_horizon, (T*)ep->avg_vel, (T*)ep->x_ee, (T*)ep->goal_est, nullptr, nullptr, B, stream);
+        if (rc) return rc;
+        if (ep->resolve_deadlocks) {
+            rc = deadlock_rec_dev<T>(h, (const T*)ep->x_ee, rec, est ? (const T*)ep->goal_est : nullptr, (const T*)ep->avg_vel,
+                                     nullptr, ep->sm_state, ep->time_step, ep->time_deadlock_out, ep->st_int, (T*)ep->st_goal,
+                                     ep->flag, B, stream);
+            if (rc) return rc;
+        }
+        episode_mid_kernel<T><<<g_rb, 256, 0, st>>>(rec, (est && !ep->resolve_deadlocks) ? (const T*)ep->goal_est : nullptr,
+                                                    h->cfg.estimate_robot, (T)ep->w1_action, R, (long long)B);
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+    } else {
+        T* kx = (T*)ep->kin_scratch;
+        const size_t n = (size_t)MRF_NLINKS * 3 * RB;
+        rc = kinematics_dev<T>(h, rec + MRF_Q * RB, rec + MRF_QD * RB, kx, kx + n, kx + 2 * n, B, stream);
+        if (rc) return rc;
+        xee = kx + (size_t)(MRF_NLINKS - 1) * 3 * RB; // hand rows [3][R][B]
+        link_major = 1;
+    }
+    const int S1 = MRF_NLINKS * ep->n_per_link;
+    rc = obstacles_dev<T>(h, ep->n_per_link, ep->offsets, 0, rec + MRF_Q * RB, rec + MRF_QD * RB, (T*)ep->obst, (T*)ep->spheres_x,
+                          nullptr, B, stream);
+    if (rc) return rc;
+    rc = action_dev<T, false>(h, 0, R, rec, S1 * (R - 1), (const T*)ep->obst, 0, (T*)ep->action, nullptr, nullptr, B, stream);
+    if (rc) return rc;
+    episode_post_kernel<T><<<g_b, 128, 0, st>>>(
+        rec, (const T*)ep->action, xee, link_major, (const T*)ep->goal0, R > 1 ? (const T*)ep->spheres_x : nullptr, S1,
+        (ep->rollout_fabrics && ep->resolve_deadlocks) ? ep->flag : nullptr, lim, (T)h->cfg.dt, (T)ep->epsilon,
+        (T)ep->clearance_radius_sum, ep->time_step, ep->done_at, ep->deadlock_steps, (T*)ep->min_clearance, R, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return MRF_OK;
+}
+extern "C" int mrf_episode_step_dev_f64(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream) {
+    return episode_step_dev<double>(h, ep, B, stream);
+}
+extern "C" int mrf_episode_step_dev_f32(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream) {
+    return episode_step_dev<float>(h, ep, B, stream);
+}
+
 template <typename T> static int fma_peak(mrf_handle_t h, double* tflops) {
     MRF_CUDA(cudaSetDevice(h->device));
     cudaDeviceProp prop;

@@ -10,8 +10,8 @@ Per control step, for every scenario (file:line in examples/example_pandas_Joint
   6. kinematic environment step q += dt * clip(action)  (urdfenvs 'vel' mode stand-in for pybullet, :454)
 The pick-and-place state machine is replaced by a reach task: every robot keeps its goal, state-machine code 0
 ("move to goal"), and an episode succeeds when every hand is within `epsilon` (0.05, the goal struct's epsilon, :35)
-of its own goal.  Torch is used for tensor hand-off and slice bookkeeping only; one control step is captured in a CUDA
-graph and replayed.
+of its own goal.  One control step is ONE C-ABI call (mrf_episode_step_dev_*: seven kernel launches), captured in a CUDA
+graph and replayed; torch only owns the tensors.
 """
 from __future__ import annotations
 
@@ -41,8 +41,6 @@ class BatchedEpisodes:
         self.rec = t(to_soa(rec))                                    # (44,R,B): q, qdot rows are the live state
         self.goal0 = self.rec[G0:G0 + 3].permute(1, 0, 2).contiguous().clone()     # (R,3,B) task goals
         self.w0 = self.rec[W0].clone()                                              # (R,B)
-        self.goals = self.goal0.clone()                                             # working copies (deadlock mutates)
-        self.weights = self.w0.clone()
         z = lambda *s, dt=None: torch.zeros(s, dtype=dt or self.tdt, device=self.dev)
         self.avg, self.xee, self.gest = z(R, B), z(R, 3, B), z(3, B)
         self.obst = z(8 * self.n_per_link * (R - 1), 10, R, B)
@@ -53,59 +51,49 @@ class BatchedEpisodes:
         self.st_int = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=self.dev).repeat_interleave(B).contiguous()
         self.st_goal = z(3, B)
         self.flag = z(B, dt=torch.int32)
-        self.vlim = torch.tensor(VEL_LIMITS, dtype=self.tdt, device=self.dev).view(7, 1, 1)
         self.dt = float(self.fab.cfg.dt)
         # metrics
         self.done_at = torch.full((B,), -1, dtype=torch.int32, device=self.dev)
         self.deadlock_steps = z(B, dt=torch.int32)
         self.min_clear = torch.full((B,), 100.0, dtype=self.tdt, device=self.dev)   # :231 min_clearance = 100
         self.sx = z(8 * self.n_per_link, 3, R, B)
-        self.kx, self.kv, self.ka = z(8, 3, R, B), z(8, 3, R, B), z(8, 3, R, B)
         self.graph = None
         self.steps_done = 0
+        self._ep = None
 
-    # one control step; every operation is a kernel launch on the current stream (graph-capturable)
+    def _episode_struct(self):
+        """The MrfEpisode argument of mrf_episode_step_dev_* (built once: the tensors never move)."""
+        import ctypes as C
+        from ._lib import MrfEpisode
+        from .spheres import sphere_offsets
+        R, B = self.R, self.B
+        self._offsets = np.ascontiguousarray(sphere_offsets(self.n_per_link), dtype=np.float64)
+        if not self.rollout_fabrics:
+            self.kin_scratch = self.torch.zeros((3, 8, 3, R, B), dtype=self.tdt, device=self.dev)
+        ep = MrfEpisode()
+        ep.struct_size = C.sizeof(MrfEpisode)
+        ep.n_horizon, ep.rollout_fabrics, ep.resolve_deadlocks = self.N, int(self.rollout_fabrics), int(self.resolve_deadlocks)
+        ep.n_per_link, ep.epsilon, ep.w1_rollout, ep.w1_action, ep.clearance_radius_sum = self.n_per_link, self.epsilon, 10.0, 20.0, 0.16
+        for i, v in enumerate(VEL_LIMITS):
+            ep.vel_limit[i] = v
+        ep.offsets = self._offsets.ctypes.data
+        p = lambda t: None if t is None else t.data_ptr()
+        ep.rec, ep.goal0, ep.w0, ep.avg_vel, ep.x_ee, ep.goal_est = p(self.rec), p(self.goal0), p(self.w0), p(self.avg), p(self.xee), p(self.gest)
+        ep.obst, ep.spheres_x, ep.action = p(self.obst), p(self.sx), p(self.act)
+        ep.kin_scratch = p(getattr(self, "kin_scratch", None))
+        ep.sm_state, ep.time_step, ep.time_deadlock_out, ep.st_int, ep.st_goal = p(self.sm), p(self.tstep), p(self.tdo), p(self.st_int), p(self.st_goal)
+        ep.flag, ep.done_at, ep.deadlock_steps, ep.min_clearance = p(self.flag), p(self.done_at), p(self.deadlock_steps), p(self.min_clear)
+        return ep
+
+    # one control step = one C-ABI call = seven kernel launches on the current stream (graph-capturable)
     def _step(self):
-        torch, R = self.torch, self.R
-        rec = self.rec
-        rec[QD:QD + 7].copy_(torch.minimum(torch.maximum(rec[QD:QD + 7], -self.vlim), self.vlim))     # :288
-        self.goals.copy_(self.goal0)
-        self.weights.copy_(self.w0)
-        if self.rollout_fabrics:
-            rec[G0:G0 + 3].copy_(self.goals.permute(1, 0, 2))
-            rec[W0].copy_(self.weights)
-            rec[W1].fill_(10.0)                                                                       # :43,364
-            self.fab.rollout_dev(rec, self.N, avg_vel=self.avg, x_ee=self.xee, goal_est=self.gest)
-            if self.fab.cfg.estimate_goal and R > 1:
-                self.goals[1].copy_(self.gest)                                                        # :346-348
-            if self.resolve_deadlocks:
-                self.fab.deadlock_dev(self.xee, self.goals, self.weights, self.sm, self.tstep, self.tdo, self.st_int,
-                                      self.st_goal, avg_vel=self.avg, flag=self.flag)
-                self.deadlock_steps.add_(self.flag)
-        else:
-            self.fab.kinematics_dev(rec[Q:Q + 7], rec[QD:QD + 7], x=self.kx, v=self.kv, a=self.ka)    # MRDF: hands' FK only
-            self.xee.copy_(self.kx[7].permute(1, 0, 2))
-        # executed action with the (possibly overridden) goals / weights, weight_goal_1 = 20          :417-445
-        rec[G0:G0 + 3].copy_(self.goals.permute(1, 0, 2))
-        rec[W0].copy_(self.weights)
-        rec[W1].fill_(20.0)
-        q, qd = rec[Q:Q + 7], rec[QD:QD + 7]
-        self.fab.obstacles_dev(q, qd, n_per_link=self.n_per_link, vel_mode=0, obst=self.obst, spheres_x=self.sx)
-        self.fab.action_dev(rec, self.obst, action=self.act)
-        a = torch.minimum(torch.maximum(self.act, -self.vlim), self.vlim)                             # :453
-        a = torch.where(torch.isfinite(a), a, torch.zeros_like(a))
-        qd.copy_(a)
-        q.add_(a * self.dt)                                                                           # kinematic env step
-        # metrics: reach test on the task goals, minimum sphere clearance between robots (:461-470)
-        dist = (self.xee - self.goal0).square().sum(dim=1).sqrt()                                     # (R,B)
-        reached = (dist < self.epsilon).all(dim=0)
-        first = reached & (self.done_at < 0)
-        self.done_at.copy_(torch.where(first, self.tstep, self.done_at))
-        for a_ in range(R):
-            for b_ in range(a_ + 1, R):
-                d = (self.sx[:, None, :, a_] - self.sx[None, :, :, b_]).square().sum(dim=2).sqrt()   # (S,S,B)
-                self.min_clear.copy_(torch.minimum(self.min_clear, d.flatten(0, 1).min(dim=0).values - 0.16))
-        self.tstep.add_(1)
+        import ctypes as C
+        from ._lib import check, lib
+        if self._ep is None:
+            self._ep = self._episode_struct()
+        fn = lib().mrf_episode_step_dev_f32 if self.tdt == self.torch.float32 else lib().mrf_episode_step_dev_f64
+        check(fn(self.fab.handle.ptr, C.byref(self._ep), self.B, self.torch.cuda.current_stream(self.dev).cuda_stream),
+              "mrf_episode_step_dev")
 
     def run(self, n_steps: int):
         torch = self.torch
@@ -136,4 +124,5 @@ class BatchedEpisodes:
                 "deadlock_steps": self.deadlock_steps.cpu().numpy(),
                 "min_clearance": self.min_clear.double().cpu().numpy(),
                 "q": self.rec[Q:Q + 7].permute(2, 1, 0).double().cpu().numpy(),
-                "x_ee": self.xee.permute(2, 0, 1).double().cpu().numpy()}
+                "x_ee": (self.xee.permute(2, 0, 1) if self.rollout_fabrics else
+                         self.kin_scratch[0, 7].permute(2, 1, 0)).double().cpu().numpy()}
