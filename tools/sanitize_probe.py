@@ -17,6 +17,13 @@ obst = fab.obstacles_dev(d[0:7].contiguous(), d[7:14].contiguous(), n_per_link=2
 act = fab.action_dev(d, obst)
 fab.rollout_cart_dev(0, d[:, 0].contiguous(), obst[:, :, 0].contiguous(), N)
 fab.kinematics_dev(d[0:7].contiguous(), d[7:14].contiguous())
+fab.handle.set_coop_max_batch(512)
 big = fab.rollout_host(np.tile(rec, (120, 1, 1))[:8200].astype(np.float32), 2, dtype="f32")   # pipelined host path
+pinned = torch.from_numpy(np.tile(rec, (120, 1, 1))[:8229].astype(np.float32)).pin_memory().numpy()
+inplace = fab.rollout_host(pinned, 2, dtype="f32")        # page-locked records read in place (ticketed tiles, ragged tail)
+assert np.array_equal(inplace["avg_vel"][:8200].view(np.uint8), big["avg_vel"].view(np.uint8))
+from multi_robot_fabrics_b200.episodes import BatchedEpisodes
+for kw in (dict(rollout_fabrics=True, resolve_deadlocks=True, estimate_goal=True), dict(rollout_fabrics=False)):
+    BatchedEpisodes(rec, n_horizon=3, dtype="f32", n_obst_per_link=2, use_graph=False, **kw).run(3).results()
 torch.cuda.synchronize()
 print("sanitize probe done", float(act.abs().max()))
