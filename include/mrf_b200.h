@@ -248,8 +248,8 @@ typedef struct MrfEpisode {
     double vel_limit[MRF_DOF];      /* :221 */
     const double* offsets;      /* HOST pointer [8][n_per_link][3], link-frame sphere offsets */
     void* rec;                  /* T [MRF_REC][R][B]: rows q, qdot are the live state; goal / weight rows are rewritten */
-    const void* goal0;          /* T [R][3][B] task goals */
-    const void* w0;             /* T [R][B] task weight_goal_0 */
+    void* goal0;                /* T [R][3][B] task goals (read-only for the reach task) */
+    void* w0;                   /* T [R][B] task weight_goal_0 */
     void* avg_vel;              /* T [R][B]      (rollout_fabrics) */
     void* x_ee;                 /* T [R][3][B]   hand positions at the measured state */
     void* goal_est;             /* T [3][B]      (rollout_fabrics) */
@@ -266,6 +266,20 @@ typedef struct MrfEpisode {
     int32_t* done_at;           /* [B] in/out: first step index at which the task was reached (-1 = not yet) */
     int32_t* deadlock_steps;    /* [B] in/out: += flag */
     void* min_clearance;        /* T [B] in/out: running minimum */
+    /* pick-and-place task (:289-312,417-448) instead of the reach task: each robot's state machine
+     * (others_planner/state_machine.py:133-214, see mrf_fsm_dev) sets this step's goal0 / w0 (then in/out), gates the
+     * deadlock logic, selects the obstacle-free grasp planner in state 2 and holds the arm in states 3 / 5; the finger
+     * joints integrate its gripper velocity inside [0, 0.04]; blocks are kinematic (they do not fall, so the
+     * state machine's "dropped" branch never fires); done_at = first step at which every robot reports state 10. */
+    int32_t pick_and_place;
+    int32_t n_blocks;           /* blocks per robot */
+    const void* blocks;         /* T [n_blocks][R][3][B] rest positions of each robot's blocks (picked in order) */
+    const void* start_goal;     /* T [R][3][B] */
+    void* q_grip;               /* T [R][2][B] in/out finger joints (open = 0.04) */
+    void* goal_block;           /* T [R][3][B] scratch: current block + 0.1 in z */
+    void* fsm_above;            /* T [R][3][B] in/out */
+    int32_t* fsm_st;            /* [6][R][B] in/out, rows as in mrf_fsm_dev_*; state initial 1 */
+    void* grip_action;          /* T [R][2][B] out */
 } MrfEpisode;
 int mrf_episode_step_dev_f64(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);
 int mrf_episode_step_dev_f32(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);

@@ -185,7 +185,7 @@ template <typename T, bool CART>
 __global__ void __launch_bounds__(kActThreads, sizeof(T) == 4 ? MRF_ACTION_MINBLOCKS : 1)
     action_kernel(const __grid_constant__ DevCfg<T> cfg, int robot_first, int n_rob, const T* __restrict__ rec, int S,
                   const T* __restrict__ obst, int N, T* __restrict__ out, T* __restrict__ qN, T* __restrict__ qdN,
-                  long long B) {
+                  long long B, const int32_t* __restrict__ sm_state) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, tid = threadIdx.x;
     T* kin = reinterpret_cast<T*>(smem_raw);
@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(kActThreads, sizeof(T) == 4 ? MRF_ACTION_MINBL
     load_params<T>(ld, prm, NT, tid);
     Chain<T> ch;
     GlobalSrc<T, CART> src{obst, stride, idx, S, T(0), T(1), T(1), prm + P_N * NT, NT, tid};
+    // state-machine code 2 ("from pregrasp to the block"): the reference switches to the planner built without collision
+    // links (example_pandas_Jointspace.py:440)
+    src.grasp = sm_state != nullptr && sm_state[idx] == 2;
     if (!CART) {
         T act[kDof];
         chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
@@ -954,7 +957,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
 
 template <typename T, bool CART>
 static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, int S, const T* obst, int N, T* out,
-                      T* qN, T* qdN, int64_t B, void* stream) {
+                      T* qN, T* qdN, int64_t B, void* stream, const int32_t* sm_state = nullptr) {
     if (!h || !rec || (S > 0 && !obst)) return fail(MRF_EINVAL, "mrf_action: null argument");
     if (B <= 0 || S < 0 || n_rob < 1 || robot_first < 0 || robot_first + n_rob > h->cfg.n_robots)
         return fail(MRF_EINVAL, "mrf_action: bad sizes");
@@ -966,7 +969,7 @@ static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, 
     const long long total = (long long)n_rob * B;
     const long long grid = (total + kActThreads - 1) / kActThreads;
     action_kernel<T, CART><<<(unsigned)grid, kActThreads, smem, (cudaStream_t)stream>>>(
-        devcfg<T>(h), robot_first, n_rob, rec, S, obst, N, out, qN, qdN, (long long)B);
+        devcfg<T>(h), robot_first, n_rob, rec, S, obst, N, out, qN, qdN, (long long)B, sm_state);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;
@@ -1703,26 +1706,58 @@ __global__ void episode_mid_kernel(T* __restrict__ rec, const T* __restrict__ go
         for (int c = 0; c < 3; ++c) rec[(MRF_G0 + c) * RB + idx] = goal_est[(long long)c * B + b];
     }
 }
+// pick-and-place task (:289-303): hand position at the measured state for the state machine, and the block each robot
+// goes for next -- block number nr_blocks_success of its own stack, grasp height 0.1 above the block (:302-303)
+template <typename T>
+__global__ void episode_blocks_kernel(const T* __restrict__ hand, T* __restrict__ x_ee, const T* __restrict__ blocks, int n_blocks,
+                                      const int32_t* __restrict__ st, T* __restrict__ goal_block, int R, long long B) {
+    const long long RB = (long long)R * B, idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= RB) return;
+    const int r = (int)(idx / B);
+    const long long b = idx - (long long)r * B;
+    const int n_ok = st[1 * RB + idx];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        x_ee[((long long)r * 3 + c) * B + b] = hand[((long long)c * R + r) * B + b];
+        if (n_ok < n_blocks)
+            goal_block[((long long)r * 3 + c) * B + b] = blocks[(((long long)n_ok * R + r) * 3 + c) * B + b] + (c == 2 ? T(0.1) : T(0));
+    }
+}
 // :453-470 clip the action, kinematic environment step (urdfenvs 'vel' mode stand-in), reach / clearance / deadlock metrics
 template <typename T>
 __global__ void episode_post_kernel(T* __restrict__ rec, const T* __restrict__ act, const T* __restrict__ x_ee, int xee_link_major,
                                     const T* __restrict__ goal0, const T* __restrict__ sx, int S, const int32_t* __restrict__ flag,
                                     EpLimits lim, T dt, T eps, T rsum, int32_t* __restrict__ tstep, int32_t* __restrict__ done_at,
-                                    int32_t* __restrict__ deadlock_steps, T* __restrict__ min_clear, int R, long long B) {
+                                    int32_t* __restrict__ deadlock_steps, T* __restrict__ min_clear, int R, long long B,
+                                    const int32_t* __restrict__ sm, T* __restrict__ q_grip, const T* __restrict__ grip_action) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const long long RB = (long long)R * B;
     bool reached = true;
     for (int r = 0; r < R; ++r) {
         const long long idx = (long long)r * B + b;
+        const int state = sm != nullptr ? sm[idx] : 0;
 #pragma unroll
         for (int i = 0; i < MRF_DOF; ++i) {
             const T l = (T)lim.v[i];
             T a = act[(long long)i * RB + idx];
             a = a < -l ? -l : (a > l ? l : a);
             if (!(a - a == T(0))) a = T(0); // non-finite action: hold still
+            if (state == 3 || state == 5) a = T(0); // gripping / releasing: the arm holds still (:418-419)
             rec[(MRF_QD + i) * RB + idx] = a;
             rec[(MRF_Q + i) * RB + idx] += a * dt;
+        }
+        if (q_grip != nullptr) { // finger joints follow the state machine's gripper velocity inside their limits [0, 0.04]
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                T* g = q_grip + ((long long)r * 2 + k) * B + b;
+                T v = *g + dt * grip_action[((long long)r * 2 + k) * B + b];
+                *g = v < T(0) ? T(0) : (v > T(0.04) ? T(0.04) : v);
+            }
+        }
+        if (sm != nullptr) { // pick-and-place: done when every state machine reports "all blocks picked" (:305-312)
+            reached = reached && state == 10;
+            continue;
         }
         T d2 = T(0);
 #pragma unroll
@@ -1765,7 +1800,8 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
     if (ep->rollout_fabrics && (!ep->avg_vel || !ep->goal_est || ep->n_horizon <= 0))
         return fail(MRF_EINVAL, "mrf_episode_step: rollouts need avg_vel, goal_est and n_horizon > 0");
     if (ep->rollout_fabrics && ep->resolve_deadlocks &&
-        (!ep->sm_state || !ep->time_deadlock_out || !ep->st_int || !ep->st_goal || !ep->flag || !ep->deadlock_steps))
+        ((!ep->sm_state && !ep->pick_and_place) || !ep->time_deadlock_out || !ep->st_int || !ep->st_goal || !ep->flag ||
+         !ep->deadlock_steps))
         return fail(MRF_EINVAL, "mrf_episode_step: deadlock resolution needs its state arrays");
     if (!ep->rollout_fabrics && !ep->kin_scratch) return fail(MRF_EINVAL, "mrf_episode_step: MRDF mode needs kin_scratch");
     if (B <= 0) return fail(MRF_EINVAL, "mrf_episode_step: B must be positive");
@@ -1778,6 +1814,28 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
     for (int i = 0; i < MRF_DOF; ++i) lim.v[i] = ep->vel_limit[i];
     const unsigned g_rb = (unsigned)((RB + 255) / 256), g_b = (unsigned)((B + 127) / 128);
     const bool est = h->cfg.estimate_goal != 0 && R > 1;
+    const bool pnp = ep->pick_and_place != 0;
+    const int32_t* sm_state = ep->sm_state;
+    if (pnp) {
+        if (!ep->kin_scratch || !ep->blocks || !ep->q_grip || !ep->start_goal || !ep->goal_block || !ep->fsm_above || !ep->fsm_st ||
+            !ep->grip_action || ep->n_blocks < 1)
+            return fail(MRF_EINVAL, "mrf_episode_step: pick-and-place needs its state arrays");
+        T* kx = (T*)ep->kin_scratch;
+        const size_t n = (size_t)MRF_NLINKS * 3 * RB;
+        int rc0 = kinematics_dev<T>(h, rec + MRF_Q * RB, rec + MRF_QD * RB, kx, kx + n, kx + 2 * n, B, stream);
+        if (rc0) return rc0;
+        episode_blocks_kernel<T><<<g_rb, 256, 0, st>>>(kx + (size_t)(MRF_NLINKS - 1) * 3 * RB, (T*)ep->x_ee, (const T*)ep->blocks,
+                                                       ep->n_blocks, ep->fsm_st, (T*)ep->goal_block, R, (long long)B);
+        MRF_CUDA(cudaGetLastError());
+        h->launches += 1;
+        int nb[MRF_MAX_ROBOTS];
+        for (int r = 0; r < MRF_MAX_ROBOTS; ++r) nb[r] = ep->n_blocks;
+        // the state machine rewrites this step's task goal and weight_goal_0 (goal0 / w0) and the gripper command
+        rc0 = fsm_dev<T>(h, nb, (const T*)ep->x_ee, (const T*)ep->q_grip, (const T*)ep->goal_block, (const T*)ep->start_goal,
+                         (T*)ep->goal0, (T*)ep->fsm_above, (T*)ep->w0, ep->fsm_st, (T*)ep->grip_action, B, stream);
+        if (rc0) return rc0;
+        sm_state = ep->fsm_st; // row 0 of [6][R][B] = state codes
+    }
     episode_pre_kernel<T><<<g_rb, 256, 0, st>>>(rec, (const T*)ep->goal0, (const T*)ep->w0, lim,
                                                 (T)(ep->rollout_fabrics ? ep->w1_rollout : ep->w1_action), R, (long long)B);
     MRF_CUDA(cudaGetLastError());
@@ -1790,7 +1848,7 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
         if (rc) return rc;
         if (ep->resolve_deadlocks) {
             rc = deadlock_rec_dev<T>(h, (const T*)ep->x_ee, rec, est ? (const T*)ep->goal_est : nullptr, (const T*)ep->avg_vel,
-                                     nullptr, ep->sm_state, ep->time_step, ep->time_deadlock_out, ep->st_int, (T*)ep->st_goal,
+                                     nullptr, sm_state, ep->time_step, ep->time_deadlock_out, ep->st_int, (T*)ep->st_goal,
                                      ep->flag, B, stream);
             if (rc) return rc;
         }
@@ -1798,7 +1856,7 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
                                                     h->cfg.estimate_robot, (T)ep->w1_action, R, (long long)B);
         MRF_CUDA(cudaGetLastError());
         h->launches += 1;
-    } else {
+    } else if (!pnp) {
         T* kx = (T*)ep->kin_scratch;
         const size_t n = (size_t)MRF_NLINKS * 3 * RB;
         rc = kinematics_dev<T>(h, rec + MRF_Q * RB, rec + MRF_QD * RB, kx, kx + n, kx + 2 * n, B, stream);
@@ -1810,12 +1868,14 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
     rc = obstacles_dev<T>(h, ep->n_per_link, ep->offsets, 0, rec + MRF_Q * RB, rec + MRF_QD * RB, (T*)ep->obst, (T*)ep->spheres_x,
                           nullptr, B, stream);
     if (rc) return rc;
-    rc = action_dev<T, false>(h, 0, R, rec, S1 * (R - 1), (const T*)ep->obst, 0, (T*)ep->action, nullptr, nullptr, B, stream);
+    rc = action_dev<T, false>(h, 0, R, rec, S1 * (R - 1), (const T*)ep->obst, 0, (T*)ep->action, nullptr, nullptr, B, stream,
+                              pnp ? sm_state : nullptr);
     if (rc) return rc;
     episode_post_kernel<T><<<g_b, 128, 0, st>>>(
         rec, (const T*)ep->action, xee, link_major, (const T*)ep->goal0, R > 1 ? (const T*)ep->spheres_x : nullptr, S1,
         (ep->rollout_fabrics && ep->resolve_deadlocks) ? ep->flag : nullptr, lim, (T)h->cfg.dt, (T)ep->epsilon,
-        (T)ep->clearance_radius_sum, ep->time_step, ep->done_at, ep->deadlock_steps, (T*)ep->min_clearance, R, (long long)B);
+        (T)ep->clearance_radius_sum, ep->time_step, ep->done_at, ep->deadlock_steps, (T*)ep->min_clearance, R, (long long)B,
+        pnp ? sm_state : nullptr, pnp ? (T*)ep->q_grip : nullptr, pnp ? (const T*)ep->grip_action : nullptr);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;

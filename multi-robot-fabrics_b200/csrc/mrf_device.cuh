@@ -616,7 +616,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
 
     // ---- collision leaves per distinct ego point (runtime loop: one copy of the leaf code keeps the kernel
     //      inside the instruction cache; the column count K of each point is warp-uniform) ----
-    if (cfg.has_coll) {
+    if (src.collide(cfg.has_coll != 0)) {
         const V3<T> nh = mk(prm[(P_NH + 0) * NT + tid], prm[(P_NH + 1) * NT + tid], prm[(P_NH + 2) * NT + tid]);
         const T dn = prm[P_DN * NT + tid];
         // Obstacle-major accumulation for sources that stream the spheres from global memory (executed action,
@@ -829,6 +829,7 @@ constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane e
 // other robots of the same scenario, read from the CTA's shared kinematics table (generic: table driven, any radii)
 template <typename T> struct SmemSrc {
     static constexpr bool kObstacleMajor = false; // shared-memory points: re-reading per ego point is cheap
+    MRF_HD bool collide(bool has) const { return has; }
     const DevCfg<T>& cfg;
     const T* kin;
     int NT, lane, r;
@@ -862,6 +863,7 @@ template <typename T> struct SmemSrc {
 // with their multiplicities (link3, link4, link5==6 [x2], link7, link8, link1==2 [x2]) as compile-time constants.
 template <typename T, int R> struct SmemSrcUniform {
     static constexpr bool kObstacleMajor = false;
+    MRF_HD bool collide(bool has) const { return has; }
     const T* kin;
     int lane, r;
     T vref, aref, ro;
@@ -929,6 +931,8 @@ template <typename T, bool CART> struct GlobalSrc {
     T vref, aref;
     T* ring;   // shared memory, kObstRing * MRF_OBST * NT scalars (element [slot][c][tid]); nullptr on the host
     int NT, tid;
+    bool grasp = false; // this thread evaluates the obstacle-free grasp planner (example_pandas_Jointspace.py:160-166,440)
+    MRF_HD bool collide(bool has) const { return has && !grasp; }
     template <typename F> MRF_HD void emit(const T* cur, F& f) const {
         V3<T> xo = mk(cur[0], cur[1], cur[2]);
         V3<T> vo = mk(cur[3], cur[4], cur[5]);

@@ -8,9 +8,12 @@ Per control step, for every scenario (file:line in examples/example_pandas_Joint
   4. other robots' collision spheres (n_obst_per_link, link-origin velocity):400-412   (obstacles kernel)
   5. executed action per robot (weight_goal_1 = 20), velocity clip          :417-453   (action kernel)
   6. kinematic environment step q += dt * clip(action)  (urdfenvs 'vel' mode stand-in for pybullet, :454)
-The pick-and-place state machine is replaced by a reach task: every robot keeps its goal, state-machine code 0
-("move to goal"), and an episode succeeds when every hand is within `epsilon` (0.05, the goal struct's epsilon, :35)
-of its own goal.  One control step is ONE C-ABI call (mrf_episode_step_dev_*: seven kernel launches), captured in a CUDA
+Two task protocols.  Reach task (default): every robot keeps its goal, state-machine code 0 ("move to goal"), and an
+episode succeeds when every hand is within `epsilon` (0.05, the goal struct's epsilon, :35) of its own goal.
+Pick-and-place (`blocks=`, `start_goal=`): the reference's state machine (others_planner/state_machine.py) runs on the
+device every step -- it sets goals / weight_goal_0, gates the deadlock logic, switches to the obstacle-free grasp
+planner in state 2, holds the arm while gripping / releasing and drives the finger joints; blocks are kinematic (picked
+in order, never dropped); an episode succeeds when every robot has picked all its blocks (state 10).  One control step is ONE C-ABI call (mrf_episode_step_dev_*: seven kernel launches), captured in a CUDA
 graph and replayed; torch only owns the tensors.
 """
 from __future__ import annotations
@@ -26,7 +29,7 @@ VEL_LIMITS = [2.175, 2.175, 2.175, 2.175, 2.61, 2.61, 2.61]          # example_p
 class BatchedEpisodes:
     def __init__(self, rec: np.ndarray, n_horizon: int = 10, rollout_fabrics: bool = True, resolve_deadlocks: bool = True,
                  estimate_goal: bool = False, static_or_dyn: int = 1, n_obst_per_link: int = 1, device: int = 0,
-                 dtype: str = "f32", epsilon: float = 0.05, use_graph: bool = True):
+                 dtype: str = "f32", epsilon: float = 0.05, use_graph: bool = True, blocks=None, start_goal=None):
         import torch
         self.torch = torch
         B, R, _ = rec.shape
@@ -57,6 +60,20 @@ class BatchedEpisodes:
         self.deadlock_steps = z(B, dt=torch.int32)
         self.min_clear = torch.full((B,), 100.0, dtype=self.tdt, device=self.dev)   # :231 min_clearance = 100
         self.sx = z(8 * self.n_per_link, 3, R, B)
+        # pick-and-place task: blocks (B, n_blocks, R, 3) rest positions, start_goal (B, R, 3)
+        self.pick_and_place = blocks is not None
+        if self.pick_and_place:
+            blocks = np.asarray(blocks, dtype=np.float64)
+            self.n_blocks = blocks.shape[1]
+            self.blocks = t(np.transpose(blocks, (1, 2, 3, 0)))                      # (n_blocks,R,3,B)
+            self.start_goal = t(np.transpose(np.asarray(start_goal, dtype=np.float64), (1, 2, 0)))   # (R,3,B)
+            self.q_grip = torch.full((R, 2, B), 0.04, dtype=self.tdt, device=self.dev)
+            self.goal_block, self.fsm_above, self.grip_action = z(R, 3, B), z(R, 3, B), z(R, 2, B)
+            self.fsm_st = z(6, R, B, dt=torch.int32)
+            self.fsm_st[0].fill_(1)                                                   # state_machine.py:8
+            self.goal0.copy_(self.start_goal)                                         # :33
+            self.w0.fill_(2.0)                                                        # :34
+            self.kin_scratch = z(3, 8, 3, R, B)
         self.graph = None
         self.steps_done = 0
         self._ep = None
@@ -68,7 +85,7 @@ class BatchedEpisodes:
         from .spheres import sphere_offsets
         R, B = self.R, self.B
         self._offsets = np.ascontiguousarray(sphere_offsets(self.n_per_link), dtype=np.float64)
-        if not self.rollout_fabrics:
+        if not self.rollout_fabrics and not self.pick_and_place:
             self.kin_scratch = self.torch.zeros((3, 8, 3, R, B), dtype=self.tdt, device=self.dev)
         ep = MrfEpisode()
         ep.struct_size = C.sizeof(MrfEpisode)
@@ -83,6 +100,10 @@ class BatchedEpisodes:
         ep.kin_scratch = p(getattr(self, "kin_scratch", None))
         ep.sm_state, ep.time_step, ep.time_deadlock_out, ep.st_int, ep.st_goal = p(self.sm), p(self.tstep), p(self.tdo), p(self.st_int), p(self.st_goal)
         ep.flag, ep.done_at, ep.deadlock_steps, ep.min_clearance = p(self.flag), p(self.done_at), p(self.deadlock_steps), p(self.min_clear)
+        if self.pick_and_place:
+            ep.pick_and_place, ep.n_blocks = 1, self.n_blocks
+            ep.blocks, ep.start_goal, ep.q_grip, ep.goal_block = p(self.blocks), p(self.start_goal), p(self.q_grip), p(self.goal_block)
+            ep.fsm_above, ep.fsm_st, ep.grip_action = p(self.fsm_above), p(self.fsm_st), p(self.grip_action)
         return ep
 
     # one control step = one C-ABI call = seven kernel launches on the current stream (graph-capturable)
@@ -120,9 +141,13 @@ class BatchedEpisodes:
     def results(self) -> dict:
         self.torch.cuda.synchronize(self.dev)
         done = self.done_at.cpu().numpy()
-        return {"steps": self.steps_done, "success": done >= 0, "steps_to_success": done,
+        extra = {}
+        if self.pick_and_place:
+            extra = {"state": self.fsm_st[0].T.cpu().numpy(), "blocks_picked": self.fsm_st[1].T.cpu().numpy(),
+                     "q_grip": self.q_grip.permute(2, 0, 1).double().cpu().numpy()}
+        return {**extra, "steps": self.steps_done, "success": done >= 0, "steps_to_success": done,
                 "deadlock_steps": self.deadlock_steps.cpu().numpy(),
                 "min_clearance": self.min_clear.double().cpu().numpy(),
                 "q": self.rec[Q:Q + 7].permute(2, 1, 0).double().cpu().numpy(),
-                "x_ee": (self.xee.permute(2, 0, 1) if self.rollout_fabrics else
+                "x_ee": (self.xee.permute(2, 0, 1) if (self.rollout_fabrics or self.pick_and_place) else
                          self.kin_scratch[0, 7].permute(2, 1, 0)).double().cpu().numpy()}

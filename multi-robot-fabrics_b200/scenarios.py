@@ -117,3 +117,19 @@ def obstacles_from_positions(x, v=None, a=None, radius=0.08) -> np.ndarray:
         o[..., 6:9] = a
     o[..., 9] = radius
     return o
+
+
+def pick_and_place_layout(rec: np.ndarray, n_blocks: int = 2, seed: int = 0, spread: float = 0.12, drop: float = 0.16):
+    """A synthetic pick-and-place task for episodes.BatchedEpisodes(blocks=, start_goal=): every robot's start goal is
+    its hand position in `rec` (B,R,44) and its blocks rest `drop` below that height, uniformly within +-`spread` in x, y
+    (the reference spreads cubes over the table around the start goals, create_simulation_manipulators.py:39-63).
+    -> blocks (B, n_blocks, R, 3), start_goal (B, R, 3)."""
+    B, R = rec.shape[:2]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    start = np.zeros((B, R, 3))
+    for r in range(R):
+        start[:, r] = link_positions(rec[:, r, Q:Q + 7], mount_matrix(r))[:, 7]
+    blocks = start[:, None, :, :] + np.stack([rng.uniform(-spread, spread, (B, n_blocks, R)),
+                                              rng.uniform(-spread, spread, (B, n_blocks, R)),
+                                              np.full((B, n_blocks, R), -drop)], axis=-1)
+    return blocks, start

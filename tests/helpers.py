@@ -96,3 +96,61 @@ def oracle_episode(rec, T, N, rollout=True, resolve=True, estimate=False, n_per_
         if done_at < 0 and all(np.linalg.norm(xee[i] - goal0[i]) < 0.05 for i in range(R)):
             done_at = t
     return q, n_flags, done_at
+
+
+def oracle_pick_and_place(rec, blocks, start_goal, T, N, rollout=True, resolve=True, estimate=False, n_per_link=1):
+    """CPU restatement of the pick-and-place control loop (examples/example_pandas_Jointspace.py:280-458) for ONE scenario
+    with the kinematic environment of multi_robot_fabrics_b200.episodes: oracle O2, the deadlock restatement and the
+    state-machine restatement (both pinned to the reference's classes).  blocks (n_blocks, R, 3), start_goal (R, 3).
+    -> q (R,7), states (R,), blocks picked (R,), deadlock steps, done_at, q_grip (R,2)"""
+    from oracle.deadlock_ref import DeadlockOracle
+    from oracle.fsm_ref import FsmOracle
+    R, nb = rec.shape[0], blocks.shape[0]
+    cfg = o2.default_config(R)
+    cfg_grasp = o2.default_config(R, has_collision_links=0)
+    off = o2.sphere_offsets_ref(n_per_link)
+    vlim = np.array([2.175] * 4 + [2.61] * 3)
+    q, qd = rec[:, 0:7].copy(), rec[:, 7:14].copy()
+    q_grip = np.full((R, 2), 0.04)
+    fsm = [FsmOracle(start_goal[i], nb) for i in range(R)]
+    goal_block = [np.zeros(3) for _ in range(R)]
+    dl, tdo, n_flags, done_at = DeadlockOracle(R), 1000, 0, -1
+    for t in range(T):
+        qd = np.clip(qd, -vlim, vlim)
+        xee = [o2.kinematics(cfg, i, q[i], qd[i])[0][7] for i in range(R)]
+        for i in range(R):
+            if fsm[i].n_ok < nb:
+                goal_block[i] = blocks[fsm[i].n_ok, i] + np.array([0.0, 0.0, 0.1])                  # :302-303
+        states = [fsm[i].step(xee[i], q_grip[i], goal_block[i]) for i in range(R)]
+        if done_at < 0 and all(s == 10 for s in states):
+            done_at = t
+        goals, weights = [fsm[i].goal.copy() for i in range(R)], [float(fsm[i].weight) for i in range(R)]
+        if rollout:
+            if estimate:
+                x, v = o2.endeffector(cfg, 1, q[1], qd[1])
+                goals[1] = x + 0.2 * v
+            r = rec.copy()
+            r[:, 0:7], r[:, 7:14], r[:, 14:17], r[:, 17], r[:, 21] = q, qd, np.array(goals), weights, 10.0
+            avg, _ = o2.rollout_jointspace_avg(cfg, r, N)
+            if resolve:
+                goals, weights, tdo, flag = dl.step(xee, goals, weights, t, tdo, float(sum(avg[0]) / R), list(states))
+                n_flags += int(flag)
+        lists = o2.obstacle_lists(cfg, q, qd, off, vel_mode=0)
+        act = np.zeros((R, 7))
+        for i in range(R):
+            if states[i] in (3, 5):
+                continue                                                                              # :418-419
+            r = rec[i].copy()
+            r[0:7], r[7:14], r[14:17], r[17], r[21] = q[i], qd[i], goals[i], weights[i], 20.0
+            o = lists[i]
+            try:
+                act[i] = o2.action(cfg_grasp if states[i] == 2 else cfg, i, r, o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+            except FloatingPointError:          # metric not positive definite: NaN action, the arm holds still
+                act[i] = np.nan
+        a = np.clip(act, -vlim, vlim)
+        a[~np.isfinite(a)] = 0.0
+        for i in range(R):
+            q_grip[i] = np.clip(q_grip[i] + 0.01 * fsm[i].gripper_action(q_grip[i]), 0.0, 0.04)
+        qd = a
+        q = q + 0.01 * a
+    return q, np.array([f.state for f in fsm]), np.array([f.n_ok for f in fsm]), n_flags, done_at, q_grip

@@ -8,9 +8,13 @@ R = int(os.environ.get("ED_R", 2)); B = int(os.environ.get("ED_B", 4096)); T = i
 base = m.scenarios.generate(min(B, 4096), R, seed=5)
 rec = np.tile(base, ((B + len(base) - 1) // len(base), 1, 1))[:B]
 rec[:, :, 7:14] = 0.0
+task = {}
+if int(os.environ.get("ED_PNP", 0)):     # pick-and-place protocol instead of the reach task
+    blocks, start = m.scenarios.pick_and_place_layout(rec, n_blocks=int(os.environ.get("ED_BLOCKS", 2)), seed=1)
+    task = dict(blocks=blocks, start_goal=start)
 for name, kw in (("MRDF", dict(rollout_fabrics=False)), ("RF", dict(rollout_fabrics=True, resolve_deadlocks=True)),
                  ("RF-CV", dict(rollout_fabrics=True, resolve_deadlocks=True, estimate_goal=True))):
-    ep = BatchedEpisodes(rec, n_horizon=N, dtype="f32", **kw)
+    ep = BatchedEpisodes(rec, n_horizon=N, dtype="f32", **kw, **task)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = ep.run(T).results()
     dt = time.perf_counter() - t0
@@ -19,4 +23,5 @@ for name, kw in (("MRDF", dict(rollout_fabrics=False)), ("RF", dict(rollout_fabr
                           episodes_per_s=round(B / dt, 1), control_steps_per_s=round(B * T / dt),
                           success_rate=float(ok.mean()), median_steps_to_success=float(np.median(res["steps_to_success"][ok])) if ok.any() else None,
                           scenarios_with_deadlock=float((res["deadlock_steps"] > 0).mean()),
-                          min_clearance_p01=float(np.nanquantile(res["min_clearance"], 0.01)))))
+                          min_clearance_p01=float(np.nanquantile(res["min_clearance"], 0.01)),
+                          **({"blocks_picked_mean": float(res["blocks_picked"].mean())} if task else {}))))
