@@ -23,7 +23,9 @@ pinned = torch.from_numpy(np.tile(rec, (120, 1, 1))[:8229].astype(np.float32)).p
 inplace = fab.rollout_host(pinned, 2, dtype="f32")        # page-locked records read in place (ticketed tiles, ragged tail)
 assert np.array_equal(inplace["avg_vel"][:8200].view(np.uint8), big["avg_vel"].view(np.uint8))
 from multi_robot_fabrics_b200.episodes import BatchedEpisodes
+blocks, start = m.scenarios.pick_and_place_layout(rec, n_blocks=1, seed=1)
 for kw in (dict(rollout_fabrics=True, resolve_deadlocks=True, estimate_goal=True), dict(rollout_fabrics=False)):
     BatchedEpisodes(rec, n_horizon=3, dtype="f32", n_obst_per_link=2, use_graph=False, **kw).run(3).results()
+    BatchedEpisodes(rec, n_horizon=3, dtype="f32", use_graph=False, blocks=blocks, start_goal=start, **kw).run(3).results()
 torch.cuda.synchronize()
 print("sanitize probe done", float(act.abs().max()))
