@@ -216,6 +216,16 @@ int mrf_rollout_cart_host_f64(mrf_handle_t h, int robot, const double* rec, int 
                               double* avg_vel, double* qN, double* qdN, int64_t B);
 int mrf_rollout_cart_host_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,
                               float* avg_vel, float* qN, float* qdN, int64_t B);
+/* Sweeps of independent batches: a two-deep pipeline over the in-place path of mrf_rollout_host_*.  submit enqueues one
+ * batch (all buffers page-locked; they must stay untouched until the matching wait) and returns; with two batches in
+ * flight it first waits for the older one.  wait(all = 0) blocks until the oldest submitted batch has its results in
+ * host memory, wait(all = 1) until every submitted batch has.  The PCIe reads of batch i+1 overlap the horizons of
+ * batch i.  Same results as mrf_rollout_host_* (get_velocity_rollouts, forward_planner_Jointspace.py:298-336). */
+int mrf_rollout_host_submit_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee, double* goal_est,
+                                int64_t B);
+int mrf_rollout_host_submit_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                                int64_t B);
+int mrf_rollout_host_wait(mrf_handle_t h, int all);
 /*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */
 int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,
                             int64_t B);

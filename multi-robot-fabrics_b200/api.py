@@ -58,6 +58,21 @@ class Fabrics:
                  hptr(o.get("qN")), hptr(o.get("qdN")), B), "mrf_rollout_host")
         return o
 
+    def rollout_host_submit(self, rec, N: int, out: dict, dtype: str = "f32"):
+        """Asynchronous rollout_host for sweeps: `rec` (B,R,44) and the arrays in `out` (avg_vel (B,R), x_ee (B,R,3),
+        goal_est (B,3); any subset) must be page-locked numpy arrays of the entry's dtype and stay untouched until
+        rollout_host_wait().  Up to two batches are in flight."""
+        dt = _NP[dtype]
+        for a in (rec, *out.values()):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise MrfError("rollout_host_submit: arrays must be C-contiguous and of the entry's dtype")
+        fn = getattr(lib(), f"mrf_rollout_host_submit_{dtype}")
+        check(fn(self.handle.ptr, hptr(rec), N, hptr(out.get("avg_vel")), hptr(out.get("x_ee")), hptr(out.get("goal_est")),
+                 rec.shape[0]), "mrf_rollout_host_submit")
+
+    def rollout_host_wait(self, all: bool = False):
+        check(lib().mrf_rollout_host_wait(self.handle.ptr, 1 if all else 0), "mrf_rollout_host_wait")
+
     def action_host(self, rec, obst=None, robot_first: int = 0, dtype: str = "f64"):
         """rec (B,n_rob,44), obst (B,n_rob,S,10) -> action (B,n_rob,7)."""
         dt = _NP[dtype]

@@ -760,7 +760,10 @@ struct MrfHandle_ {
     long long coop_max_batch; // batches up to this size use the cooperative low-latency rollout kernel
     int zero_copy;            // page-locked host records are read by the kernel directly (MRF_ZERO_COPY=0 disables)
     int zc_window;            // tiles admitted to the bus at a time in that mode
-    unsigned* d_sync;         // its ticket / loaded counters
+    unsigned* d_sync;         // its ticket / loaded counters: one pair per in-flight launch (slot 0 = synchronous entry)
+    int zc_slot;              // next slot of the submit/wait pipeline
+    int zc_pending[2];        // submissions in flight per pipeline slot
+    int zc_oldest;
 };
 
 extern "C" int mrf_version(void) { return 100; }
@@ -844,7 +847,10 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->zc_window = 32;
     if (const char* e = getenv("MRF_ZC_WINDOW")) h->zc_window = atoi(e) > 0 ? atoi(e) : 32;
     h->d_sync = nullptr;
-    if (cudaMalloc(&h->d_sync, 2 * sizeof(unsigned)) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
+    h->zc_slot = 0;
+    h->zc_pending[0] = h->zc_pending[1] = 0;
+    h->zc_oldest = 0;
+    if (cudaMalloc(&h->d_sync, 6 * sizeof(unsigned)) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -901,7 +907,7 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------- device-pointer entries --------------------------------------
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
-                       void* stream, bool aos = false) {
+                       void* stream, bool aos = false, int sync_slot = 0) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -930,7 +936,8 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         rc = set_smem(rollout_kernel<T, RR, UU, AA>, smem);                                                          \
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                           \
-            devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync, (unsigned)h->zc_window); \
+            devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
+            (unsigned)h->zc_window);                                                                                 \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
@@ -940,7 +947,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
             if (aos) MRF_LAUNCH_ROLLOUT_K(RR, false, true) else MRF_LAUNCH_ROLLOUT_K(RR, false, false)               \
         }                                                                                                            \
         break;
-    if (aos) MRF_CUDA(cudaMemsetAsync(h->d_sync, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
+    if (aos) MRF_CUDA(cudaMemsetAsync(h->d_sync + 2 * sync_slot, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
     switch (R) {
         MRF_LAUNCH_ROLLOUT(1)
         MRF_LAUNCH_ROLLOUT(2)
@@ -1341,6 +1348,63 @@ static int rollout_host(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee
         }
     }
     return finish_timed(h);
+}
+
+// Two-deep submit / wait pipeline over the in-place path, for sweeps of independent batches: while batch i computes,
+// the tiles of batch i+1 are already being read over PCIe (the kernels sit on two streams and share the SMs), so the
+// bus fill of one launch hides behind the tail of the previous one.  All buffers must be page-locked.
+static int rollout_wait_oldest(mrf_handle_t h) {
+    const int s = h->zc_oldest;
+    if (!h->zc_pending[s]) return MRF_OK;
+    MRF_CUDA(cudaSetDevice(h->device));
+    MRF_CUDA(cudaEventSynchronize(h->ev_chunk[s]));
+    h->zc_pending[s] = 0;
+    h->zc_oldest = s ^ 1;
+    return MRF_OK;
+}
+template <typename T>
+static int rollout_host_submit(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B) {
+    if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout_host_submit: null argument");
+    if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout_host_submit: B and N must be positive");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const T* view = (const T*)pinned_view(rec);
+    T* outs[3] = {avg_vel, x_ee, goal_est};
+    T* dv[3] = {nullptr, nullptr, nullptr};
+    bool ok = view != nullptr;
+    for (int i = 0; i < 3 && ok; ++i)
+        if (outs[i]) {
+            cudaPointerAttributes a;
+            ok = cudaPointerGetAttributes(&a, outs[i]) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer;
+            if (ok) dv[i] = (T*)a.devicePointer; else (void)cudaGetLastError();
+        }
+    if (!ok) return fail(MRF_EINVAL, "mrf_rollout_host_submit: records and results must be page-locked host memory "
+                                     "(cudaHostAlloc / cudaHostRegister, records 16-byte aligned)");
+    const int s = h->zc_slot;
+    if (h->zc_pending[s]) { // both slots busy: the oldest submission is the one in this slot
+        int rc = rollout_wait_oldest(h);
+        if (rc) return rc;
+    }
+    int rc = rollout_dev<T>(h, view, N, dv[0], dv[1], dv[2], nullptr, nullptr, B, h->s_chunk[s], true, 1 + s);
+    if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev_chunk[s], h->s_chunk[s]));
+    if (!h->zc_pending[s ^ 1]) h->zc_oldest = s;
+    h->zc_pending[s] = 1;
+    h->zc_slot = s ^ 1;
+    return MRF_OK;
+}
+extern "C" int mrf_rollout_host_submit_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee,
+                                           double* goal_est, int64_t B) {
+    return rollout_host_submit<double>(h, rec, N, avg_vel, x_ee, goal_est, B);
+}
+extern "C" int mrf_rollout_host_submit_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee,
+                                           float* goal_est, int64_t B) {
+    return rollout_host_submit<float>(h, rec, N, avg_vel, x_ee, goal_est, B);
+}
+extern "C" int mrf_rollout_host_wait(mrf_handle_t h, int all) {
+    if (!h) return fail(MRF_EINVAL, "mrf_rollout_host_wait: null handle");
+    int rc = rollout_wait_oldest(h);
+    if (rc || !all) return rc;
+    return rollout_wait_oldest(h);
 }
 
 template <typename T, bool CART>

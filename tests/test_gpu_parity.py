@@ -480,3 +480,26 @@ def test_degenerate_inputs_propagate_like_the_oracle(fabs):
             okm &= (np.abs(ref) < 10).all(axis=2, keepdims=True)
         assert np.abs(act - ref)[okm].max() / np.abs(ref[okm]).max() < tol, dtype
     assert np.isnan(ref[1]).all() and np.isnan(ref[5]).all() and np.isfinite(ref[[0, 3, 4]]).all()
+
+
+def test_submit_wait_pipeline_equals_blocking_call(built):
+    """mrf_rollout_host_submit / _wait (two batches in flight) return what the blocking entry returns, batch by batch."""
+    import torch
+    from multi_robot_fabrics_b200 import scenarios
+    R, N, B = 3, 4, 4096 + 5
+    fab = Fabrics(R, estimate_goal=1)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    recs = [pin(np.tile(scenarios.generate(256, R, seed=40 + i), (17, 1, 1))[:B].astype(np.float32)) for i in range(5)]
+    outs = [{"avg_vel": pin(np.zeros((B, R), np.float32)), "x_ee": pin(np.zeros((B, R, 3), np.float32)),
+             "goal_est": pin(np.zeros((B, 3), np.float32))} for _ in range(5)]
+    for rec, out in zip(recs, outs):
+        fab.rollout_host_submit(rec, N, out, dtype="f32")
+    fab.rollout_host_wait(all=True)
+    fab.handle.set_coop_max_batch(0)                       # the blocking reference through the same (throughput) kernel
+    for rec, out in zip(recs, outs):
+        ref = fab.rollout_host(np.array(rec), N, dtype="f32")
+        for k in ref:
+            assert np.array_equal(out[k].view(np.uint8), ref[k].view(np.uint8)), k
+    with pytest.raises(m.MrfError):
+        fab.rollout_host_submit(np.array(recs[0]), N, outs[0], dtype="f32")      # pageable records are refused
+    fab.close()
