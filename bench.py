@@ -397,8 +397,8 @@ def ours(a):
         dist.all_reduce(e2e_pipe_t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * R * H * pipe_steps / float(e2e_pipe_t.item())
     assert np.array_equal(bufs[0][1]["avg_vel"].view(np.uint8), np.ascontiguousarray(bufs[1][1]["avg_vel"][::-1]).view(np.uint8))
-    h2d = int(h_rec.nbytes)
-    d2h = int(sum(v.nbytes for v in out.values()))
+    h2d = int(h_rec.nbytes) * world                       # whole job, like `value`
+    d2h = int(sum(v.nbytes for v in out.values())) * world
 
     # informational: device-resident batches launched back to back on two streams (four record sets = 138 MB > L2, so no
     # flush is needed).  The CTAs of step i+1 fill the SMs that step i's last, partial wave leaves idle; `value` above
