@@ -385,19 +385,37 @@ def ours(a):
     for i in range(4):
         fab.rollout_host_submit(bufs[i % 2][0], H, bufs[i % 2][1], dtype=a.dtype)
     fab.rollout_host_wait(all=True)
+    full_avg = [bufs[0][1]["avg_vel"].copy(), bufs[1][1]["avg_vel"].copy()]
+    # The synthetic scenarios differ in q, qdot, x_goal_0 and weight_goal_0 only -- the per-step entries of the reference's
+    # inputs_action dict; every other argument (x_goal_1/2, weights 1/2, angle_goal_1, constraint_0, radii) is the same for
+    # all scenarios, so the sweep submits COMPACT records (18 of 44 scalars per robot) plus one shared (R,44) template per
+    # batch: the same results with 41 % of the PCIe traffic, which is what bounds the step when eight GPUs share the host.
+    assert np.all(rec_h[:, :, 18:] == rec_h[0:1, :, 18:])
+    shared_tail = np.ascontiguousarray(rec_h[0])
+    cbufs = []
+    for hr, ho in bufs:
+        cv = pin((B, R, 18))
+        cv[...] = hr[:, :, :18]
+        cbufs.append((cv, ho))
+    bufs = cbufs
+    submit = lambda i: fab.rollout_host_submit(bufs[i % 2][0], H, bufs[i % 2][1], dtype=a.dtype, shared=shared_tail)
+    for i in range(4):
+        submit(i)
+    fab.rollout_host_wait(all=True)
+    assert all(np.array_equal(full_avg[k].view(np.uint8), bufs[k][1]["avg_vel"].view(np.uint8)) for k in range(2))
     if world > 1:
         dist.barrier()
     pipe_steps = max(6, min(a.steps, 20))
     t0 = time.perf_counter()
     for i in range(pipe_steps):
-        fab.rollout_host_submit(bufs[i % 2][0], H, bufs[i % 2][1], dtype=a.dtype)
+        submit(i)
     fab.rollout_host_wait(all=True)
     e2e_pipe_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_pipe_t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * R * H * pipe_steps / float(e2e_pipe_t.item())
     assert np.array_equal(bufs[0][1]["avg_vel"].view(np.uint8), np.ascontiguousarray(bufs[1][1]["avg_vel"][::-1]).view(np.uint8))
-    h2d = int(h_rec.nbytes) * world                       # whole job, like `value`
+    h2d = int(bufs[0][0].nbytes + shared_tail.astype(ndt).nbytes) * world      # whole job, like `value`
     d2h = int(sum(v.nbytes for v in out.values())) * world
 
     # informational: device-resident batches launched back to back on two streams (four record sets = 138 MB > L2, so no
@@ -501,7 +519,8 @@ def ours(a):
             "dtype": a.dtype, "data": "synthetic", "config": config_dict(a),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "synchronous_call_value": e2e_sync,
-                    "timing": "host wall clock over a stream of independent batches through mrf_rollout_host_submit / _wait "
+                    "timing": "host wall clock over a stream of independent batches through mrf_rollout_host_submit_compact / _wait "
+                              "(per scenario and robot: q, qdot, x_goal_0, weight_goal_0; the arguments shared by all scenarios once per batch) "
                               "(two in flight, two sets of page-locked buffers; the kernel reads each step's records in place "
                               "over PCIe and writes its results back to host memory; rollout only, the deadlock heuristic "
                               "consumes its host outputs), max over ranks; synchronous_call_value = one blocking "

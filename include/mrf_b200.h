@@ -225,6 +225,15 @@ int mrf_rollout_host_submit_f64(mrf_handle_t h, const double* rec, int N, double
                                 int64_t B);
 int mrf_rollout_host_submit_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
                                 int64_t B);
+/* Compact records for the same pipeline: rec_var [B][R][MRF_G1] holds only what changes from scenario to scenario (q,
+ * qdot, x_goal_0, weight_goal_0 -- the per-step entries of the reference's inputs_action dict,
+ * example_pandas_Jointspace.py:354-368); rec_shared [R][MRF_REC] (ordinary host memory, copied at submission) supplies the
+ * remaining fields of every robot's record (x_goal_1/2, weights 1/2, angle_goal_1, constraint_0, body radii).  Less
+ * than half the bytes cross PCIe; results are identical to submitting the expanded records. */
+int mrf_rollout_host_submit_compact_f64(mrf_handle_t h, const double* rec_var, const double* rec_shared, int N,
+                                        double* avg_vel, double* x_ee, double* goal_est, int64_t B);
+int mrf_rollout_host_submit_compact_f32(mrf_handle_t h, const float* rec_var, const float* rec_shared, int N,
+                                        float* avg_vel, float* x_ee, float* goal_est, int64_t B);
 int mrf_rollout_host_wait(mrf_handle_t h, int all);
 /*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */
 int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,

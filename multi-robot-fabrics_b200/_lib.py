@@ -70,6 +70,7 @@ EXPORTS = [
     "mrf_kinematics_host_f64", "mrf_deadlock_host_f64", "mrf_launch_count", "mrf_last_kernel_ms", "mrf_fma_peak", "mrf_set_coop_max_batch",
     "mrf_episode_step_dev_f64", "mrf_episode_step_dev_f32",
     "mrf_rollout_host_submit_f64", "mrf_rollout_host_submit_f32", "mrf_rollout_host_wait",
+    "mrf_rollout_host_submit_compact_f64", "mrf_rollout_host_submit_compact_f32",
 ]
 
 
@@ -113,6 +114,8 @@ def lib():
     L.mrf_rollout_host_submit_f64.argtypes = [vp, vp, i32, vp, vp, vp, i64]
     L.mrf_rollout_host_submit_f32.argtypes = [vp, vp, i32, vp, vp, vp, i64]
     L.mrf_rollout_host_wait.argtypes = [vp, i32]
+    L.mrf_rollout_host_submit_compact_f64.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64]
+    L.mrf_rollout_host_submit_compact_f32.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64]
     L.mrf_episode_step_dev_f64.argtypes = [vp, C.POINTER(MrfEpisode), i64, vp]
     L.mrf_episode_step_dev_f32.argtypes = [vp, C.POINTER(MrfEpisode), i64, vp]
     L.mrf_fma_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]

@@ -58,7 +58,7 @@ class Fabrics:
                  hptr(o.get("qN")), hptr(o.get("qdN")), B), "mrf_rollout_host")
         return o
 
-    def rollout_host_submit(self, rec, N: int, out: dict, dtype: str = "f32"):
+    def rollout_host_submit(self, rec, N: int, out: dict, dtype: str = "f32", shared=None):
         """Asynchronous rollout_host for sweeps: `rec` (B,R,44) and the arrays in `out` (avg_vel (B,R), x_ee (B,R,3),
         goal_est (B,3); any subset) must be page-locked numpy arrays of the entry's dtype and stay untouched until
         rollout_host_wait().  Up to two batches are in flight."""
@@ -66,6 +66,14 @@ class Fabrics:
         for a in (rec, *out.values()):
             if a.dtype != dt or not a.flags.c_contiguous:
                 raise MrfError("rollout_host_submit: arrays must be C-contiguous and of the entry's dtype")
+        if shared is not None:     # compact records: rec (B,R,18) = q, qdot, x_goal_0, weight_goal_0; shared (R,44)
+            if rec.shape[1:] != (self.n_robots, 18):
+                raise MrfError(f"compact records must be (B,{self.n_robots},18), got {rec.shape}")
+            shared = np.ascontiguousarray(shared, dtype=dt).reshape(self.n_robots, REC)
+            fn = getattr(lib(), f"mrf_rollout_host_submit_compact_{dtype}")
+            check(fn(self.handle.ptr, hptr(rec), hptr(shared), N, hptr(out.get("avg_vel")), hptr(out.get("x_ee")),
+                     hptr(out.get("goal_est")), rec.shape[0]), "mrf_rollout_host_submit_compact")
+            return
         fn = getattr(lib(), f"mrf_rollout_host_submit_{dtype}")
         check(fn(self.handle.ptr, hptr(rec), N, hptr(out.get("avg_vel")), hptr(out.get("x_ee")), hptr(out.get("goal_est")),
                  rec.shape[0]), "mrf_rollout_host_submit")

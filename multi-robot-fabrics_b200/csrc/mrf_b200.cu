@@ -53,7 +53,7 @@ template <typename T, int R, bool UNIFORM, bool AOS>
 __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : MRF_ROLLOUT_MINBLOCKS_F64)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
-                   unsigned* __restrict__ sync, unsigned window) {
+                   unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
@@ -77,19 +77,26 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     const long long bb = live ? b : B - 1; // idle lanes shadow the last scenario so barriers stay uniform
     const T* ld_base = rec + (long long)r * B + bb;
     long long ld_stride = (long long)R * B;
+    const T* tail = rec_tail; // shared trailing fields (device memory, [R][MRF_REC]) when the records are compact
     if (AOS) {
+        // each host record holds the first n_var fields (n_var = MRF_REC: whole records; n_var = MRF_G1 = 18: q, qdot,
+        // x_goal_0, weight_goal_0 -- what changes from scenario to scenario; the rest comes from rec_tail)
         const long long first = (long long)tile * kTile;
         const int nb = (int)(B - first < kTile ? B - first : kTile);
-        const int nvec = nb * R * MRF_REC * (int)sizeof(T) / 16; // MRF_REC * sizeof(T) is a multiple of 16
-        const int4* src = reinterpret_cast<const int4*>(rec + first * R * MRF_REC);
+        const int nvals = nb * R * n_var;
+        const int nvec = nvals * (int)sizeof(T) / 16; // a full tile is a whole number of 16-byte words; a ragged one may not be
+        const T* srcT = rec + first * R * n_var;
+        const int4* src = reinterpret_cast<const int4*>(srcT);
         int4* dst = reinterpret_cast<int4*>(kin);
         for (int i = tid; i < nvec; i += NT) dst[i] = src[i];
+        for (int i = nvec * (16 / (int)sizeof(T)) + tid; i < nvals; i += NT) kin[i] = srcT[i];
         __syncthreads();
         if (tid == 0) atomicAdd(&sync[1], 1u);
-        ld_base = kin + ((live ? lane : nb - 1) * R + r) * MRF_REC;
+        ld_base = kin + ((live ? lane : nb - 1) * R + r) * n_var;
         ld_stride = 1;
+        tail += r * MRF_REC;
     }
-    auto ld = [&](int f) { return AOS ? ld_base[f] : rec[((long long)f * R + r) * B + bb]; };
+    auto ld = [&](int f) { return AOS ? (f < n_var ? ld_base[f] : tail[f]) : rec[((long long)f * R + r) * B + bb]; };
     (void)ld_stride;
 
     T q[kDof], qd[kDof];
@@ -761,6 +768,7 @@ struct MrfHandle_ {
     int zero_copy;            // page-locked host records are read by the kernel directly (MRF_ZERO_COPY=0 disables)
     int zc_window;            // tiles admitted to the bus at a time in that mode
     unsigned* d_sync;         // its ticket / loaded counters: one pair per in-flight launch (slot 0 = synchronous entry)
+    void* d_tail[2];          // shared trailing record fields of compact submissions, one per pipeline slot
     int zc_slot;              // next slot of the submit/wait pipeline
     int zc_pending[2];        // submissions in flight per pipeline slot
     int zc_oldest;
@@ -850,6 +858,9 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->zc_slot = 0;
     h->zc_pending[0] = h->zc_pending[1] = 0;
     h->zc_oldest = 0;
+    h->d_tail[0] = h->d_tail[1] = nullptr;
+    for (int i = 0; i < 2; ++i)
+        if (cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
     if (cudaMalloc(&h->d_sync, 6 * sizeof(unsigned)) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
@@ -873,6 +884,8 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_sync) cudaFree(h->d_sync);
+    for (int i = 0; i < 2; ++i)
+        if (h->d_tail[i]) cudaFree(h->d_tail[i]);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_up[i]);
@@ -907,7 +920,7 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------- device-pointer entries --------------------------------------
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
-                       void* stream, bool aos = false, int sync_slot = 0) {
+                       void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -937,7 +950,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                           \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
-            (unsigned)h->zc_window);                                                                                 \
+            (unsigned)h->zc_window, n_var, rec_tail);                                                                \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
@@ -1363,7 +1376,8 @@ static int rollout_wait_oldest(mrf_handle_t h) {
     return MRF_OK;
 }
 template <typename T>
-static int rollout_host_submit(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B) {
+static int rollout_host_submit(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, int64_t B,
+                               const T* shared = nullptr) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout_host_submit: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout_host_submit: B and N must be positive");
     MRF_CUDA(cudaSetDevice(h->device));
@@ -1384,7 +1398,15 @@ static int rollout_host_submit(mrf_handle_t h, const T* rec, int N, T* avg_vel, 
         int rc = rollout_wait_oldest(h);
         if (rc) return rc;
     }
-    int rc = rollout_dev<T>(h, view, N, dv[0], dv[1], dv[2], nullptr, nullptr, B, h->s_chunk[s], true, 1 + s);
+    int rc;
+    const T* d_tail = nullptr;
+    if (shared) { // compact records: the shared trailing fields travel once per submission (R x 44 scalars)
+        const size_t tb = sizeof(T) * (size_t)h->cfg.n_robots * MRF_REC;
+        MRF_CUDA(cudaMemcpyAsync(h->d_tail[s], shared, tb, cudaMemcpyHostToDevice, h->s_chunk[s]));
+        d_tail = (const T*)h->d_tail[s];
+    }
+    rc = rollout_dev<T>(h, view, N, dv[0], dv[1], dv[2], nullptr, nullptr, B, h->s_chunk[s], true, 1 + s,
+                        shared ? MRF_G1 : MRF_REC, d_tail);
     if (rc) return rc;
     MRF_CUDA(cudaEventRecord(h->ev_chunk[s], h->s_chunk[s]));
     if (!h->zc_pending[s ^ 1]) h->zc_oldest = s;
@@ -1399,6 +1421,16 @@ extern "C" int mrf_rollout_host_submit_f64(mrf_handle_t h, const double* rec, in
 extern "C" int mrf_rollout_host_submit_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee,
                                            float* goal_est, int64_t B) {
     return rollout_host_submit<float>(h, rec, N, avg_vel, x_ee, goal_est, B);
+}
+extern "C" int mrf_rollout_host_submit_compact_f64(mrf_handle_t h, const double* rec_var, const double* rec_shared, int N,
+                                                   double* avg_vel, double* x_ee, double* goal_est, int64_t B) {
+    if (!rec_shared) return fail(MRF_EINVAL, "mrf_rollout_host_submit_compact: null argument");
+    return rollout_host_submit<double>(h, rec_var, N, avg_vel, x_ee, goal_est, B, rec_shared);
+}
+extern "C" int mrf_rollout_host_submit_compact_f32(mrf_handle_t h, const float* rec_var, const float* rec_shared, int N,
+                                                   float* avg_vel, float* x_ee, float* goal_est, int64_t B) {
+    if (!rec_shared) return fail(MRF_EINVAL, "mrf_rollout_host_submit_compact: null argument");
+    return rollout_host_submit<float>(h, rec_var, N, avg_vel, x_ee, goal_est, B, rec_shared);
 }
 extern "C" int mrf_rollout_host_wait(mrf_handle_t h, int all) {
     if (!h) return fail(MRF_EINVAL, "mrf_rollout_host_wait: null handle");

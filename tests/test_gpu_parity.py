@@ -502,4 +502,13 @@ def test_submit_wait_pipeline_equals_blocking_call(built):
             assert np.array_equal(out[k].view(np.uint8), ref[k].view(np.uint8)), k
     with pytest.raises(m.MrfError):
         fab.rollout_host_submit(np.array(recs[0]), N, outs[0], dtype="f32")      # pageable records are refused
+    # compact records: only q, qdot, x_goal_0, weight_goal_0 per scenario, the other fields once per submission
+    assert all(np.all(r[:, :, 18:] == r[0:1, :, 18:]) for r in recs)
+    outs_c = [{k: pin(np.zeros_like(v)) for k, v in o.items()} for o in outs]
+    for rec, out in zip(recs, outs_c):
+        fab.rollout_host_submit(pin(rec[:, :, :18]), N, out, dtype="f32", shared=rec[0])
+    fab.rollout_host_wait(all=True)
+    for out, ref in zip(outs_c, outs):
+        for k in ref:
+            assert np.array_equal(out[k].view(np.uint8), ref[k].view(np.uint8)), k
     fab.close()
