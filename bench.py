@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=65536, help="scenarios per GPU (weak scaling)")
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
