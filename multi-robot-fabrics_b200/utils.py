@@ -133,21 +133,24 @@ class UtilsKinematics:
 
 def compute_x_obsts_dyn_0(q_robots, qdot_robots, x_collision_sphere_poses=None, nr_robots=2, fk_dict_spheres=(),
                           nr_dyn_obsts=(0, 0)):
-    """utils_apply_fk.py:3-33 with the same argument list; sphere POSITIONS come from the environment dict as in the
-    reference (keys whose first element contains the robot index), velocities from the sphere functions."""
-    q = [np.append(q_robots[i], 0) for i in range(nr_robots)]
-    qdot = [np.append(qdot_robots[i], 0) for i in range(nr_robots)]
-    x_dyns_obsts = [[] for _ in range(nr_robots)]
-    v_dyns_obsts = [[] for _ in range(nr_robots)]
-    per_robot = [[] for _ in range(nr_robots)]
-    for i in range(nr_robots):
-        others = [j for j in range(nr_robots) if j != i]
-        per_robot[i] = [x for key, x in x_collision_sphere_poses.items() if str(i) in key[0]]
-        for j in others:
-            x_dyns_obsts[j] = x_dyns_obsts[j] + per_robot[i]
-            v = fk_dict_spheres[j]["vel_fun"](q[j], qdot[j]).full().transpose()
-            v_dyns_obsts[i].extend(np.vsplit(v, nr_dyn_obsts[i]))
-    return x_dyns_obsts, v_dyns_obsts, per_robot
+    """Same call and return values as utils_apply_fk.py:3-33: per ego robot the other robots' sphere positions (taken
+    from the environment dict, keys whose first element names the robot index) and sphere velocities (from the sphere
+    functions, 8-dof argument = joints + one finger), and the per-robot position lists."""
+    pad = lambda a: np.append(a, 0)
+    own_x = {j: [x for key, x in x_collision_sphere_poses.items() if str(j) in key[0]] for j in range(nr_robots)}
+    own_v = {j: fk_dict_spheres[j]["vel_fun"](pad(q_robots[j]), pad(qdot_robots[j])).full().transpose()
+             for j in range(nr_robots)}
+    x_dyn, v_dyn = [], []
+    for ego in range(nr_robots):
+        xs, vs = [], []
+        for j in range(nr_robots):
+            if j == ego:
+                continue
+            xs += own_x[j]
+            vs.extend(np.vsplit(own_v[j], nr_dyn_obsts[ego]))
+        x_dyn.append(xs)
+        v_dyn.append(vs)
+    return x_dyn, v_dyn, [own_x[j] for j in range(nr_robots)]
 
 
 def compute_endeffector(q_robots, qdot_robots, fk_endeff, nr_robots=2):
