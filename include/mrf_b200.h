@@ -20,6 +20,15 @@
  *   mrf_kinematics_*      UtilsKinematics.necessary_kinematics fk/jac/jac_dot functions
  *                         multi_robot_fabrics/utils/utils.py:16-54 (as used at
  *                         examples/example_pandas_Jointspace.py:324-343)
+ *   mrf_obstacles_*       define_symbolic_collision_link_poses sphere functions + compute_x_obsts_dyn_0 and the obstacle
+ *                         assembly of the caller loop
+ *                         multi_robot_fabrics/utils/utils.py:87-119, utils/utils_apply_fk.py:3-33,
+ *                         examples/example_pandas_Jointspace.py:400-412
+ *   mrf_point_action_*    point-mass planner compute_action (examples/example_pointmasses_static.py:102-129,191-199)
+ *   mrf_fsm_*             StateMachine.get_state_machine_panda + gripper action
+ *                         multi_robot_fabrics/others_planner/state_machine.py:70-84,133-214
+ *   mrf_episode_step_*    one iteration of the control loop examples/example_pandas_Jointspace.py:280-458
+ *   mrf_rollout_host_submit_* / _wait   get_velocity_rollouts for a stream of independent batches (sweeps)
  *
  * Conventions
  *  - Plain pointers and sizes; no exceptions cross the boundary.  Every function returns 0 on success or a
@@ -27,7 +36,8 @@
  *  - "_dev" entries take DEVICE pointers owned by the caller, structure-of-arrays with the scenario index
  *    fastest (layouts below), and are asynchronous on the given cudaStream_t (passed as void*).
  *  - "_host" entries take HOST pointers in the reference's natural array-of-records order, copy to the device,
- *    run the same kernels and copy the results back (synchronous).
+ *    run the same kernels and copy the results back (synchronous); page-locked rollout records are read by the kernel
+ *    in place (see mrf_rollout_host_*).
  *  - There is no CPU fallback: without a CUDA device mrf_create fails with MRF_ENODEV.
  *  - A handle is not thread-safe; distinct handles are independent.
  */
