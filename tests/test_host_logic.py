@@ -178,3 +178,16 @@ def test_scenarios_are_deterministic_and_clear(built):
     assert m.scenarios.clearance(a).min() >= 0.25
     x, *_ = o2.kinematics(o2.default_config(3), 2, a[0, 2, 0:7], a[0, 2, 7:14])
     assert np.abs(m.scenarios.link_positions(a[0, 2, 0:7], m.scenarios.mount_matrix(2)) - x).max() < 1e-12
+
+
+def test_pick_and_place_layout_matches_oracle_kinematics(built):
+    """The synthetic pick-and-place task: start goals are the hands' positions (oracle FK), blocks lie `drop` below."""
+    rec = m.scenarios.generate(6, 3, seed=4)
+    blocks, start = m.scenarios.pick_and_place_layout(rec, n_blocks=2, seed=1, spread=0.1, drop=0.2)
+    assert blocks.shape == (6, 2, 3, 3) and start.shape == (6, 3, 3)
+    cfg = o2.default_config(3)
+    for b in range(6):
+        for r in range(3):
+            x = o2.kinematics(cfg, r, rec[b, r, 0:7], rec[b, r, 7:14])[0][7]
+            assert np.abs(start[b, r] - x).max() < 1e-12
+    assert np.allclose(blocks[..., 2], start[:, None, :, 2] - 0.2) and np.abs(blocks[..., :2] - start[:, None, :, :2]).max() <= 0.1
