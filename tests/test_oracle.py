@@ -228,3 +228,23 @@ def test_assumption_knobs_agree_between_o1_and_o2(built):
     assert np.abs(a1 - a2).max() < 1e-11
     base = o2.action(o2.default_config(2), 0, rec, obst[:, 0:3], obst[:, 3:6], obst[:, 6:9], obst[:, 9])
     assert np.abs(a2 - base).max() > 1e-6
+
+
+def test_pick_and_place_cpu_loop_visits_the_protocol(built):
+    """The CPU restatement of the pick-and-place control loop (the checker of the device control step) really grasps and
+    releases a block: states leave 1, the gripper closes and re-opens, at least one block is counted."""
+    from helpers import oracle_pick_and_place
+    import multi_robot_fabrics_b200 as m
+    R, nb = 2, 1
+    rng = np.random.default_rng(9)
+    rec = m.scenarios.generate(4, R, seed=91)
+    rec[:, :, 7:14] = 0.0
+    cfg = o2.default_config(R)
+    b = 3
+    start = np.array([o2.kinematics(cfg, r, rec[b, r, 0:7], rec[b, r, 7:14])[0][7] for r in range(R)])
+    offs = rng.uniform(-0.06, 0.06, (4, R, 2))                       # blocks a few centimetres from the hands
+    blocks = np.zeros((nb, R, 3))
+    for r in range(R):
+        blocks[0, r] = start[r] + np.array([offs[b, r, 0], offs[b, r, 1], -0.16])
+    q, states, picked, n_flags, done_at, q_grip = oracle_pick_and_place(rec[b], blocks, start, 420, 3, estimate=True)
+    assert np.isfinite(q).all() and picked.sum() >= 1 and 10 in states
