@@ -97,6 +97,8 @@ typedef struct MrfConfig {
 typedef struct MrfHandle_* mrf_handle_t;
 
 int mrf_version(void);
+/* Message of the last failure ON THE CALLING THREAD (thread-local storage, not per handle: it also reports failures
+ * of calls that have no handle yet, e.g. mrf_create). Valid until the same thread's next failing call. */
 const char* mrf_last_error(void);
 int mrf_config_default(MrfConfig* cfg, int n_robots);       /* the reference's 2/3-Panda set-up */
 int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out);
@@ -191,6 +193,45 @@ int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, cons
                              const float* avg_sum, const int32_t* sm_state, const int32_t* time_step,
                              int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, int64_t B,
                              void* stream);
+
+/* RF-CV post step of a sweep: the deadlock heuristic in place on rec_work (as mrf_deadlock_rec_dev) with the per-scenario
+ * results a sweep gathers written straight into result [R+1][B] (rows 0..R-1 = avg_vel, row R = deadlock flag as a
+ * number; nullable).  rec = the records the rollout read (unchanged), rec_work = the tensor whose goal / weight rows the
+ * heuristic overwrites (may be the same tensor if the caller does not reuse the records).
+ *
+ * FP32 ("deadlock flags identical", north star): the heuristic thresholds rollout outputs (deadlock_prevention.py:61-66:
+ * vel_avg_tot < 0.16, end-effector distance < 0.35) and compares them with each other (:76 closest pair, :85 leader).
+ * With risk [R][B] given (from mrf_rollout_risk_dev_f32), scenarios whose FP32 values sit within a guard band of one of
+ * those tests (the band widens with the stiffness indicator, see mrf_set_guard) or that are
+ * non-finite are RE-ROLLED BY THE FP64 KERNEL from the same records inside this call, and the heuristic reads the FP64
+ * values for them -- the flags then equal those of a float64 evaluation of the same inputs.  mrf_set_guard() tunes the
+ * bands; mrf_guard_stats() reports how many scenarios were re-rolled.  risk == NULL: no re-roll (plain FP32 decision).
+ * FP64: risk is ignored (nothing to guard). */
+int mrf_rfcv_post_dev_f32(mrf_handle_t h, const float* rec, int N, const float* x_ee, float* rec_work, const float* goal_est,
+                          const float* avg_vel, const float* risk, const int32_t* sm_state, const int32_t* time_step,
+                          int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, float* result,
+                          int64_t B, void* stream);
+int mrf_rfcv_post_dev_f64(mrf_handle_t h, const double* rec, int N, const double* x_ee, double* rec_work,
+                          const double* goal_est, const double* avg_vel, const double* risk, const int32_t* sm_state,
+                          const int32_t* time_step, int32_t* time_deadlock_out, int32_t* st_int, double* st_goal,
+                          int32_t* flag, double* result, int64_t B, void* stream);
+/* mrf_rollout_dev without trajectories plus risk [R][B]: per robot the maximum over the horizon of the summed
+ * collision-leaf metric (sphere leaf 0.02 w / (x^4 rho^2), plane leaf 0.2 s / x^2) -- large near contact, where the
+ * explicit dt integration amplifies FP32 rounding.  Always the throughput kernel (no cooperative small-batch path). */
+int mrf_rollout_risk_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                             float* risk, int64_t B, void* stream);
+int mrf_rollout_risk_dev_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee, double* goal_est,
+                             double* risk, int64_t B, void* stream);
+/* Guard bands of mrf_rfcv_post_dev_f32 (NULL / negative = keep).  A scenario is re-rolled in FP64 when
+ * |vel_avg_tot - dl_avg_vel_constant| <= bands[t], t = (risk >= risk_edges[0]) + (risk >= risk_edges[1]) -- three
+ * stiffness tiers; defaults bands = {2e-5, 4e-3, 0.5}, risk_edges = {40, 200}, calibrated against the FP64 kernel on
+ * 4 x 65536 random scenarios (profiles/r2_guard_calibration.md) -- or when an end-effector distance is within band_dist
+ * (1e-5) of dl_dist_endeff / of a competing distance, or when the FP32 result is non-finite.  cap = most scenarios
+ * re-rolled per call (0 = max(256, B / 16)); the excess is counted as overflow and decided in FP32. */
+int mrf_set_guard(mrf_handle_t h, const double* bands, const double* risk_edges, double band_dist, int64_t cap);
+/* out[0] = scenarios re-rolled in FP64 so far, out[1] = overflow so far, out[2] = listed by the last call.  Synchronise
+ * the streams the post steps ran on first. */
+int mrf_guard_stats(mrf_handle_t h, int64_t* out);
 
 /* Batched pick-and-place state machine step: StateMachine.get_state_machine_panda and
  * get_gripper_action_panda, multi_robot_fabrics/others_planner/state_machine.py:70-84,133-214.

@@ -71,6 +71,8 @@ EXPORTS = [
     "mrf_episode_step_dev_f64", "mrf_episode_step_dev_f32",
     "mrf_rollout_host_submit_f64", "mrf_rollout_host_submit_f32", "mrf_rollout_host_wait",
     "mrf_rollout_host_submit_compact_f64", "mrf_rollout_host_submit_compact_f32",
+    "mrf_rfcv_post_dev_f32", "mrf_rfcv_post_dev_f64", "mrf_rollout_risk_dev_f32", "mrf_rollout_risk_dev_f64",
+    "mrf_set_guard", "mrf_guard_stats",
 ]
 
 
@@ -105,6 +107,10 @@ def lib():
         getattr(L, f"mrf_action_host_{p}").argtypes = [vp, i32, i32, vp, i32, vp, vp, i64]
         getattr(L, f"mrf_rollout_host_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i64]
         getattr(L, f"mrf_rollout_cart_host_{p}").argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, i64]
+        getattr(L, f"mrf_rfcv_post_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        getattr(L, f"mrf_rollout_risk_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, vp]
+    L.mrf_set_guard.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, i64]
+    L.mrf_guard_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mrf_point_action_dev_f64.argtypes = [vp, vp, i32, vp, i32, vp, vp, i64, vp]
     L.mrf_point_action_dev_f32.argtypes = [vp, vp, i32, vp, i32, vp, vp, i64, vp]
     L.mrf_point_action_host_f64.argtypes = [vp, vp, i32, vp, i32, vp, vp, i64]

@@ -53,8 +53,13 @@ template <typename T, int R, bool UNIFORM, bool AOS>
 __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : MRF_ROLLOUT_MINBLOCKS_F64)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
-                   unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail) {
+                   unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail,
+                   T* __restrict__ risk, const unsigned* __restrict__ n_live) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // n_live (device memory, optional; SoA layout only): only the first *n_live of the B columns hold scenarios -- the
+    // grid was sized on the host for a capacity, the count was produced on the device (FP64 re-roll of the guard band)
+    const long long Bn = (!AOS && n_live != nullptr) ? ((long long)*n_live < B ? (long long)*n_live : B) : B;
+    if (!AOS && (long long)blockIdx.x * kTile >= Bn) return;
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
     // (a double-buffered point table with one barrier per step was measured 2 % slower: more shared memory per CTA
@@ -73,8 +78,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         tile = *tk;
     }
     const long long b = (long long)tile * kTile + lane;
-    const bool live = b < B;
-    const long long bb = live ? b : B - 1; // idle lanes shadow the last scenario so barriers stay uniform
+    const bool live = b < Bn;
+    const long long bb = live ? b : Bn - 1; // idle lanes shadow the last scenario so barriers stay uniform
     const T* ld_base = rec + (long long)r * B + bb;
     long long ld_stride = (long long)R * B;
     const T* tail = rec_tail; // shared trailing fields (device memory, [R][MRF_REC]) when the records are compact
@@ -109,6 +114,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     Chain<T> ch;
     const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
     T acc = T(0);
+    prm[P_RISK * NT + tid] = T(0); // running maximum of the stiffness indicator (shared memory: no register held)
     // k = -1: FK at the measured state only (end-effector position, RF-CV goal estimate); k >= 0: horizon steps.
     // One loop body keeps a single copy of chain_forward in the instruction stream.
     const bool want_pre = x_ee != nullptr || goal_est != nullptr || cfg.estimate_goal != 0;
@@ -154,14 +160,15 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         }
         __syncthreads(); // every robot of the tile has published
         // Phase B (:211-249): action against the other robots' published spheres
-        T act[kDof];
+        T act[kDof], stiff;
         if (UNIFORM) {
             SmemSrcUniform<T, R> src{kin, lane, r, vref, aref, cfg.r_obst};
-            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act, &stiff);
         } else {
             SmemSrc<T> src{cfg, kin, NT, lane, r, vref, aref};
-            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
+            fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act, &stiff);
         }
+        prm[P_RISK * NT + tid] = Mth<T>::max(prm[P_RISK * NT + tid], stiff);
 #pragma unroll
         for (int i = 0; i < kDof; ++i) {
             qd[i] = act[i];
@@ -178,6 +185,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     }
     // compute_velocity_average (:102-116): mean SQUARE joint velocity over the horizon
     if (avg_vel != nullptr && live) avg_vel[AOS ? b * R + r : (long long)r * B + b] = acc / (T(N) * T(kDof));
+    // stiffness indicator (maximum over the horizon of fabric_action's sum of leaf metrics), see mrf_rfcv_post_dev_f32
+    if (risk != nullptr && live) risk[AOS ? b * R + r : (long long)r * B + b] = prm[P_RISK * NT + tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,30 +320,47 @@ __device__ __forceinline__ double np_norm3(double x, double y, double z) {
     return __dsqrt_rn(__fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x))));
 }
 
+// Optional FP64 overrides for scenarios the FP32 rollout could not decide safely (see guard_select_kernel): slot[b] >= 0
+// selects column slot[b] of the compact FP64 results avg [R][cap], x_ee [R][3][cap], goal_est [3][cap].
+struct DlOverride {
+    const int* slot;
+    const double* avg;
+    const double* x_ee;
+    const double* goal_est;
+    long long cap;
+};
+
 template <typename T>
 __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
                                 const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
                                 const int* __restrict__ sm_state,
                                 const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
                                 T* __restrict__ st_goal, int* __restrict__ flag, const T* __restrict__ goal_est,
-                                long long B) {
+                                long long B, DlOverride ov, T* __restrict__ result) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int R = c.R;
+    const int os = ov.slot != nullptr ? ov.slot[b] : -1; // >= 0: this scenario was re-rolled in FP64
     if (c.est_robot >= 0 && goal_est != nullptr) // goal_pandas[1] = estimate (example_pandas_Jointspace.py:346-348)
-        for (int k = 0; k < 3; ++k) goals[c.est_robot * c.g_sr + k * c.g_sc + b] = goal_est[(long long)k * B + b];
+        for (int k = 0; k < 3; ++k)
+            goals[c.est_robot * c.g_sr + k * c.g_sc + b] = os >= 0 ? (T)ov.goal_est[k * ov.cap + os] : goal_est[(long long)k * B + b];
     // the reference does this arithmetic in float64 whatever the planner precision
     double x[MRF_MAX_ROBOTS][3], g[MRF_MAX_ROBOTS][3], dist_goal[MRF_MAX_ROBOTS];
     int st[MRF_MAX_ROBOTS];
     double avg_sum = 0.0;
     for (int i = 0; i < R; ++i) {
         for (int k = 0; k < 3; ++k) {
-            x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
-            g[i][k] = (double)goals[i * c.g_sr + k * c.g_sc + b];
+            x[i][k] = os >= 0 ? ov.x_ee[((long long)i * 3 + k) * ov.cap + os] : (double)x_ee[((long long)i * 3 + k) * B + b];
+            g[i][k] = (os >= 0 && i == c.est_robot && goal_est != nullptr) ? ov.goal_est[k * ov.cap + os]
+                                                                           : (double)goals[i * c.g_sr + k * c.g_sc + b];
         }
         dist_goal[i] = np_norm3(__dsub_rn(x[i][0], g[i][0]), __dsub_rn(x[i][1], g[i][1]), __dsub_rn(x[i][2], g[i][2]));
         st[i] = sm_state[(long long)i * B + b];
-        if (avg_vel) avg_sum += (double)avg_vel[(long long)i * B + b];
+        if (avg_vel) {
+            const double a = os >= 0 ? ov.avg[(long long)i * ov.cap + os] : (double)avg_vel[(long long)i * B + b];
+            avg_sum += a;
+            if (result) result[(long long)i * B + b] = (T)a;
+        }
     }
     // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375), or the caller's scalar
     avg_sum = avg_vel ? avg_sum / (double)R : (double)avg_sum_in[b];
@@ -404,6 +430,95 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
     st_int[3 * B + b] = dead1;
     for (int k = 0; k < 3; ++k) st_goal[k * B + b] = (T)g0[k];
     if (flag) flag[b] = fl;
+    if (result) result[(long long)R * B + b] = (T)fl; // what a sweep gathers per scenario: avg_vel[R] and the flag
+}
+
+// ------------------------------------------------------------------------------------------------
+// "deadlock flags identical" for the FP32 path.  The heuristic compares rollout outputs with thresholds
+// (deadlock_prevention.py:61-66: vel_avg_tot < 0.16, ee distance < 0.35) and with each other (:76,85: closest pair,
+// leader = closer to its goal); an FP32 rollout answers those tests like the reference's float64 one unless a value sits
+// within the FP32 error of the threshold.  guard_select_kernel lists exactly those scenarios -- a narrow band for
+// ordinary scenarios, a wide one for numerically stiff ones (risk = max over the horizon of the summed leaf metric:
+// near contact the explicit dt = 0.01 integration amplifies rounding) and anything non-finite; they are re-rolled by the
+// FP64 kernel from the same records and the deadlock kernel reads the FP64 values for them (DlOverride).
+// ------------------------------------------------------------------------------------------------
+struct GuardCfg {
+    int R, est_robot;
+    double c_avg, c_dist, band_dist;
+    double band[3], edge[2]; // |vel_avg_tot - c_avg| <= band[t], tier t = (risk >= edge[0]) + (risk >= edge[1])
+    unsigned cap;
+};
+// counters: [0] listed this call (may exceed cap), [1] not used, [2] cumulative re-rolled, [3] cumulative overflow
+template <typename T>
+__global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, const T* __restrict__ x_ee,
+                                    const T* __restrict__ rec, const T* __restrict__ goal_est, const T* __restrict__ risk,
+                                    int* __restrict__ slot_of, unsigned* __restrict__ counters, int* __restrict__ list,
+                                    long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int R = c.R;
+    const long long RB = (long long)R * B;
+    double s = 0.0, rk = 0.0, x[MRF_MAX_ROBOTS][3], dg[MRF_MAX_ROBOTS];
+    for (int i = 0; i < R; ++i) {
+        s += (double)avg_vel[(long long)i * B + b];
+        if (risk) rk = fmax(rk, (double)risk[(long long)i * B + b]);
+        double d2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
+            const double g = (i == c.est_robot && goal_est != nullptr) ? (double)goal_est[(long long)k * B + b]
+                                                                       : (double)rec[(MRF_G0 + k) * RB + (long long)i * B + b];
+            d2 += (x[i][k] - g) * (x[i][k] - g);
+        }
+        dg[i] = sqrt(d2);
+    }
+    s /= (double)R;
+    const double da = fabs(s - c.c_avg);
+    bool guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk); // non-finite FP32 rollout
+    const double band = c.band[(rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0)];
+    guard = guard || da <= band;
+    // geometric knife edges only matter when the velocity test can pass
+    if (!guard && s < c.c_avg + band) {
+        double de[MRF_MAX_ROBOTS * (MRF_MAX_ROBOTS - 1) / 2];
+        int np = 0;
+        for (int a = 0; a < R; ++a)
+            for (int q = a + 1; q < R; ++q) {
+                const double d = sqrt((x[a][0] - x[q][0]) * (x[a][0] - x[q][0]) + (x[a][1] - x[q][1]) * (x[a][1] - x[q][1]) +
+                                      (x[a][2] - x[q][2]) * (x[a][2] - x[q][2]));
+                guard = guard || fabs(d - c.c_dist) <= c.band_dist;                 // :64
+                if (d < c.c_dist + c.band_dist) {
+                    guard = guard || fabs(dg[a] - dg[q]) <= c.band_dist;            // :85 leader choice
+                    for (int e = 0; e < np; ++e) guard = guard || fabs(de[e] - d) <= c.band_dist; // :76 closest pair
+                    de[np++] = d;
+                }
+            }
+    }
+    int slot = -1;
+    if (guard) {
+        const unsigned t = atomicAdd(&counters[0], 1u);
+        if (t < c.cap) {
+            slot = (int)t;
+            list[t] = (int)b;
+        }
+    }
+    slot_of[b] = slot;
+}
+// compact FP64 records [44][R][cap] of the listed scenarios from the FP32 records [44][R][B] (exact promotion)
+template <typename T>
+__global__ void guard_gather_kernel(const T* __restrict__ rec, double* __restrict__ rec64, const int* __restrict__ list,
+                                    unsigned* __restrict__ counters, int R, long long B, unsigned cap) {
+    const unsigned n = counters[0] < cap ? counters[0] : cap;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        counters[2] += n;
+        counters[3] += counters[0] - n;
+    }
+    if (idx >= (long long)R * cap) return;
+    const int r = (int)(idx / cap);
+    const unsigned slot = (unsigned)(idx - (long long)r * cap);
+    if (slot >= n) return;
+    const long long b = list[slot];
+#pragma unroll 4
+    for (int f = 0; f < MRF_REC; ++f) rec64[((long long)f * R + r) * cap + slot] = (double)rec[((long long)f * R + r) * B + b];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -772,6 +887,11 @@ struct MrfHandle_ {
     int zc_slot;              // next slot of the submit/wait pipeline
     int zc_pending[2];        // submissions in flight per pipeline slot
     int zc_oldest;
+    // FP64 re-roll of guard-band scenarios (mrf_rfcv_post_dev_f32)
+    double guard_band[3], guard_edge[2], guard_band_dist;
+    long long guard_cap;      // 0 = max(256, B / 16)
+    void* guard_buf;          // counters, list, slot_of, compact FP64 records and results
+    size_t guard_bytes;
 };
 
 extern "C" int mrf_version(void) { return 100; }
@@ -804,7 +924,7 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
     c->exec_scale = 1.0;
     static const double pos[4][3] = {{0.0, 0.0, 0.65}, {1.0, 0.0, 0.65}, {0.7, 0.6, 0.65}, {0.0, 0.0, 0.65}};
     for (int r = 0; r < MRF_MAX_ROBOTS; ++r) { // parameters_manipulators.py:83-110,138-150
-        const double yaw = r == 0 ? 0.0 : M_PI;
+        const double yaw = (r == 1 || r == 2) ? M_PI : 0.0; // set_planner_panda: i_robot in {1, 2} (parameters_manipulators.py:138-150)
         double* T = c->mount[r];
         T[0] = cos(yaw); T[1] = -sin(yaw); T[4] = sin(yaw); T[5] = cos(yaw); T[10] = 1.0; T[15] = 1.0;
         T[3] = pos[r][0]; T[7] = pos[r][1]; T[11] = pos[r][2];
@@ -824,6 +944,25 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
     c->dl_time_gate = 10;           // :66,83
     return MRF_OK;
 }
+
+static int create_resources(MrfHandle_* h) {
+    for (int i = 0; i < 2; ++i) MRF_CUDA(cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC));
+    MRF_CUDA(cudaMalloc(&h->d_sync, 12 * sizeof(unsigned))); // [0..5] ticket pairs, [8..11] guard counters
+    MRF_CUDA(cudaMemset(h->d_sync, 0, 12 * sizeof(unsigned)));
+    MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MRF_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    MRF_CUDA(cudaEventCreate(&h->ev0));
+    MRF_CUDA(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < 8; ++i) MRF_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    MRF_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) {
+        MRF_CUDA(cudaStreamCreateWithFlags(&h->s_chunk[i], cudaStreamNonBlocking));
+        MRF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    }
+    return MRF_OK;
+}
+
+extern "C" int mrf_destroy(mrf_handle_t h);
 
 extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     if (!cfg || !out) return fail(MRF_EINVAL, "mrf_create: null argument");
@@ -859,20 +998,28 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->zc_pending[0] = h->zc_pending[1] = 0;
     h->zc_oldest = 0;
     h->d_tail[0] = h->d_tail[1] = nullptr;
-    for (int i = 0; i < 2; ++i)
-        if (cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
-    if (cudaMalloc(&h->d_sync, 6 * sizeof(unsigned)) != cudaSuccess) { delete h; return fail(MRF_ECUDA, "mrf_create: cudaMalloc failed"); }
+    // defaults calibrated on B200 (tools/guard_probe.py, profiles/r2_guard_calibration.md)
+    // FP32 error of vel_avg_tot against FP64 over 4 x 65536 random scenarios, by stiffness tier: risk < 40: max 7e-6;
+    // 40..200: max 9.3e-4; >= 200: up to O(1) (explicit-Euler blow-ups near contact).  A flag can only flip if
+    // |vel_avg_tot - 0.16| <= 2 x that error, hence the bands.
+    h->guard_band[0] = 2e-5;
+    h->guard_band[1] = 4e-3;
+    h->guard_band[2] = 0.5;
+    h->guard_edge[0] = 40.0;
+    h->guard_edge[1] = 200.0;
+    h->guard_band_dist = 1e-5;
+    h->guard_cap = 0;
+    h->guard_buf = nullptr;
+    h->guard_bytes = 0;
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
-    MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    MRF_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    MRF_CUDA(cudaEventCreate(&h->ev0));
-    MRF_CUDA(cudaEventCreate(&h->ev1));
-    for (int i = 0; i < 8; ++i) MRF_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
-    MRF_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
-    for (int i = 0; i < 8; ++i) {
-        MRF_CUDA(cudaStreamCreateWithFlags(&h->s_chunk[i], cudaStreamNonBlocking));
-        MRF_CUDA(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    // every failure below releases what was created so far (the handle is value-initialised: null streams / events /
+    // buffers are skipped by mrf_destroy)
+    int rc = create_resources(h);
+    if (rc != MRF_OK) {
+        const std::string msg = g_err;
+        mrf_destroy(h);
+        return fail(rc, msg);
     }
     *out = h;
     return MRF_OK;
@@ -884,18 +1031,22 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_sync) cudaFree(h->d_sync);
+    if (h->guard_buf) cudaFree(h->guard_buf);
     for (int i = 0; i < 2; ++i)
         if (h->d_tail[i]) cudaFree(h->d_tail[i]);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_up[i]);
-    cudaEventDestroy(h->ev_free);
+    // a partially created handle (mrf_create failure path) holds null streams / events: skip them
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 8; ++i)
+        if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+    if (h->ev_free) cudaEventDestroy(h->ev_free);
     for (int i = 0; i < 8; ++i) {
-        cudaEventDestroy(h->ev_chunk[i]);
-        cudaStreamDestroy(h->s_chunk[i]);
+        if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+        if (h->s_chunk[i]) cudaStreamDestroy(h->s_chunk[i]);
     }
-    cudaStreamDestroy(h->stream);
-    cudaStreamDestroy(h->s_copy);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    (void)cudaGetLastError();
     delete h;
     return MRF_OK;
 }
@@ -920,7 +1071,8 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 // ---------------------------------- device-pointer entries --------------------------------------
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
-                       void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr) {
+                       void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr,
+                       T* risk = nullptr, const unsigned* n_live = nullptr) {
     if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -929,12 +1081,13 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
     if (aos && (qN || qdN)) return fail(MRF_EINVAL, "mrf_rollout: record-order input has no trajectory output");
-    if (!aos && R >= 2 && B <= h->coop_max_batch) {
+    if (!aos && R >= 2 && B <= h->coop_max_batch && !risk) {
+        // (n_live: see rollout_kernel; both kernels take it)
         // few scenarios: latency matters, not throughput -> one CTA per scenario, one warp per robot (mrf_coop.cuh)
         switch (R) {
-            case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
-            case 3: rollout_coop_kernel<T, 3><<<(unsigned)B, 96, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
-            case 4: rollout_coop_kernel<T, 4><<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
+            case 3: rollout_coop_kernel<T, 3><<<(unsigned)B, 96, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
+            case 4: rollout_coop_kernel<T, 4><<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
             default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
         }
         MRF_CUDA(cudaGetLastError());
@@ -950,7 +1103,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                           \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
-            (unsigned)h->zc_window, n_var, rec_tail);                                                                \
+            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live);                                                  \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
@@ -1014,9 +1167,14 @@ static int kinematics_dev(mrf_handle_t h, const T* q, const T* qd, T* x, T* v, T
 template <typename T>
 static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const T* avg_sum,
                         const int32_t* sm_state, const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal,
-                        int32_t* flag, int64_t B, void* stream, bool rec_layout = false, const T* goal_est = nullptr) {
+                        int32_t* flag, int64_t B, void* stream, bool rec_layout = false, const T* goal_est = nullptr,
+                        DlOverride ov = DlOverride{nullptr, nullptr, nullptr, nullptr, 0}, T* result = nullptr) {
     if (!h || !x_ee || !goals || !weights || !sm_state || !time_step || !tdo || !st_int || !st_goal)
         return fail(MRF_EINVAL, "mrf_deadlock: null argument");
+    if (h->cfg.n_robots < 2)
+        return fail(MRF_EINVAL, "mrf_deadlock: the heuristic is defined on robot pairs, n_robots must be >= 2 "
+                                "(deadlock_prevention.py:29-30)");
+    if (result && !avg_vel) return fail(MRF_EINVAL, "mrf_deadlock: the result tensor needs per-robot avg_vel");
     if ((avg_vel == nullptr) == (avg_sum == nullptr))
         return fail(MRF_EINVAL, "mrf_deadlock: give exactly one of avg_vel [R][B] and avg_sum [B]");
     if (B <= 0) return fail(MRF_EINVAL, "mrf_deadlock: B must be positive");
@@ -1028,7 +1186,8 @@ static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, con
             c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
             c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
     deadlock_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, goal_est, (long long)B);
+        d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, goal_est, (long long)B,
+        ov, result);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;
@@ -1104,6 +1263,118 @@ extern "C" int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float
                                         float* st_goal, int32_t* flag, int64_t B, void* stream) {
     return deadlock_rec_dev<float>(h, x_ee, rec, goal_est, avg_vel, avg_sum, sm_state, time_step, time_deadlock_out, st_int,
                                    st_goal, flag, B, stream);
+}
+
+// ---------------------------------- RF-CV post step: FP64 guard re-roll + deadlock heuristic ----------------------
+static int guard_reserve(mrf_handle_t h, size_t bytes) {
+    if (h->guard_bytes >= bytes) return MRF_OK;
+    if (h->guard_buf) MRF_CUDA(cudaFree(h->guard_buf));
+    h->guard_buf = nullptr;
+    h->guard_bytes = 0;
+    if (cudaMalloc(&h->guard_buf, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MRF_ENOMEM, "mrf_rfcv_post: device allocation failed");
+    }
+    h->guard_bytes = bytes;
+    return MRF_OK;
+}
+
+template <typename T>
+static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* rec_work, const T* goal_est,
+                         const T* avg_vel, const T* risk, const int32_t* sm_state, const int32_t* time_step, int32_t* tdo,
+                         int32_t* st_int, T* st_goal, int32_t* flag, T* result, int64_t B, void* stream) {
+    if (!h || !rec || !rec_work || !x_ee || !avg_vel) return fail(MRF_EINVAL, "mrf_rfcv_post: null argument");
+    if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rfcv_post: B and N must be positive");
+    const int R = h->cfg.n_robots;
+    const long long RB = (long long)R * B;
+    const bool est = h->cfg.estimate_goal != 0 && goal_est != nullptr;
+    DlOverride ov{nullptr, nullptr, nullptr, nullptr, 0};
+    if (sizeof(T) == 4 && risk != nullptr) {
+        if (R < 2 || R > 4) return fail(MRF_EINVAL, "mrf_rfcv_post: n_robots must be 2..4");
+        MRF_CUDA(cudaSetDevice(h->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        const long long cap = h->guard_cap > 0 ? h->guard_cap : (B / 16 > 256 ? B / 16 : 256);
+        // doubles first (8-byte aligned), then the integer arrays
+        const size_t n64 = (size_t)cap * ((size_t)MRF_REC * R + R + 3 * R + 3);
+        const size_t bytes = sizeof(double) * n64 + sizeof(int) * ((size_t)cap + (size_t)B);
+        int rc = guard_reserve(h, bytes);
+        if (rc) return rc;
+        double* rec64 = (double*)h->guard_buf;
+        double* avg64 = rec64 + (size_t)MRF_REC * R * cap;
+        double* xee64 = avg64 + (size_t)R * cap;
+        double* gest64 = xee64 + (size_t)3 * R * cap;
+        int* list = (int*)(gest64 + (size_t)3 * cap);
+        int* slot_of = list + cap;
+        unsigned* counters = h->d_sync + 8;
+        MRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
+        GuardCfg g{R, est ? h->cfg.estimate_robot : -1, h->cfg.dl_avg_vel_constant, h->cfg.dl_dist_endeff, h->guard_band_dist,
+                   {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
+        guard_select_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk,
+                                                                           slot_of, counters, list, (long long)B);
+        MRF_CUDA(cudaGetLastError());
+        guard_gather_kernel<T><<<(unsigned)(((long long)R * cap + 127) / 128), 128, 0, st>>>(rec, rec64, list, counters, R,
+                                                                                            (long long)B, (unsigned)cap);
+        MRF_CUDA(cudaGetLastError());
+        // FP64 re-roll of the listed scenarios: grid sized for cap, the kernels read the count from device memory.  Small
+        // capacities use the cooperative low-latency kernel, large ones the throughput kernel (32 scenarios per CTA: a few
+        // CTAs that slot into the tail of the sweep's next FP32 launch instead of one 24 K-register CTA per scenario)
+        const long long keep = h->coop_max_batch;
+        h->coop_max_batch = cap <= 512 ? cap : 0;
+        rc = rollout_dev<double>(h, rec64, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
+                                 nullptr, counters);
+        h->coop_max_batch = keep;
+        if (rc) return rc;
+        h->launches += 2;
+        ov = DlOverride{slot_of, avg64, xee64, gest64, cap};
+    }
+    return deadlock_dev<T>(h, x_ee, rec_work + MRF_G0 * RB, rec_work + MRF_W0 * RB, avg_vel, nullptr, sm_state, time_step, tdo,
+                           st_int, st_goal, flag, B, stream, true, goal_est, ov, result);
+}
+extern "C" int mrf_rfcv_post_dev_f32(mrf_handle_t h, const float* rec, int N, const float* x_ee, float* rec_work,
+                                     const float* goal_est, const float* avg_vel, const float* risk,
+                                     const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                                     int32_t* st_int, float* st_goal, int32_t* flag, float* result, int64_t B, void* stream) {
+    return rfcv_post_dev<float>(h, rec, N, x_ee, rec_work, goal_est, avg_vel, risk, sm_state, time_step, time_deadlock_out,
+                                st_int, st_goal, flag, result, B, stream);
+}
+extern "C" int mrf_rfcv_post_dev_f64(mrf_handle_t h, const double* rec, int N, const double* x_ee, double* rec_work,
+                                     const double* goal_est, const double* avg_vel, const double* risk,
+                                     const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
+                                     int32_t* st_int, double* st_goal, int32_t* flag, double* result, int64_t B,
+                                     void* stream) {
+    return rfcv_post_dev<double>(h, rec, N, x_ee, rec_work, goal_est, avg_vel, risk, sm_state, time_step, time_deadlock_out,
+                                 st_int, st_goal, flag, result, B, stream);
+}
+extern "C" int mrf_rollout_risk_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
+                                        float* risk, int64_t B, void* stream) {
+    return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, nullptr, nullptr, B, stream, false, 0, MRF_REC, nullptr, risk);
+}
+extern "C" int mrf_rollout_risk_dev_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee,
+                                        double* goal_est, double* risk, int64_t B, void* stream) {
+    return rollout_dev<double>(h, rec, N, avg_vel, x_ee, goal_est, nullptr, nullptr, B, stream, false, 0, MRF_REC, nullptr, risk);
+}
+extern "C" int mrf_set_guard(mrf_handle_t h, const double* bands, const double* risk_edges, double band_dist, int64_t cap) {
+    if (!h) return fail(MRF_EINVAL, "mrf_set_guard: null handle");
+    if (bands)
+        for (int i = 0; i < 3; ++i) h->guard_band[i] = bands[i];
+    if (risk_edges) {
+        if (!(risk_edges[0] <= risk_edges[1])) return fail(MRF_EINVAL, "mrf_set_guard: risk_edges must be ascending");
+        h->guard_edge[0] = risk_edges[0];
+        h->guard_edge[1] = risk_edges[1];
+    }
+    if (band_dist >= 0) h->guard_band_dist = band_dist;
+    if (cap >= 0) h->guard_cap = cap;
+    return MRF_OK;
+}
+extern "C" int mrf_guard_stats(mrf_handle_t h, int64_t* out) {
+    if (!h || !out) return fail(MRF_EINVAL, "mrf_guard_stats: null argument");
+    MRF_CUDA(cudaSetDevice(h->device));
+    unsigned c[4];
+    MRF_CUDA(cudaMemcpy(c, h->d_sync + 8, sizeof(c), cudaMemcpyDeviceToHost));
+    out[0] = c[2];
+    out[1] = c[3];
+    out[2] = c[0];
+    return MRF_OK;
 }
 
 // ---------------------------------- host-pointer entries ----------------------------------------
@@ -1942,7 +2213,7 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
     if (ep->rollout_fabrics) {
         rc = rollout_dev<T>(h, rec, ep->n_horizon, (T*)ep->avg_vel, (T*)ep->x_ee, (T*)ep->goal_est, nullptr, nullptr, B, stream);
         if (rc) return rc;
-        if (ep->resolve_deadlocks) {
+        if (ep->resolve_deadlocks && R >= 2) { // the heuristic is defined on robot pairs
             rc = deadlock_rec_dev<T>(h, (const T*)ep->x_ee, rec, est ? (const T*)ep->goal_est : nullptr, (const T*)ep->avg_vel,
                                      nullptr, sm_state, ep->time_step, ep->time_deadlock_out, ep->st_int, (T*)ep->st_goal,
                                      ep->flag, B, stream);
@@ -1969,7 +2240,7 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
     if (rc) return rc;
     episode_post_kernel<T><<<g_b, 128, 0, st>>>(
         rec, (const T*)ep->action, xee, link_major, (const T*)ep->goal0, R > 1 ? (const T*)ep->spheres_x : nullptr, S1,
-        (ep->rollout_fabrics && ep->resolve_deadlocks) ? ep->flag : nullptr, lim, (T)h->cfg.dt, (T)ep->epsilon,
+        (ep->rollout_fabrics && ep->resolve_deadlocks && R >= 2) ? ep->flag : nullptr, lim, (T)h->cfg.dt, (T)ep->epsilon,
         (T)ep->clearance_radius_sum, ep->time_step, ep->done_at, ep->deadlock_steps, (T*)ep->min_clearance, R, (long long)B,
         pnp ? sm_state : nullptr, pnp ? (T*)ep->q_grip : nullptr, pnp ? (const T*)ep->grip_action : nullptr);
     MRF_CUDA(cudaGetLastError());

@@ -42,7 +42,7 @@ template <typename T> constexpr bool kAxesInSmem = sizeof(T) == 8;
 template <typename T> constexpr int kKinRows = kPts * 9 + (kAxesInSmem<T> ? 18 : 0);
 constexpr int kMaxEnt = 8 * (MRF_MAX_ROBOTS - 1); // sphere entries one robot sees (all links of all other robots)
 // parameter block (per thread, shared memory)
-enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P_NH = 19, P_DN = 22, P_RB = 23, P_N = 29 };
+enum { P_G0 = 0, P_W0 = 3, P_G1 = 4, P_W1 = 7, P_G2 = 8, P_W2 = 9, P_ANG = 10, P_NH = 19, P_DN = 22, P_RB = 23, P_RISK = 29, P_N = 30 };
 
 // ------------------------------------------------------------------------------------------------
 // math
@@ -567,8 +567,12 @@ template <typename T> MRF_HD void attractor_scalars(T n, T w, T& dpsi, T& m2) {
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename Src>
 MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, const Chain<T>& ch, const T* kin,
-                          const T* prm, int NT, int tid, const Src& src, T* act) {
+                          const T* prm, int NT, int tid, const Src& src, T* act, T* stiff = nullptr) {
     const T sigma = cfg.sigma;
+    // stiffness indicator of this evaluation: sum over the ego points of trace(A_e) = sum over the collision leaves of
+    // M_l |grad x|^2 (sphere leaf: 0.02 w / (x^4 rho^2), plane leaf: 0.2 s / x^2).  Near contact it explodes like 1/x^4;
+    // the FP32 rollouts use its maximum over the horizon to decide which scenarios are re-rolled in FP64 (mrf_rfcv_post).
+    T stiff_sum = T(0);
     Spec<T> G;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -706,6 +710,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             acc.b.x += plo(acc2.b.x) + phi(acc2.b.x); acc.b.y += plo(acc2.b.y) + phi(acc2.b.y);
             acc.b.z += plo(acc2.b.z) + phi(acc2.b.z);
             num += plo(acc2.num) + phi(acc2.num);
+            stiff_sum += (acc.A.xx + acc.A.yy) + acc.A.zz;
             V3<T> Jc[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j)
@@ -721,6 +726,8 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             }
         }
     }
+
+    if (stiff != nullptr) *stiff = stiff_sum;
 
     // ---- q^T M_g q ----
     T qMq = G.m7 * qd[6] * qd[6];

@@ -418,6 +418,11 @@ class deadlockprevention:  # noqa: N801 (the reference's class name)
     def deadlock_checking(self, x_robots, goal_robots, goal_weights, time_step, time_deadlock_out, avg_sum,
                           state_machine_robots=()):
         R = self.n_robots
+        # the reference indexes state_machine_robots[z[0]] for every pair (deadlock_prevention.py:62): a short list is an
+        # IndexError there, and would be an out-of-bounds read in the kernel
+        if len(state_machine_robots) != R or len(x_robots) != R or len(goal_robots) != R or len(goal_weights) != R:
+            raise IndexError(f"deadlock_checking: x_robots, goal_robots, goal_weights and state_machine_robots need one "
+                             f"entry per robot ({R})")
         x = np.ascontiguousarray(np.stack([_vec(v, 3) for v in x_robots])[None])
         g = np.ascontiguousarray(np.stack([_vec(v, 3) for v in goal_robots])[None])
         w = np.ascontiguousarray(np.array([[float(np.asarray(v).reshape(-1)[0]) for v in goal_weights]]))

@@ -21,7 +21,7 @@ PANDA_LIMITS = np.array([[-2.8973, 2.8973], [-1.7628, 1.7628], [-2.8973, 2.8973]
 VEL_LIMITS = np.array([2.175, 2.175, 2.175, 2.175, 2.61, 2.61, 2.61])
 ROT_PANDA = np.array([[0.0, 0.0, -1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]])   # parameters_manipulators.py:121
 MOUNT_XYZ = np.array([[0.0, 0.0, 0.65], [1.0, 0.0, 0.65], [0.7, 0.6, 0.65], [0.0, 0.0, 0.65]])
-MOUNT_YAW = np.array([0.0, math.pi, math.pi, math.pi])
+MOUNT_YAW = np.array([0.0, math.pi, math.pi, 0.0])      # example_pandas_Jointspace.py:108-110: pi for robots 1, 2
 POS0_2 = np.array([1.125, 0.19, 0.12, -1.66, -0.0, 1.88, np.pi / 4])          # parameters_manipulators.py:93
 
 _JXYZ = np.array([[0, 0, 0.333], [0, 0, 0], [0, -0.316, 0], [0.0825, 0, 0], [-0.0825, 0.384, 0], [0, 0, 0],

@@ -14,8 +14,9 @@ import numpy as np
 
 
 class DeadlockOracle:
-    def __init__(self, n_robots: int):
+    def __init__(self, n_robots: int, dist_endeff: float = 0.35):
         self.n = n_robots
+        self.dist_endeff = dist_endeff   # :64 (a literal in the reference; a knob here so tests can provoke deadlocks)
         # deadlock_prevention.py:20-27 (manipulator branch)
         self.avg_vel_constant, self.dist_constant = 0.16, 0.0
         self.w_follower, self.w_leader = 2, 3
@@ -35,7 +36,7 @@ class DeadlockOracle:
             d_ee = np.linalg.norm(x[a] - x[b])                                        # :63
             ok_state = states[a] in (0, 1) and states[b] in (0, 1)                    # :62
             if (avg_sum < self.avg_vel_constant and dist_goal[a] + dist_goal[b] > self.dist_constant
-                    and time_step > 10 and ok_state and d_ee < 0.35):                 # :66
+                    and time_step > 10 and ok_state and d_ee < self.dist_endeff):                 # :66
                 flag = True                                                           # :73
                 if d_ee < best:          # :74-80 rescans recorded distances with a strict '<': first minimum wins
                     best, self.dead = d_ee, [a, b]

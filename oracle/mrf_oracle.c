@@ -62,7 +62,7 @@ void mrfo_config_default(mrfo_config* c, int n_robots) {
     /* parameters_manipulators.py:83-110,138-150: mounts (0,0,.65) yaw 0; (1,0,.65) yaw pi; (0.7,0.6,.65) yaw pi */
     static const double pos[3][3] = {{0.0, 0.0, 0.65}, {1.0, 0.0, 0.65}, {0.7, 0.6, 0.65}};
     for (int r = 0; r < MRFO_MAX_ROBOTS; r++) {
-        double yaw = (r == 0) ? 0.0 : M_PI;
+        double yaw = (r == 1 || r == 2) ? M_PI : 0.0; /* set_planner_panda: i_robot in {1, 2} */
         const double* p = pos[r < 3 ? r : 0];
         double* T = c->mount[r];
         memset(T, 0, 16 * sizeof(double));
@@ -550,6 +550,16 @@ int mrfo_max_threads(void) {
 #endif
 }
 
+/* Host cores this process may run on, whatever OMP_NUM_THREADS says (a launcher such as torchrun exports
+ * OMP_NUM_THREADS=1 to every rank; the CPU arm of bench.py sets its thread count explicitly from this). */
+int mrfo_hw_threads(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
 int mrfo_rollout_jointspace_batch(const mrfo_config* c, const double* rec, long batch, int N, double* qN,
                                   double* qdN, double* avg_vel, double* x_ee, int n_threads) {
     const int R = c->n_robots;
@@ -571,5 +581,33 @@ int mrfo_action_batch(const mrfo_config* c, int robot, const double* rec, long b
     for (long b = 0; b < batch; b++)
         rc |= mrfo_action(c, robot, rec + b * MRFO_ROBOT_IN, S, xo + b * 3 * S, vo + b * 3 * S, ao + b * 3 * S,
                           ro + b * S, action + b * DOF, 0);
+    return rc;
+}
+
+/* RF-CV control-step rollout, batched: per scenario the constant-velocity goal estimate of robot `est_robot`
+ * (example_pandas_Jointspace.py:346-348: goal_1 = x_ee + est_h * v_ee, with v_ee the first Jacobian column unless
+ * use_jqd) followed by the coupled rollout -- the whole per-scenario path inside one OpenMP loop, nothing left to a
+ * Python loop.  rec is not modified; goal_est (nullable) [batch][3] receives the estimate. */
+int mrfo_rollout_rfcv_batch(const mrfo_config* c, const double* rec, long batch, int N, int est_robot, double est_h,
+                            int use_jqd, double* qN, double* qdN, double* avg_vel, double* x_ee, double* goal_est,
+                            int n_threads) {
+    const int R = c->n_robots;
+    int rc = 0;
+    if (est_robot >= R) est_robot = -1;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads > 0 ? n_threads : mrfo_max_threads()) reduction(| : rc)
+    for (long b = 0; b < batch; b++) {
+        double loc[MRFO_MAX_ROBOTS * MRFO_ROBOT_IN];
+        memcpy(loc, rec + b * R * MRFO_ROBOT_IN, sizeof(double) * (size_t)R * MRFO_ROBOT_IN);
+        if (est_robot >= 0) {
+            double* rr = loc + est_robot * MRFO_ROBOT_IN;
+            double x[3], v[3];
+            mrfo_endeffector(c, est_robot, rr + MRFO_Q, rr + MRFO_QD, use_jqd, x, v);
+            for (int k = 0; k < 3; k++) rr[MRFO_G0 + k] = x[k] + est_h * v[k];
+            if (goal_est)
+                for (int k = 0; k < 3; k++) goal_est[b * 3 + k] = rr[MRFO_G0 + k];
+        }
+        rc |= mrfo_rollout_jointspace(c, loc, N, qN ? qN + b * R * N * DOF : 0, qdN ? qdN + b * R * N * DOF : 0,
+                                      avg_vel ? avg_vel + b * R : 0, x_ee ? x_ee + b * R * 3 : 0);
+    }
     return rc;
 }

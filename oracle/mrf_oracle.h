@@ -87,7 +87,14 @@ int mrfo_point_action(const mrfo_config* c, const double* q, const double* qd, c
                       double r_body, int Ss, const double* xs, const double* rs, int Sd, const double* xd,
                       const double* vd, const double* ad, const double* rd, double* action);
 
+/* RF-CV control-step rollout: goal estimate of robot est_robot (-1: none; example_pandas_Jointspace.py:346-348) +
+ * coupled rollout, per scenario inside one OpenMP loop.  goal_est (nullable) [batch][3]. */
+int mrfo_rollout_rfcv_batch(const mrfo_config* c, const double* rec, long batch, int N, int est_robot, double est_h,
+                            int use_jqd, double* qN, double* qdN, double* avg_vel, double* x_ee, double* goal_est,
+                            int n_threads);
+
 int mrfo_max_threads(void);
+int mrfo_hw_threads(void); /* cores available to the process, ignoring OMP_NUM_THREADS */
 
 #ifdef __cplusplus
 }

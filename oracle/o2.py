@@ -56,7 +56,10 @@ def lib():
         _lib.mrfo_action_batch.argtypes = [cp, C.c_int, d, C.c_long, C.c_int, d, d, d, d, d, C.c_int]
         _lib.mrfo_spheres.argtypes = [cp, C.c_int, d, d, C.c_int, d, d, d, d]
         _lib.mrfo_point_action.argtypes = [cp, d, d, d, C.c_double, C.c_double, C.c_int, d, d, C.c_int, d, d, d, d, d]
+        _lib.mrfo_rollout_rfcv_batch.argtypes = [cp, d, C.c_long, C.c_int, C.c_int, C.c_double, C.c_int, d, d, d, d, d,
+                                                 C.c_int]
         _lib.mrfo_max_threads.restype = C.c_int
+        _lib.mrfo_hw_threads.restype = C.c_int
     return _lib
 
 
@@ -137,6 +140,22 @@ def rollout_jointspace_avg(cfg, rec, N, n_threads=0):
     return avg, xee
 
 
+def rollout_rfcv(cfg, rec, N, est_robot=1, est_h=0.2, use_jqd=False, trajectories=False, n_threads=0):
+    """RF-CV control-step rollout of a batch (B,R,44): goal estimate of `est_robot` (example_pandas_Jointspace.py:346-348;
+    -1 = none) + coupled rollout, all inside one OpenMP loop of the C library.
+    -> dict(avg_vel (B,R), x_ee (B,R,3), goal_est (B,3)[, qN, qdN (B,R,N,7)])."""
+    rec = _c(rec)
+    R = cfg.n_robots
+    rec3 = rec.reshape(-1, R, ROBOT_IN)
+    B = rec3.shape[0]
+    o = dict(avg_vel=np.zeros((B, R)), x_ee=np.zeros((B, R, 3)), goal_est=rec3[:, min(max(est_robot, 0), R - 1), G0:G0 + 3].copy())
+    if trajectories:
+        o["qN"], o["qdN"] = np.zeros((B, R, N, 7)), np.zeros((B, R, N, 7))
+    lib().mrfo_rollout_rfcv_batch(C.byref(cfg), _p(rec3), B, N, est_robot, est_h, int(use_jqd), _p(o.get("qN")),
+                                  _p(o.get("qdN")), _p(o["avg_vel"]), _p(o["x_ee"]), _p(o["goal_est"]), n_threads)
+    return o
+
+
 def rollout_cartesian(cfg, robot, rec, xo, vo, ro, N):
     rec = _c(rec)
     xo, vo, ro = _c(xo).reshape(-1, 3), _c(vo).reshape(-1, 3), _c(ro).reshape(-1)
@@ -209,6 +228,11 @@ def point_action(cfg, q, qd, goal, w_goal, r_body, xs=(), rs=(), xd=(), vd=(), a
 
 def max_threads() -> int:
     return int(lib().mrfo_max_threads())
+
+
+def hw_threads() -> int:
+    """Cores the process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    return max(1, min(int(lib().mrfo_hw_threads()), len(os.sched_getaffinity(0))))
 
 
 # --------------------------------------------------------------------------------------------- #

@@ -4,6 +4,15 @@ import numpy as np
 from oracle import o2
 
 
+def rel_ps(got, ref, ok=None):
+    """Worst PER-SCENARIO relative error: for every scenario (axis 0) max |got - ref| over the remaining axes divided by
+    that scenario's own max |ref|; the maximum over the scenarios selected by `ok`."""
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    ax = tuple(range(1, ref.ndim))
+    e = np.abs(got - ref).max(axis=ax) / np.abs(ref).max(axis=ax)
+    return float(e.max() if ok is None else e[ok].max())
+
+
 def oracle_rollout(rec, R, N, estimate_goal=0, static_or_dyn=1):
     """Oracle O2 coupled rollout incl. the RF-CV goal estimate; returns qN, qdN, avg, xee, goal_est, ok-mask."""
     ocfg = o2.default_config(R, static_or_dyn=static_or_dyn)
