@@ -10,7 +10,7 @@ kernel (goal estimate + H horizon steps for 3 Pandas per scenario, FP32) followe
 (mrf_rfcv_post_dev_f32: FP64 re-roll of the scenarios whose FP32 results sit in the guard band of a deadlock threshold,
 then the deadlock kernel, which writes the per-scenario result tensor avg_vel[R] + flag) and, for N > 1, the all_gather of
 that tensor.  The steps of a sweep are independent batches: the post step and the gather of step i run on a side stream
-while the compute stream already runs the rollout of step i+1 (double-buffered outputs; sharding.gather_into).  One
+while the compute stream already runs the rollout of step i+1 (three output sets, high-priority side stream; sharding.gather_into).  One
 robot-step = one fabric action evaluation of one robot at one horizon step (FK/J/Jdot qdot, leaves, pullback, solve,
 integrator update, avg-velocity accumulation).
 
@@ -263,67 +263,95 @@ def bind_to_gpu_socket(index: int) -> None:
 
 
 def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_risk):
-    """K steps of the RF-CV sweep: rollout on the compute stream, post step (+ gather) on a side stream, two sets of
-    outputs in flight.  Returns total ms (events, first launch -> everything complete), per-rollout kernel ms, buffers."""
+    """K steps of the RF-CV sweep.  The steps are independent batches, so they are pipelined the way a production sweep
+    runs them: rollouts alternate between TWO streams (the first wave of step i+1 fills the SMs that the last, partial
+    wave of step i leaves idle: 2048 tiles on 592 CTA slots), the post step (+ gather) of every step runs on a third
+    stream, NBUF output sets are in flight.  Returns total ms (events: before the first launch -> everything complete),
+    per-launch rollout durations, buffers."""
     from multi_robot_fabrics_b200 import sharding
     _, R, B = recs[0].shape
     tdt = recs[0].dtype
     main = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(device=dev)
-    mk = lambda *shape, dtype=tdt: [torch.empty(shape, dtype=dtype, device=dev) for _ in range(2)]
+    NBUF = int(os.environ.get("MRF_BENCH_NBUF", "4"))
+    NROLL = int(os.environ.get("MRF_BENCH_NROLL", "2"))
+    roll = [torch.cuda.Stream(device=dev) for _ in range(NROLL)] if NROLL > 1 else [main]
+    # the rollout kernels fill the register file of every SM, so the post step's small kernels run when rollout CTAs
+    # retire; high priority places them first
+    # the post steps of consecutive batches overlap too (one FP64 re-roll tile has a latency of ~0.8 ms): one stream and
+    # one scratch slot per output set
+    NPOST = min(NBUF, 4, int(os.environ.get("MRF_BENCH_NPOST", "4")))
+    sides = [torch.cuda.Stream(device=dev, priority=int(os.environ.get("MRF_BENCH_PRIO", "-1"))) for _ in range(NPOST)]
+    mk = lambda *shape, dtype=tdt: [torch.empty(shape, dtype=dtype, device=dev) for _ in range(NBUF)]
     avg, xee, gest, risk = mk(R, B), mk(R, 3, B), mk(3, B), mk(R, B)
     flag, result = mk(B, dtype=torch.int32), mk(R + 1, B)
     gathered = mk(world, R + 1, B) if world > 1 else None
-    sm_state = torch.zeros((R, B), dtype=torch.int32, device=dev)
+    # heuristic state per output set (concurrent post steps must not share the in/out state arrays)
+    sm_state = [torch.zeros((R, B), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     tstep = torch.full((B,), 100, dtype=torch.int32, device=dev)
-    tdo = torch.full((B,), 1000, dtype=torch.int32, device=dev)
-    st_int = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous()
-    st_goal = torch.zeros((3, B), dtype=tdt, device=dev)
-    roll_done = [torch.cuda.Event() for _ in range(2)]
-    post_done = [torch.cuda.Event() for _ in range(2)]
+    tdo = [torch.full((B,), 1000, dtype=torch.int32, device=dev) for _ in range(NBUF)]
+    st_int = [torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous() for _ in range(NBUF)]
+    st_goal = [torch.zeros((3, B), dtype=tdt, device=dev) for _ in range(NBUF)]
+    roll_done = [torch.cuda.Event() for _ in range(NBUF)]
+    post_done = [torch.cuda.Event() for _ in range(NBUF)]
     kev = []
 
     def step(i, timed):
-        k, s_ = i % 2, i % len(recs)
-        if i >= 2:
-            main.wait_event(post_done[k])          # the post step of i-2 has consumed this output set
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(main)
-        fab.rollout_dev(recs[s_], H, avg_vel=avg[k], x_ee=xee[k], goal_est=gest[k], risk=risk[k] if with_risk else None)
-        if timed:
-            e1.record(main)
-            kev.append((e0, e1))
-        roll_done[k].record(main)
+        k, s_ = i % NBUF, i % len(recs)
+        rs = roll[i % len(roll)]
+        with torch.cuda.stream(rs):
+            if i >= NBUF:
+                rs.wait_event(post_done[k])        # the post step of step i-NBUF has consumed this output set
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(rs)
+            fab.rollout_dev(recs[s_], H, avg_vel=avg[k], x_ee=xee[k], goal_est=gest[k], risk=risk[k] if with_risk else None)
+            if timed:
+                e1.record(rs)
+                kev.append((e0, e1))
+            roll_done[k].record(rs)
+        side = sides[k % NPOST]
         with torch.cuda.stream(side):
             side.wait_event(roll_done[k])
-            fab.rfcv_post_dev(recs[s_], H, xee[k], works[s_], gest[k], avg[k], sm_state, tstep, tdo, st_int, st_goal,
-                              risk=risk[k] if with_risk else None, flag=flag[k], result=result[k])
+            fab.rfcv_post_dev(recs[s_], H, xee[k], works[s_], gest[k], avg[k], sm_state[k], tstep, tdo[k], st_int[k],
+                              st_goal[k], risk=risk[k] if with_risk else None, flag=flag[k], result=result[k],
+                              slot=k % NPOST)
             if world > 1:
                 sharding.gather_into(gathered[k], result[k])
             post_done[k].record(side)
 
+    def join():
+        for s_ in roll + sides:
+            if s_ is not main:
+                main.wait_stream(s_)
+
+    for s_ in roll + sides:
+        if s_ is not main:
+            s_.wait_stream(main)
     for i in range(warmup):
         step(i, False)
-    main.wait_stream(side)
+    join()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(main)
-    side.wait_event(t0)
+    for s_ in roll + sides:
+        if s_ is not main:
+            s_.wait_event(t0)
+    h0 = time.perf_counter()
     for i in range(steps):
         step(warmup + i, True)
-    main.wait_stream(side)
+    host_ms = (time.perf_counter() - h0) * 1e3
+    join()
     t1.record(main)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    last = (warmup + steps - 1) % 2
-    return dict(total_ms=t0.elapsed_time(t1), kern_ms=[e0.elapsed_time(e1) for e0, e1 in kev], avg=avg[last],
-                flag=flag[last], result=result[last], last_set=(warmup + steps - 1) % len(recs),
-                gathered=None if gathered is None else gathered[last])
+    last = (warmup + steps - 1) % NBUF
+    return dict(host_enqueue_ms=host_ms, total_ms=t0.elapsed_time(t1), kern_ms=[e0.elapsed_time(e1) for e0, e1 in kev],
+                avg=avg[last], flag=flag[last], result=result[last], last_set=(warmup + steps - 1) % len(recs),
+                gathered=None if gathered is None else gathered[last], rollout_streams=len(roll))
 
 
 def ours(a):
@@ -367,7 +395,10 @@ def ours(a):
     launches0 = fab.handle.launches
     torch.cuda.synchronize()
     sampler.start()
-    sw = _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_risk=True)
+    if os.environ.get("MRF_BENCH_GUARD_BANDS"):      # diagnostics: override the guard tiers, e.g. "0,0,0"
+        fab.set_guard(bands=[float(v) for v in os.environ["MRF_BENCH_GUARD_BANDS"].split(",")])
+    sw = _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup,
+                with_risk=os.environ.get("MRF_BENCH_NORISK", "0") != "1")
     clocks = sampler.stop()
     launches = (fab.handle.launches - launches0) * steps // (steps + warmup)
     total_ms = torch.tensor([sw["total_ms"]], dtype=torch.float64, device=dev)
@@ -377,7 +408,8 @@ def ours(a):
     value = world * B * R * H * steps / total_s
     kernel_ms = statistics.mean(sw["kern_ms"])
     rerolled, overflow, _ = fab.guard_stats()
-    guard = {"fp64_rerolled_per_step": rerolled / (steps + warmup), "overflow": overflow}
+    guard = {"fp64_rerolled_per_step": rerolled / (steps + warmup), "overflow": overflow,
+             "host_enqueue_ms_per_step": sw["host_enqueue_ms"] / steps}
     nonfinite = float((~torch.isfinite(sw["avg"])).any(dim=0).float().mean().item())
 
     # parity spot check of what was timed (oracle as the checker; not timed): avg_vel and deadlock flags of the last step

@@ -55,6 +55,7 @@ extern "C" {
 #define MRF_NLINKS 8   /* panda_link1..8, examples/parameters_manipulators.py:25-26 */
 #define MRF_REC 44     /* scalars per robot record */
 #define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
+#define MRF_GUARD_SLOTS 4   /* scratch slots of mrf_rfcv_post_dev (concurrent post steps on different streams) */
 #define MRF_MAX_SPHERES_PER_LINK 8   /* n_obst_per_link, examples/configs/panda_config.yaml:8 (reference default 4) */
 
 /* Per-robot record = the numeric arguments of one fabric action / of get_velocity_rollouts
@@ -201,20 +202,23 @@ int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, cons
  *
  * FP32 ("deadlock flags identical", north star): the heuristic thresholds rollout outputs (deadlock_prevention.py:61-66:
  * vel_avg_tot < 0.16, end-effector distance < 0.35) and compares them with each other (:76 closest pair, :85 leader).
- * With risk [R][B] given (from mrf_rollout_risk_dev_f32), scenarios whose FP32 values sit within a guard band of one of
+ * With risk [R][B] given (from mrf_rollout_risk_dev_f32), scenarios that have a candidate pair at all (states, time gate,
+ * hands closer than the threshold plus the band) and whose FP32 values sit within a guard band of one of
  * those tests (the band widens with the stiffness indicator, see mrf_set_guard) or that are
  * non-finite are RE-ROLLED BY THE FP64 KERNEL from the same records inside this call, and the heuristic reads the FP64
  * values for them -- the flags then equal those of a float64 evaluation of the same inputs.  mrf_set_guard() tunes the
  * bands; mrf_guard_stats() reports how many scenarios were re-rolled.  risk == NULL: no re-roll (plain FP32 decision).
- * FP64: risk is ignored (nothing to guard). */
+ * FP64: risk is ignored (nothing to guard).
+ * slot (0..MRF_GUARD_SLOTS-1) selects the scratch the re-roll uses: post steps that may run concurrently (different
+ * streams) must use different slots; calls on one stream can share one.  out[2] of mrf_guard_stats refers to slot 0. */
 int mrf_rfcv_post_dev_f32(mrf_handle_t h, const float* rec, int N, const float* x_ee, float* rec_work, const float* goal_est,
                           const float* avg_vel, const float* risk, const int32_t* sm_state, const int32_t* time_step,
                           int32_t* time_deadlock_out, int32_t* st_int, float* st_goal, int32_t* flag, float* result,
-                          int64_t B, void* stream);
+                          int64_t B, void* stream, int slot);
 int mrf_rfcv_post_dev_f64(mrf_handle_t h, const double* rec, int N, const double* x_ee, double* rec_work,
                           const double* goal_est, const double* avg_vel, const double* risk, const int32_t* sm_state,
                           const int32_t* time_step, int32_t* time_deadlock_out, int32_t* st_int, double* st_goal,
-                          int32_t* flag, double* result, int64_t B, void* stream);
+                          int32_t* flag, double* result, int64_t B, void* stream, int slot);
 /* mrf_rollout_dev without trajectories plus risk [R][B]: per robot the maximum over the horizon of the summed
  * collision-leaf metric (sphere leaf 0.02 w / (x^4 rho^2), plane leaf 0.2 s / x^2) -- large near contact, where the
  * explicit dt integration amplifies FP32 rounding.  Always the throughput kernel (no cooperative small-batch path). */

@@ -211,10 +211,11 @@ class Fabrics:
         return avg_vel
 
     def rfcv_post_dev(self, rec, N: int, x_ee, rec_work, goal_est, avg_vel, sm_state, time_step, time_deadlock_out, st_int,
-                      st_goal, risk=None, flag=None, result=None):
+                      st_goal, risk=None, flag=None, result=None, slot: int = 0):
         """Post step of an RF-CV sweep (mrf_rfcv_post_dev): deadlock heuristic in place on rec_work, per-scenario results
         into result (R+1,B); FP32 with `risk`: guard-band / stiff scenarios are re-rolled in FP64 first so that the flags
-        equal a float64 evaluation of the same records."""
+        equal a float64 evaluation of the same records.  Post steps that may run concurrently (different streams) need
+        different scratch slots (0..3)."""
         import torch
         p = self._prec(rec)
         _, R, B = rec.shape
@@ -237,7 +238,7 @@ class Fabrics:
         fn = getattr(lib(), f"mrf_rfcv_post_dev_{p}")
         check(fn(self.handle.ptr, self._tp(rec), N, self._tp(x_ee), self._tp(rec_work), self._tp(goal_est),
                  self._tp(avg_vel), self._tp(risk), self._tp(sm_state), self._tp(time_step), self._tp(time_deadlock_out),
-                 self._tp(st_int), self._tp(st_goal), self._tp(flag), self._tp(result), B, self._stream()),
+                 self._tp(st_int), self._tp(st_goal), self._tp(flag), self._tp(result), B, self._stream(), int(slot)),
               "mrf_rfcv_post_dev")
         return flag
 

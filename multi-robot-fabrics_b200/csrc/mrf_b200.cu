@@ -49,24 +49,34 @@ namespace mrf {
 // tiles with the horizons of earlier ones.  Tiles are handed out by an atomic ticket and admitted to the bus in ticket
 // order, `window` tiles at a time (sync[0] = tickets, sync[1] = tiles loaded): without that every CTA of a wave would
 // share the bus, all would start -- and later finish -- together, and each wave would stall for its whole transfer.
-template <typename T, int R, bool UNIFORM, bool AOS>
+template <typename T, int R, bool UNIFORM, bool AOS, bool STRIDE = false>
 __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : MRF_ROLLOUT_MINBLOCKS_F64)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
                    unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail,
-                   T* __restrict__ risk, const unsigned* __restrict__ n_live) {
+                   T* __restrict__ risk, unsigned* __restrict__ n_live, const float* __restrict__ rec_f32,
+                   const int* __restrict__ list, long long B_src) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // n_live (device memory, optional; SoA layout only): only the first *n_live of the B columns hold scenarios -- the
-    // grid was sized on the host for a capacity, the count was produced on the device (FP64 re-roll of the guard band)
-    const long long Bn = (!AOS && n_live != nullptr) ? ((long long)*n_live < B ? (long long)*n_live : B) : B;
-    if (!AOS && (long long)blockIdx.x * kTile >= Bn) return;
+    // STRIDE (FP64 re-roll of the guard band): the scenarios are the first min(*n_live, B) entries of `list` -- produced
+    // on the device by guard_select_kernel -- read from the FP32 records rec_f32 [44][R][B_src] (exact promotion); results
+    // go to compact arrays of stride B.  The grid is a handful of CTAs that stride over the tiles, so only a few
+    // (register-heavy) CTAs have to find room next to the FP32 sweep.  Ordinary launches: one CTA per tile, no loop.
+    const long long Bn = STRIDE ? ((long long)*n_live < B ? (long long)*n_live : B) : B;
+    if (STRIDE && blockIdx.x == 0 && threadIdx.x == 0) { // guard statistics: [1] listed by this call, [2] re-rolled, [3] overflow
+        n_live[1] = n_live[0];
+        n_live[2] += (unsigned)Bn;
+        n_live[3] += n_live[0] - (unsigned)Bn;
+    }
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
+    unsigned tile_first = blockIdx.x;
+    if (STRIDE && (long long)tile_first * kTile >= Bn) return;
+  do {
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
     // (a double-buffered point table with one barrier per step was measured 2 % slower: more shared memory per CTA
     //  and non-immediate offsets; the barrier stall is load imbalance between the robots' warps, not barrier count)
     T* kin = reinterpret_cast<T*>(smem_raw);
     T* prm = kin + kKinRows<T> * NT;
-    unsigned tile = blockIdx.x;
+    unsigned tile = tile_first;
     if (AOS) {
         unsigned* tk = reinterpret_cast<unsigned*>(prm);
         if (tid == 0) {
@@ -101,7 +111,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         ld_stride = 1;
         tail += r * MRF_REC;
     }
-    auto ld = [&](int f) { return AOS ? (f < n_var ? ld_base[f] : tail[f]) : rec[((long long)f * R + r) * B + bb]; };
+    const long long b_src = STRIDE ? (long long)list[bb] : 0;
+    auto ld = [&](int f) {
+        if (STRIDE) return (T)rec_f32[((long long)f * R + r) * B_src + b_src];
+        return AOS ? (f < n_var ? ld_base[f] : tail[f]) : rec[((long long)f * R + r) * B + bb];
+    };
     (void)ld_stride;
 
     T q[kDof], qd[kDof];
@@ -187,6 +201,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     if (avg_vel != nullptr && live) avg_vel[AOS ? b * R + r : (long long)r * B + b] = acc / (T(N) * T(kDof));
     // stiffness indicator (maximum over the horizon of fabric_action's sum of leaf metrics), see mrf_rfcv_post_dev_f32
     if (risk != nullptr && live) risk[AOS ? b * R + r : (long long)r * B + b] = prm[P_RISK * NT + tid];
+    if (STRIDE) {
+        __syncthreads(); // the next tile of this CTA overwrites the tables
+        tile_first += gridDim.x;
+    }
+  } while (STRIDE && (long long)tile_first * kTile < Bn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,6 +347,7 @@ struct DlOverride {
     const double* x_ee;
     const double* goal_est;
     long long cap;
+    unsigned* counters; // the list counter is reset once its consumers are done
 };
 
 template <typename T>
@@ -337,8 +357,10 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
                                 const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
                                 T* __restrict__ st_goal, int* __restrict__ flag, const T* __restrict__ goal_est,
                                 long long B, DlOverride ov, T* __restrict__ result) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    // grid-stride over the scenarios: a few fat CTAs instead of B / 128 thin ones -- next to a sweep whose rollout kernels
+    // fill every SM's register file, each CTA of a small kernel delays one rollout CTA slot at a wave boundary
+    if (ov.counters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ov.counters[0] = 0; // list consumed (same stream order)
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
     const int R = c.R;
     const int os = ov.slot != nullptr ? ov.slot[b] : -1; // >= 0: this scenario was re-rolled in FP64
     if (c.est_robot >= 0 && goal_est != nullptr) // goal_pandas[1] = estimate (example_pandas_Jointspace.py:346-348)
@@ -431,6 +453,7 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
     for (int k = 0; k < 3; ++k) st_goal[k * B + b] = (T)g0[k];
     if (flag) flag[b] = fl;
     if (result) result[(long long)R * B + b] = (T)fl; // what a sweep gathers per scenario: avg_vel[R] and the flag
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -452,16 +475,18 @@ struct GuardCfg {
 template <typename T>
 __global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, const T* __restrict__ x_ee,
                                     const T* __restrict__ rec, const T* __restrict__ goal_est, const T* __restrict__ risk,
-                                    int* __restrict__ slot_of, unsigned* __restrict__ counters, int* __restrict__ list,
-                                    long long B) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+                                    const int* __restrict__ sm_state, const int* __restrict__ time_step, int time_gate,
+                                    double dist_constant, int* __restrict__ slot_of, unsigned* __restrict__ counters,
+                                    int* __restrict__ list, long long B) {
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
     const int R = c.R;
     const long long RB = (long long)R * B;
     double s = 0.0, rk = 0.0, x[MRF_MAX_ROBOTS][3], dg[MRF_MAX_ROBOTS];
+    int st[MRF_MAX_ROBOTS];
     for (int i = 0; i < R; ++i) {
         s += (double)avg_vel[(long long)i * B + b];
         if (risk) rk = fmax(rk, (double)risk[(long long)i * B + b]);
+        st[i] = sm_state[(long long)i * B + b];
         double d2 = 0.0;
         for (int k = 0; k < 3; ++k) {
             x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
@@ -472,25 +497,35 @@ __global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, c
         dg[i] = sqrt(d2);
     }
     s /= (double)R;
-    const double da = fabs(s - c.c_avg);
-    bool guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk); // non-finite FP32 rollout
-    const double band = c.band[(rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0)];
-    guard = guard || da <= band;
-    // geometric knife edges only matter when the velocity test can pass
-    if (!guard && s < c.c_avg + band) {
-        double de[MRF_MAX_ROBOTS * (MRF_MAX_ROBOTS - 1) / 2];
-        int np = 0;
+    // Only a scenario with a candidate pair -- both robots in state 0 / 1, hands closer than the distance threshold (plus
+    // the band), goal distances above the constant, time gate open (deadlock_prevention.py:61-66) -- can raise the flag at
+    // all; for every other scenario the velocity test is never consulted and nothing needs FP64.
+    bool cand = false, knife = false;
+    double de[MRF_MAX_ROBOTS * (MRF_MAX_ROBOTS - 1) / 2];
+    int np = 0;
+    if (time_step[b] > time_gate) {
         for (int a = 0; a < R; ++a)
             for (int q = a + 1; q < R; ++q) {
+                if (!((st[a] == 0 || st[a] == 1) && (st[q] == 0 || st[q] == 1))) continue;
                 const double d = sqrt((x[a][0] - x[q][0]) * (x[a][0] - x[q][0]) + (x[a][1] - x[q][1]) * (x[a][1] - x[q][1]) +
                                       (x[a][2] - x[q][2]) * (x[a][2] - x[q][2]));
-                guard = guard || fabs(d - c.c_dist) <= c.band_dist;                 // :64
-                if (d < c.c_dist + c.band_dist) {
-                    guard = guard || fabs(dg[a] - dg[q]) <= c.band_dist;            // :85 leader choice
-                    for (int e = 0; e < np; ++e) guard = guard || fabs(de[e] - d) <= c.band_dist; // :76 closest pair
+                if (!(d >= c.c_dist + c.band_dist) && !(dg[a] + dg[q] <= dist_constant - c.band_dist)) { // NaN counts as candidate
+                    cand = true;
+                    knife = knife || fabs(d - c.c_dist) <= c.band_dist;                           // :64 distance test
+                    knife = knife || fabs(dg[a] + dg[q] - dist_constant) <= c.band_dist;          // :61 goal-distance test
+                    knife = knife || fabs(dg[a] - dg[q]) <= c.band_dist;                          // :85 leader choice
+                    for (int e = 0; e < np; ++e) knife = knife || fabs(de[e] - d) <= c.band_dist; // :76 closest pair
                     de[np++] = d;
                 }
             }
+    }
+    bool guard = false;
+    if (cand) {
+        const double da = fabs(s - c.c_avg);
+        const double band = c.band[(rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0)];
+        guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk);   // non-finite FP32 rollout
+        guard = guard || da <= band;                                   // velocity knife edge, widened by stiffness tier
+        guard = guard || (knife && s < c.c_avg + band);                // geometric knife edges matter if the velocity test can pass
     }
     int slot = -1;
     if (guard) {
@@ -501,24 +536,7 @@ __global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, c
         }
     }
     slot_of[b] = slot;
-}
-// compact FP64 records [44][R][cap] of the listed scenarios from the FP32 records [44][R][B] (exact promotion)
-template <typename T>
-__global__ void guard_gather_kernel(const T* __restrict__ rec, double* __restrict__ rec64, const int* __restrict__ list,
-                                    unsigned* __restrict__ counters, int R, long long B, unsigned cap) {
-    const unsigned n = counters[0] < cap ? counters[0] : cap;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx == 0) {
-        counters[2] += n;
-        counters[3] += counters[0] - n;
-    }
-    if (idx >= (long long)R * cap) return;
-    const int r = (int)(idx / cap);
-    const unsigned slot = (unsigned)(idx - (long long)r * cap);
-    if (slot >= n) return;
-    const long long b = list[slot];
-#pragma unroll 4
-    for (int f = 0; f < MRF_REC; ++f) rec64[((long long)f * R + r) * cap + slot] = (double)rec[((long long)f * R + r) * B + b];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -890,8 +908,9 @@ struct MrfHandle_ {
     // FP64 re-roll of guard-band scenarios (mrf_rfcv_post_dev_f32)
     double guard_band[3], guard_edge[2], guard_band_dist;
     long long guard_cap;      // 0 = max(256, B / 16)
-    void* guard_buf;          // counters, list, slot_of, compact FP64 records and results
-    size_t guard_bytes;
+    long long guard_coop_max; // capacities up to this re-roll with the cooperative kernel
+    void* guard_buf[MRF_GUARD_SLOTS];   // per scratch slot: list, slot_of, compact FP64 records and results
+    size_t guard_bytes[MRF_GUARD_SLOTS];
 };
 
 extern "C" int mrf_version(void) { return 100; }
@@ -947,8 +966,8 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
 
 static int create_resources(MrfHandle_* h) {
     for (int i = 0; i < 2; ++i) MRF_CUDA(cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC));
-    MRF_CUDA(cudaMalloc(&h->d_sync, 12 * sizeof(unsigned))); // [0..5] ticket pairs, [8..11] guard counters
-    MRF_CUDA(cudaMemset(h->d_sync, 0, 12 * sizeof(unsigned)));
+    MRF_CUDA(cudaMalloc(&h->d_sync, (8 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned))); // [0..5] ticket pairs, [8..] guard counters
+    MRF_CUDA(cudaMemset(h->d_sync, 0, (8 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     MRF_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     MRF_CUDA(cudaEventCreate(&h->ev0));
@@ -1009,8 +1028,12 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->guard_edge[1] = 200.0;
     h->guard_band_dist = 1e-5;
     h->guard_cap = 0;
-    h->guard_buf = nullptr;
-    h->guard_bytes = 0;
+    h->guard_coop_max = 512;
+    if (const char* e = getenv("MRF_GUARD_COOP_MAX")) h->guard_coop_max = atoll(e);
+    for (int i = 0; i < MRF_GUARD_SLOTS; ++i) {
+        h->guard_buf[i] = nullptr;
+        h->guard_bytes[i] = 0;
+    }
     fill_devcfg(*cfg, h->c32);
     fill_devcfg(*cfg, h->c64);
     // every failure below releases what was created so far (the handle is value-initialised: null streams / events /
@@ -1031,7 +1054,8 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_sync) cudaFree(h->d_sync);
-    if (h->guard_buf) cudaFree(h->guard_buf);
+    for (int i = 0; i < MRF_GUARD_SLOTS; ++i)
+        if (h->guard_buf[i]) cudaFree(h->guard_buf[i]);
     for (int i = 0; i < 2; ++i)
         if (h->d_tail[i]) cudaFree(h->d_tail[i]);
     // a partially created handle (mrf_create failure path) holds null streams / events: skip them
@@ -1072,8 +1096,9 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
                        void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr,
-                       T* risk = nullptr, const unsigned* n_live = nullptr) {
-    if (!h || !rec) return fail(MRF_EINVAL, "mrf_rollout: null argument");
+                       T* risk = nullptr, unsigned* n_live = nullptr, const float* rec_f32 = nullptr,
+                       const int* list = nullptr, long long B_src = 0) {
+    if (!h || (!rec && !n_live)) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
         return fail(MRF_EUNSUPPORTED, "mrf_rollout: the joint-space rollout is defined for mode 'vel' only "
@@ -1081,13 +1106,12 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
     if (aos && (qN || qdN)) return fail(MRF_EINVAL, "mrf_rollout: record-order input has no trajectory output");
-    if (!aos && R >= 2 && B <= h->coop_max_batch && !risk) {
-        // (n_live: see rollout_kernel; both kernels take it)
+    if (!aos && R >= 2 && B <= h->coop_max_batch && !risk && !n_live) {
         // few scenarios: latency matters, not throughput -> one CTA per scenario, one warp per robot (mrf_coop.cuh)
         switch (R) {
-            case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
-            case 3: rollout_coop_kernel<T, 3><<<(unsigned)B, 96, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
-            case 4: rollout_coop_kernel<T, 4><<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, n_live); break;
+            case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            case 3: rollout_coop_kernel<T, 3><<<(unsigned)B, 96, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
+            case 4: rollout_coop_kernel<T, 4><<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
             default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
         }
         MRF_CUDA(cudaGetLastError());
@@ -1095,24 +1119,36 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         return MRF_OK;
     }
     const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * NT;
-    const long long grid = (B + kTile - 1) / kTile;
+    long long grid = (B + kTile - 1) / kTile;
+    if (n_live != nullptr && grid > 16) grid = 16; // device-side count: a few CTAs stride over the tiles (see the kernel)
     int rc = MRF_OK;
-#define MRF_LAUNCH_ROLLOUT_K(RR, UU, AA)                                                                             \
+#define MRF_LAUNCH_ROLLOUT_K(RR, UU, AA, SS)                                                                         \
     {                                                                                                                \
-        rc = set_smem(rollout_kernel<T, RR, UU, AA>, smem);                                                          \
+        rc = set_smem(rollout_kernel<T, RR, UU, AA, SS>, smem);                                                      \
         if (rc) return rc;                                                                                           \
-        rollout_kernel<T, RR, UU, AA><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                           \
+        rollout_kernel<T, RR, UU, AA, SS><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                       \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
-            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live);                                                  \
+            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live, rec_f32, list, B_src);                            \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
         if (devcfg<T>(h).uniform_obst) {                                                                             \
-            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, true, true) else MRF_LAUNCH_ROLLOUT_K(RR, true, false)                 \
+            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, true, true, false)                                                     \
+            else if (stride) MRF_LAUNCH_ROLLOUT_STRIDE(RR, true)                                                     \
+            else MRF_LAUNCH_ROLLOUT_K(RR, true, false, false)                                                        \
         } else {                                                                                                     \
-            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, false, true) else MRF_LAUNCH_ROLLOUT_K(RR, false, false)               \
+            if (aos) MRF_LAUNCH_ROLLOUT_K(RR, false, true, false)                                                    \
+            else if (stride) MRF_LAUNCH_ROLLOUT_STRIDE(RR, false)                                                    \
+            else MRF_LAUNCH_ROLLOUT_K(RR, false, false, false)                                                       \
         }                                                                                                            \
         break;
+    // the strided variant exists for FP64 only (the guard re-roll)
+#define MRF_LAUNCH_ROLLOUT_STRIDE(RR, UU)                                                                            \
+    {                                                                                                                \
+        if constexpr (sizeof(T) == 8) MRF_LAUNCH_ROLLOUT_K(RR, UU, false, true)                                      \
+        else return fail(MRF_EINVAL, "mrf_rollout: device-side count is FP64 only");                                 \
+    }
+    const bool stride = n_live != nullptr;
     if (aos) MRF_CUDA(cudaMemsetAsync(h->d_sync + 2 * sync_slot, 0, 2 * sizeof(unsigned), (cudaStream_t)stream));
     switch (R) {
         MRF_LAUNCH_ROLLOUT(1)
@@ -1121,6 +1157,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         MRF_LAUNCH_ROLLOUT(4)
         default: return fail(MRF_EINVAL, "mrf_rollout: n_robots out of range");
     }
+#undef MRF_LAUNCH_ROLLOUT_STRIDE
 #undef MRF_LAUNCH_ROLLOUT_K
 #undef MRF_LAUNCH_ROLLOUT
     MRF_CUDA(cudaGetLastError());
@@ -1168,7 +1205,7 @@ template <typename T>
 static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, const T* avg_vel, const T* avg_sum,
                         const int32_t* sm_state, const int32_t* time_step, int32_t* tdo, int32_t* st_int, T* st_goal,
                         int32_t* flag, int64_t B, void* stream, bool rec_layout = false, const T* goal_est = nullptr,
-                        DlOverride ov = DlOverride{nullptr, nullptr, nullptr, nullptr, 0}, T* result = nullptr) {
+                        DlOverride ov = DlOverride{nullptr, nullptr, nullptr, nullptr, 0, nullptr}, T* result = nullptr) {
     if (!h || !x_ee || !goals || !weights || !sm_state || !time_step || !tdo || !st_int || !st_goal)
         return fail(MRF_EINVAL, "mrf_deadlock: null argument");
     if (h->cfg.n_robots < 2)
@@ -1185,7 +1222,8 @@ static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, con
             (rec_layout && c.estimate_goal && goal_est && c.estimate_robot < c.n_robots) ? c.estimate_robot : -1,
             c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
             c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
-    deadlock_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    const long long dl_blocks = (B + 255) / 256;
+    deadlock_kernel<T><<<(unsigned)(dl_blocks < 64 ? dl_blocks : 64), 256, 0, (cudaStream_t)stream>>>(
         d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, goal_est, (long long)B,
         ov, result);
     MRF_CUDA(cudaGetLastError());
@@ -1266,66 +1304,61 @@ extern "C" int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float
 }
 
 // ---------------------------------- RF-CV post step: FP64 guard re-roll + deadlock heuristic ----------------------
-static int guard_reserve(mrf_handle_t h, size_t bytes) {
-    if (h->guard_bytes >= bytes) return MRF_OK;
-    if (h->guard_buf) MRF_CUDA(cudaFree(h->guard_buf));
-    h->guard_buf = nullptr;
-    h->guard_bytes = 0;
-    if (cudaMalloc(&h->guard_buf, bytes) != cudaSuccess) {
+static int guard_reserve(mrf_handle_t h, int slot, size_t bytes) {
+    if (h->guard_bytes[slot] >= bytes) return MRF_OK;
+    if (h->guard_buf[slot]) MRF_CUDA(cudaFree(h->guard_buf[slot]));
+    h->guard_buf[slot] = nullptr;
+    h->guard_bytes[slot] = 0;
+    if (cudaMalloc(&h->guard_buf[slot], bytes) != cudaSuccess) {
         cudaGetLastError();
         return fail(MRF_ENOMEM, "mrf_rfcv_post: device allocation failed");
     }
-    h->guard_bytes = bytes;
+    h->guard_bytes[slot] = bytes;
     return MRF_OK;
 }
 
 template <typename T>
 static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* rec_work, const T* goal_est,
                          const T* avg_vel, const T* risk, const int32_t* sm_state, const int32_t* time_step, int32_t* tdo,
-                         int32_t* st_int, T* st_goal, int32_t* flag, T* result, int64_t B, void* stream) {
-    if (!h || !rec || !rec_work || !x_ee || !avg_vel) return fail(MRF_EINVAL, "mrf_rfcv_post: null argument");
+                         int32_t* st_int, T* st_goal, int32_t* flag, T* result, int64_t B, void* stream, int slot) {
+    if (!h || !rec || !rec_work || !x_ee || !avg_vel || !sm_state || !time_step)
+        return fail(MRF_EINVAL, "mrf_rfcv_post: null argument");
+    if (slot < 0 || slot >= MRF_GUARD_SLOTS) return fail(MRF_EINVAL, "mrf_rfcv_post: slot out of range");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rfcv_post: B and N must be positive");
     const int R = h->cfg.n_robots;
     const long long RB = (long long)R * B;
     const bool est = h->cfg.estimate_goal != 0 && goal_est != nullptr;
-    DlOverride ov{nullptr, nullptr, nullptr, nullptr, 0};
+    DlOverride ov{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
     if (sizeof(T) == 4 && risk != nullptr) {
         if (R < 2 || R > 4) return fail(MRF_EINVAL, "mrf_rfcv_post: n_robots must be 2..4");
         MRF_CUDA(cudaSetDevice(h->device));
         cudaStream_t st = (cudaStream_t)stream;
         const long long cap = h->guard_cap > 0 ? h->guard_cap : (B / 16 > 256 ? B / 16 : 256);
         // doubles first (8-byte aligned), then the integer arrays
-        const size_t n64 = (size_t)cap * ((size_t)MRF_REC * R + R + 3 * R + 3);
+        const size_t n64 = (size_t)cap * ((size_t)R + 3 * R + 3);
         const size_t bytes = sizeof(double) * n64 + sizeof(int) * ((size_t)cap + (size_t)B);
-        int rc = guard_reserve(h, bytes);
+        int rc = guard_reserve(h, slot, bytes);
         if (rc) return rc;
-        double* rec64 = (double*)h->guard_buf;
-        double* avg64 = rec64 + (size_t)MRF_REC * R * cap;
+        double* avg64 = (double*)h->guard_buf[slot];
         double* xee64 = avg64 + (size_t)R * cap;
         double* gest64 = xee64 + (size_t)3 * R * cap;
         int* list = (int*)(gest64 + (size_t)3 * cap);
         int* slot_of = list + cap;
-        unsigned* counters = h->d_sync + 8;
-        MRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
+        unsigned* counters = h->d_sync + 8 + 4 * slot; // [0] is zero on entry: reset by the previous call's deadlock kernel
         GuardCfg g{R, est ? h->cfg.estimate_robot : -1, h->cfg.dl_avg_vel_constant, h->cfg.dl_dist_endeff, h->guard_band_dist,
                    {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
-        guard_select_kernel<T><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk,
-                                                                           slot_of, counters, list, (long long)B);
+        const long long sel_blocks = (B + 255) / 256;
+        guard_select_kernel<T><<<(unsigned)(sel_blocks < 64 ? sel_blocks : 64), 256, 0, st>>>(
+            g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk, sm_state, time_step, h->cfg.dl_time_gate,
+            h->cfg.dl_dist_constant, slot_of, counters, list, (long long)B);
         MRF_CUDA(cudaGetLastError());
-        guard_gather_kernel<T><<<(unsigned)(((long long)R * cap + 127) / 128), 128, 0, st>>>(rec, rec64, list, counters, R,
-                                                                                            (long long)B, (unsigned)cap);
-        MRF_CUDA(cudaGetLastError());
-        // FP64 re-roll of the listed scenarios: grid sized for cap, the kernels read the count from device memory.  Small
-        // capacities use the cooperative low-latency kernel, large ones the throughput kernel (32 scenarios per CTA: a few
-        // CTAs that slot into the tail of the sweep's next FP32 launch instead of one 24 K-register CTA per scenario)
-        const long long keep = h->coop_max_batch;
-        h->coop_max_batch = cap <= 512 ? cap : 0;
-        rc = rollout_dev<double>(h, rec64, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
-                                 nullptr, counters);
-        h->coop_max_batch = keep;
+        h->launches += 1;
+        // FP64 re-roll of the listed scenarios by the throughput kernel, straight from the FP32 records through the list;
+        // the kernel reads the count from device memory (grid: a few CTAs striding over the tiles)
+        rc = rollout_dev<double>(h, nullptr, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
+                                 nullptr, counters, (const float*)rec, list, (long long)B);
         if (rc) return rc;
-        h->launches += 2;
-        ov = DlOverride{slot_of, avg64, xee64, gest64, cap};
+        ov = DlOverride{slot_of, avg64, xee64, gest64, cap, counters};
     }
     return deadlock_dev<T>(h, x_ee, rec_work + MRF_G0 * RB, rec_work + MRF_W0 * RB, avg_vel, nullptr, sm_state, time_step, tdo,
                            st_int, st_goal, flag, B, stream, true, goal_est, ov, result);
@@ -1333,17 +1366,18 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
 extern "C" int mrf_rfcv_post_dev_f32(mrf_handle_t h, const float* rec, int N, const float* x_ee, float* rec_work,
                                      const float* goal_est, const float* avg_vel, const float* risk,
                                      const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
-                                     int32_t* st_int, float* st_goal, int32_t* flag, float* result, int64_t B, void* stream) {
+                                     int32_t* st_int, float* st_goal, int32_t* flag, float* result, int64_t B, void* stream,
+                                     int slot) {
     return rfcv_post_dev<float>(h, rec, N, x_ee, rec_work, goal_est, avg_vel, risk, sm_state, time_step, time_deadlock_out,
-                                st_int, st_goal, flag, result, B, stream);
+                                st_int, st_goal, flag, result, B, stream, slot);
 }
 extern "C" int mrf_rfcv_post_dev_f64(mrf_handle_t h, const double* rec, int N, const double* x_ee, double* rec_work,
                                      const double* goal_est, const double* avg_vel, const double* risk,
                                      const int32_t* sm_state, const int32_t* time_step, int32_t* time_deadlock_out,
                                      int32_t* st_int, double* st_goal, int32_t* flag, double* result, int64_t B,
-                                     void* stream) {
+                                     void* stream, int slot) {
     return rfcv_post_dev<double>(h, rec, N, x_ee, rec_work, goal_est, avg_vel, risk, sm_state, time_step, time_deadlock_out,
-                                 st_int, st_goal, flag, result, B, stream);
+                                 st_int, st_goal, flag, result, B, stream, slot);
 }
 extern "C" int mrf_rollout_risk_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
                                         float* risk, int64_t B, void* stream) {
@@ -1369,11 +1403,14 @@ extern "C" int mrf_set_guard(mrf_handle_t h, const double* bands, const double* 
 extern "C" int mrf_guard_stats(mrf_handle_t h, int64_t* out) {
     if (!h || !out) return fail(MRF_EINVAL, "mrf_guard_stats: null argument");
     MRF_CUDA(cudaSetDevice(h->device));
-    unsigned c[4];
+    unsigned c[4 * MRF_GUARD_SLOTS];
     MRF_CUDA(cudaMemcpy(c, h->d_sync + 8, sizeof(c), cudaMemcpyDeviceToHost));
-    out[0] = c[2];
-    out[1] = c[3];
-    out[2] = c[0];
+    out[0] = out[1] = 0;
+    for (int i = 0; i < MRF_GUARD_SLOTS; ++i) {
+        out[0] += c[4 * i + 2];
+        out[1] += c[4 * i + 3];
+    }
+    out[2] = c[1];
     return MRF_OK;
 }
 
