@@ -55,7 +55,7 @@ extern "C" {
 #define MRF_NLINKS 8   /* panda_link1..8, examples/parameters_manipulators.py:25-26 */
 #define MRF_REC 44     /* scalars per robot record */
 #define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
-#define MRF_GUARD_SLOTS 4   /* scratch slots of mrf_rfcv_post_dev (concurrent post steps on different streams) */
+#define MRF_GUARD_SLOTS 4   /* scratch slots of the mrf_rfcv_post_dev_f32 re-roll (concurrent post steps on different streams) */
 #define MRF_MAX_SPHERES_PER_LINK 8   /* n_obst_per_link, examples/configs/panda_config.yaml:8 (reference default 4) */
 
 /* Per-robot record = the numeric arguments of one fabric action / of get_velocity_rollouts

@@ -226,15 +226,26 @@ template <typename T, int ROLL> MRF_HD V3<T> fr_joint(Frame<T>& f, T q, T qd) {
     f.w = f.w + zq;
     return f.n;
 }
+// Point table layout.  FP64: kin[(e * 9 + c) * NT + tid].  FP32: the points are stored in PAIRS (2pp, 2pp + 1) interleaved
+// per thread, kin[(((e >> 1) * 9 + c) * NT + tid) * 2 + (e & 1)], so that a reader fetches component c of two points of
+// another robot with ONE 64-bit shared-memory load straight into the register pair the packed FP32x2 leaf consumes
+// (half the LDS instructions of the leaf loop and no pack moves); a warp's 32 x 8 B are contiguous, conflict-free.
+template <typename T> constexpr bool kPairLayout = sizeof(T) == 4;
+template <typename T> MRF_HD int kin_index(int NT, int tid, int e, int c) {
+    return kPairLayout<T> ? (((e >> 1) * 9 + c) * NT + tid) * 2 + (e & 1) : (e * 9 + c) * NT + tid;
+}
+template <typename T> constexpr int kKinStride = kPairLayout<T> ? 2 : 1; // x NT: distance between components of a point
 template <typename T> MRF_HD void kin_store(T* kin, int NT, int tid, int e, const Frame<T>& f) {
-    T* k = kin + (e * 9) * NT + tid;
-    k[0 * NT] = f.p.x; k[1 * NT] = f.p.y; k[2 * NT] = f.p.z;
-    k[3 * NT] = f.v.x; k[4 * NT] = f.v.y; k[5 * NT] = f.v.z;
-    k[6 * NT] = f.ac.x; k[7 * NT] = f.ac.y; k[8 * NT] = f.ac.z;
+    T* k = kin + kin_index<T>(NT, tid, e, 0);
+    const int s = kKinStride<T> * NT;
+    k[0 * s] = f.p.x; k[1 * s] = f.p.y; k[2 * s] = f.p.z;
+    k[3 * s] = f.v.x; k[4 * s] = f.v.y; k[5 * s] = f.v.z;
+    k[6 * s] = f.ac.x; k[7 * s] = f.ac.y; k[8 * s] = f.ac.z;
 }
 template <typename T> MRF_HD V3<T> kin_load(const T* kin, int NT, int tid, int e, int c) {
-    const T* k = kin + (e * 9 + c) * NT + tid;
-    return V3<T>{k[0], k[NT], k[2 * NT]};
+    const T* k = kin + kin_index<T>(NT, tid, e, c);
+    const int s = kKinStride<T> * NT;
+    return V3<T>{k[0], k[s], k[2 * s]};
 }
 
 template <typename T>
@@ -333,6 +344,17 @@ template <typename T> MRF_HD P2<T> pdot(const V3<P2<T>>& a, const V3<P2<T>>& b) 
     return pfma(a.z, b.z, pfma(a.y, b.y, pmul(a.x, b.x)));
 }
 
+// components c..c+2 of the point pair (2pp, 2pp + 1) of thread `tid`: FP32 one 64-bit load per component
+MRF_HD V3<P2<float>> kin_load_pair(const float* kin, int NT, int tid, int pp, int c) {
+    const float2* k = reinterpret_cast<const float2*>(kin) + (pp * 9 + c) * NT + tid;
+    return V3<P2<float>>{P2<float>{k[0]}, P2<float>{k[NT]}, P2<float>{k[2 * NT]}};
+}
+MRF_HD V3<P2<double>> kin_load_pair(const double* kin, int NT, int tid, int pp, int c) {
+    const double* a = kin + ((2 * pp) * 9 + c) * NT + tid;
+    const double* b = a + 9 * NT;
+    return V3<P2<double>>{pmk(a[0], b[0]), pmk(a[NT], b[NT]), pmk(a[2 * NT], b[2 * NT])};
+}
+
 // ------------------------------------------------------------------------------------------------
 // accumulators
 // ------------------------------------------------------------------------------------------------
@@ -403,9 +425,11 @@ template <typename T> MRF_HD void acc2_zero(PointAcc2<T>& a) {
     a.b = V3<P2<T>>{z, z, z};
     a.num = z;
 }
-template <typename T>
+// cM = 0.02 x multiplicity (d2L/dxdot2 coefficient of the leaf).  IRHO: every leaf of the loop has the same rho, the
+// caller passes irho = 1 / rho (one reciprocal per ego point instead of the combined-reciprocal trick per leaf).
+template <typename T, bool IRHO>
 MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>& cc, const V3<P2<T>>& xo,
-                         const V3<P2<T>>& vo, const V3<P2<T>>& co, T vref, T aref, P2<T> rho, P2<T> wt, T sigma,
+                         const V3<P2<T>>& vo, const V3<P2<T>>& co, T vref, T aref, P2<T> rho, P2<T> irho, P2<T> cM, T sigma,
                          PointAcc2<T>& acc) {
     const P2<T> m1 = psplat(T(-1)), nvref = psplat(-vref);
     V3<P2<T>> d{pfma(xo.x, m1, p.x), pfma(xo.y, m1, p.y), pfma(xo.z, m1, p.z)};
@@ -413,20 +437,27 @@ MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>
     P2<T> n2 = pdot(d, d);
     P2<T> in1 = prsqrt(n2);
     P2<T> n = pmul(n2, in1);
-    P2<T> t = pfma(rho, m1, n);                 // n - rho
-    P2<T> nr = pmul(n, rho);
-    P2<T> u = prcp(pmul(nr, t));
-    P2<T> gs = pmul(u, t);                      // 1/(n rho)
-    P2<T> ix = pmul(pmul(u, nr), rho);          // 1/x
+    P2<T> gs, ix;
+    if (IRHO) {
+        gs = pmul(in1, irho);                   // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
+        ix = prcp(pfma(n, irho, m1));           // 1/x, x = n/rho - 1
+    } else {
+        // one reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) and 1/x
+        P2<T> t = pfma(rho, m1, n);
+        P2<T> nr = pmul(n, rho);
+        P2<T> u = prcp(pmul(nr, t));
+        gs = pmul(u, t);
+        ix = pmul(pmul(u, nr), rho);
+    }
     P2<T> dw = pdot(d, w), dc = pdot(d, cc), da = pdot(d, co), dv = pdot(d, v), ww = pdot(w, w);
-    P2<T> in2 = pmul(in1, in1);
-    P2<T> inner = padd(pfma(pmul(pmul(dw, dw), m1), in2, ww), dc);   // (kappa + g.c)/gs
+    P2<T> q = pmul(dw, in1);                                      // component of w along d
+    P2<T> inner = padd(pfma(pmul(q, m1), q, ww), dc);             // (kappa + g.c)/gs = |w|^2 - q^2 + d.c
     P2<T> xd = pmul(dw, gs);
     P2<T> ix2 = pmul(ix, ix), ix4 = pmul(ix2, ix2);
-    P2<T> hx = pmul(pmul(xd, xd), ix4);
-    P2<T> Ml = pmul(pmul(psplat(T(0.02)), wt), ix4);
-    P2<T> fl = pmul(Ml, pmul(psplat(T(-0.5)), hx));
-    P2<T> fel = pmul(pmul(psplat(T(-0.04)), wt), pmul(hx, ix));
+    P2<T> Ml = pmul(cM, ix4);                                     // d2L/dxdot2 = 0.02 w / x^4
+    P2<T> u1 = pmul(Ml, pmul(xd, xd));
+    P2<T> fl = pmul(pmul(u1, ix4), psplat(T(-0.5)));              // M h, h = -0.5 xdot^2 / x^4
+    P2<T> fel = pmul(pmul(u1, ix), psplat(T(-2)));                // Euler-Lagrange force of the leaf energy
     P2<T> Mg = pmul(Ml, gs);
     P2<T> s1 = pfma(psplat(sigma), inner, pmul(psplat(-aref), da));
     P2<T> fq = pfma(Mg, s1, fl);
@@ -650,8 +681,8 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 const P2<T> ro2 = psplat(ro), wo2 = psplat(wo);
 #pragma unroll
                 for (int ps = 0; ps < 3; ++ps)
-                    sphere_leaf2(pp[ps], vv[ps], cp[ps], xo2, vo2, co2, src.vref, src.aref, padd(ro2, rbp[ps]), wo2, sigma,
-                                 om[ps]);
+                    sphere_leaf2<T, false>(pp[ps], vv[ps], cp[ps], xo2, vo2, co2, src.vref, src.aref, padd(ro2, rbp[ps]), ro2,
+                                           pmul(wo2, psplat(T(0.02))), sigma, om[ps]);
             });
         }
 #pragma unroll 1
@@ -692,10 +723,18 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                     // sphere leaves already accumulated above
                 } else if (sizeof(T) == 4) {
                     // FP32: sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2)
-                    src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
-                        sphere_leaf2(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)),
-                                     pmul(wo, psplat(we)), sigma, acc2);
-                    });
+                    const P2<T> cw = psplat(T(0.02) * we);
+                    if constexpr (Src::kUniformRadius) {
+                        const P2<T> irho = psplat(Mth<T>::rcp(src.ro + rb)); // one rho for every leaf of this ego point
+                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
+                            sphere_leaf2<T, true>(p2, v2, c2, xo, vo, co, src.vref, src.aref, ro, irho, pmul(wo, cw), sigma, acc2);
+                        });
+                    } else {
+                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
+                            sphere_leaf2<T, false>(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)), ro,
+                                                   pmul(wo, cw), sigma, acc2);
+                        });
+                    }
                 } else {
                     // FP64: no packed instructions exist and pairing doubles the live registers -> one leaf at a time
                     src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
@@ -835,6 +874,7 @@ constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane e
 // ------------------------------------------------------------------------------------------------
 // other robots of the same scenario, read from the CTA's shared kinematics table (generic: table driven, any radii)
 template <typename T> struct SmemSrc {
+    static constexpr bool kUniformRadius = false;
     static constexpr bool kObstacleMajor = false; // shared-memory points: re-reading per ego point is cheap
     MRF_HD bool collide(bool has) const { return has; }
     const DevCfg<T>& cfg;
@@ -845,9 +885,9 @@ template <typename T> struct SmemSrc {
         const int ne = cfg.ent_n[r];
 #pragma unroll 2
         for (int k = 0; k < ne; ++k) {
-            const T* b = kin + cfg.ent_src[r][k] * 9 * NT + cfg.ent_rob[r][k] * kTile + lane;
-            f(mk(b[0], b[NT], b[2 * NT]), mk(b[3 * NT], b[4 * NT], b[5 * NT]), mk(b[6 * NT], b[7 * NT], b[8 * NT]),
-              cfg.ent_rad[r][k], cfg.ent_w[r][k]);
+            const int t = cfg.ent_rob[r][k] * kTile + lane, e = cfg.ent_src[r][k];
+            f(kin_load(kin, NT, t, e, 0), kin_load(kin, NT, t, e, 3), kin_load(kin, NT, t, e, 6), cfg.ent_rad[r][k],
+              cfg.ent_w[r][k]);
         }
     }
     // pairs of entries; an odd tail is paired with itself at weight 0
@@ -855,11 +895,13 @@ template <typename T> struct SmemSrc {
         const int ne = cfg.ent_n[r];
         for (int k = 0; k < ne; k += 2) {
             const int k1 = k + 1 < ne ? k + 1 : k;
-            const T* a = kin + cfg.ent_src[r][k] * 9 * NT + cfg.ent_rob[r][k] * kTile + lane;
-            const T* b = kin + cfg.ent_src[r][k1] * 9 * NT + cfg.ent_rob[r][k1] * kTile + lane;
-            f(V3<P2<T>>{pmk(a[0], b[0]), pmk(a[NT], b[NT]), pmk(a[2 * NT], b[2 * NT])},
-              V3<P2<T>>{pmk(a[3 * NT], b[3 * NT]), pmk(a[4 * NT], b[4 * NT]), pmk(a[5 * NT], b[5 * NT])},
-              V3<P2<T>>{pmk(a[6 * NT], b[6 * NT]), pmk(a[7 * NT], b[7 * NT]), pmk(a[8 * NT], b[8 * NT])},
+            const int ta = cfg.ent_rob[r][k] * kTile + lane, tb = cfg.ent_rob[r][k1] * kTile + lane;
+            const int ea = cfg.ent_src[r][k], eb = cfg.ent_src[r][k1];
+            const V3<T> xa = kin_load(kin, NT, ta, ea, 0), va = kin_load(kin, NT, ta, ea, 3), ca = kin_load(kin, NT, ta, ea, 6);
+            const V3<T> xb = kin_load(kin, NT, tb, eb, 0), vb = kin_load(kin, NT, tb, eb, 3), cb = kin_load(kin, NT, tb, eb, 6);
+            f(V3<P2<T>>{pmk(xa.x, xb.x), pmk(xa.y, xb.y), pmk(xa.z, xb.z)},
+              V3<P2<T>>{pmk(va.x, vb.x), pmk(va.y, vb.y), pmk(va.z, vb.z)},
+              V3<P2<T>>{pmk(ca.x, cb.x), pmk(ca.y, cb.y), pmk(ca.z, cb.z)},
               pmk(cfg.ent_rad[r][k], cfg.ent_rad[r][k1]), pmk(cfg.ent_w[r][k], k1 == k ? T(0) : cfg.ent_w[r][k1]));
         }
     }
@@ -869,6 +911,7 @@ template <typename T> struct SmemSrc {
 // (parameters_manipulators.py:23,37-43): no table look-ups, the six distinct points of each other robot are unrolled
 // with their multiplicities (link3, link4, link5==6 [x2], link7, link8, link1==2 [x2]) as compile-time constants.
 template <typename T, int R> struct SmemSrcUniform {
+    static constexpr bool kUniformRadius = true;  // every sphere has radius ro: rho = ro + radius_body is per ego point
     static constexpr bool kObstacleMajor = false;
     MRF_HD bool collide(bool has) const { return has; }
     const T* kin;
@@ -881,11 +924,11 @@ template <typename T, int R> struct SmemSrcUniform {
 #pragma unroll 1
         for (int j = 0; j < R; ++j) {
             if (j == r) continue;
-            const T* b = kin + j * kTile + lane;
+            const int t = j * kTile + lane;
 #pragma unroll 2
-            for (int pt = 0; pt < kPts; ++pt, b += 9 * NT) {
-                f(mk(b[0], b[NT], b[2 * NT]), mk(b[3 * NT], b[4 * NT], b[5 * NT]), mk(b[6 * NT], b[7 * NT], b[8 * NT]),
-                  ro, (pt == 2 || pt == 5) ? T(2) : T(1));
+            for (int pt = 0; pt < kPts; ++pt) {
+                f(kin_load(kin, NT, t, pt, 0), kin_load(kin, NT, t, pt, 3), kin_load(kin, NT, t, pt, 6), ro,
+                  (pt == 2 || pt == 5) ? T(2) : T(1));
             }
         }
     }
@@ -896,13 +939,10 @@ template <typename T, int R> struct SmemSrcUniform {
 #pragma unroll 1
         for (int j = 0; j < R; ++j) {
             if (j == r) continue;
-            const T* a = kin + j * kTile + lane;
+            const int t = j * kTile + lane;
 #pragma unroll
-            for (int pp = 0; pp < kPts / 2; ++pp, a += 18 * NT) { // 3 independent packed leaves in flight (ILP)
-                const T* b = a + 9 * NT;
-                f(V3<P2<T>>{pmk(a[0], b[0]), pmk(a[NT], b[NT]), pmk(a[2 * NT], b[2 * NT])},
-                  V3<P2<T>>{pmk(a[3 * NT], b[3 * NT]), pmk(a[4 * NT], b[4 * NT]), pmk(a[5 * NT], b[5 * NT])},
-                  V3<P2<T>>{pmk(a[6 * NT], b[6 * NT]), pmk(a[7 * NT], b[7 * NT]), pmk(a[8 * NT], b[8 * NT])}, ro2,
+            for (int pp = 0; pp < kPts / 2; ++pp) { // 3 independent packed leaves in flight (ILP); 64-bit pair loads
+                f(kin_load_pair(kin, NT, t, pp, 0), kin_load_pair(kin, NT, t, pp, 3), kin_load_pair(kin, NT, t, pp, 6), ro2,
                   pmk(pp == 1 ? T(2) : T(1), pp == 2 ? T(2) : T(1)));
             }
         }
@@ -930,6 +970,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 template <typename T, bool CART> struct GlobalSrc {
+    static constexpr bool kUniformRadius = false;
     static constexpr bool kObstacleMajor = true; // global-memory spheres: load each once (see fabric_action)
     const T* obst;
     long long stride, off;
