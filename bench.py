@@ -283,8 +283,12 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
     sides = [torch.cuda.Stream(device=dev, priority=int(os.environ.get("MRF_BENCH_PRIO", "-1"))) for _ in range(NPOST)]
     mk = lambda *shape, dtype=tdt: [torch.empty(shape, dtype=dtype, device=dev) for _ in range(NBUF)]
     avg, xee, gest, risk = mk(R, B), mk(R, 3, B), mk(3, B), mk(R, B)
-    flag, result = mk(B, dtype=torch.int32), mk(R + 1, B)
-    gathered = mk(world, R + 1, B) if world > 1 else None
+    flag = mk(B, dtype=torch.int32)
+    # per-scenario results (avg_vel[R] + flag) of EVERY timed step stay on the device; for N > 1 they are exchanged by ONE
+    # all_gather after the last step, inside the timed region ("only a final NCCL gather", north star)
+    results = torch.empty((steps, R + 1, B), dtype=tdt, device=dev)
+    scratch = torch.empty((R + 1, B), dtype=tdt, device=dev)
+    gathered = torch.empty((world, steps, R + 1, B), dtype=tdt, device=dev) if world > 1 else None
     # heuristic state per output set (concurrent post steps must not share the in/out state arrays)
     sm_state = [torch.zeros((R, B), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     tstep = torch.full((B,), 100, dtype=torch.int32, device=dev)
@@ -313,10 +317,8 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
         with torch.cuda.stream(side):
             side.wait_event(roll_done[k])
             fab.rfcv_post_dev(recs[s_], H, xee[k], works[s_], gest[k], avg[k], sm_state[k], tstep, tdo[k], st_int[k],
-                              st_goal[k], risk=risk[k] if with_risk else None, flag=flag[k], result=result[k],
-                              slot=k % NPOST)
-            if world > 1:
-                sharding.gather_into(gathered[k], result[k])
+                              st_goal[k], risk=risk[k] if with_risk else None, flag=flag[k],
+                              result=results[i - warmup] if timed else scratch, slot=k % NPOST)
             post_done[k].record(side)
 
     def join():
@@ -344,14 +346,34 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
         step(warmup + i, True)
     host_ms = (time.perf_counter() - h0) * 1e3
     join()
+    if world > 1:
+        sharding.gather_into(gathered, results)          # the sweep's only exchange
     t1.record(main)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     last = (warmup + steps - 1) % NBUF
     return dict(host_enqueue_ms=host_ms, total_ms=t0.elapsed_time(t1), kern_ms=[e0.elapsed_time(e1) for e0, e1 in kev],
-                avg=avg[last], flag=flag[last], result=result[last], last_set=(warmup + steps - 1) % len(recs),
-                gathered=None if gathered is None else gathered[last], rollout_streams=len(roll))
+                avg=avg[last], flag=flag[last], result=results[steps - 1], last_set=(warmup + steps - 1) % len(recs),
+                gathered=gathered, rollout_streams=len(roll))
+
+
+def _isolated_kernel_ms(fab, torch, dev, recs, H, launches, with_risk=True):
+    """The dominant kernel alone: `launches` rollout launches back to back on ONE stream, CUDA events around each
+    (a second timed region over the same rotating record sets; nothing else runs on the GPU)."""
+    _, R, B = recs[0].shape
+    t = lambda *shape: torch.empty(shape, dtype=recs[0].dtype, device=dev)
+    avg, xee, gest, risk = t(R, B), t(R, 3, B), t(3, B), t(R, B)
+    ev = []
+    for i in range(3 + launches):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fab.rollout_dev(recs[i % len(recs)], H, avg_vel=avg, x_ee=xee, goal_est=gest, risk=risk if with_risk else None)
+        e1.record()
+        if i >= 3:
+            ev.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    return statistics.mean(e0.elapsed_time(e1) for e0, e1 in ev)
 
 
 def ours(a):
@@ -406,7 +428,8 @@ def ours(a):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_s = float(total_ms.item()) * 1e-3
     value = world * B * R * H * steps / total_s
-    kernel_ms = statistics.mean(sw["kern_ms"])
+    kernel_ms_overlapped = statistics.mean(sw["kern_ms"])      # per-launch duration while two launches share the GPU
+    kernel_ms = _isolated_kernel_ms(fab, torch, dev, recs, H, steps)
     rerolled, overflow, _ = fab.guard_stats()
     guard = {"fp64_rerolled_per_step": rerolled / (steps + warmup), "overflow": overflow,
              "host_enqueue_ms_per_step": sw["host_enqueue_ms"] / steps}
@@ -439,7 +462,7 @@ def ours(a):
         t64 = torch.tensor([sw64["total_ms"]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t64, op=dist.ReduceOp.MAX)
-        k64 = statistics.mean(sw64["kern_ms"])
+        k64 = _isolated_kernel_ms(fab, torch, dev, recs64, H, s64, with_risk=False)
         tf64 = B * R * H / (k64 * 1e-3) * FLOPS_PER_ROBOT_STEP / 1e12
         f64 = {"value": world * B * R * H * s64 / (float(t64.item()) * 1e-3), "unit": UNIT, "steps": s64,
                "ms_per_step": float(t64.item()) / s64, "kernel": "rollout_kernel<double>", "kernel_ms": k64,
@@ -551,6 +574,11 @@ def ours(a):
         traffic = json.load(open(tfile)).get("rollout_f32_bytes_per_launch")
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": peak32, "unit": "TFLOP/s", "frac": achieved_tf / peak32,
                 "traffic": traffic, "kernel": "rollout_kernel<float>", "kernel_ms": kernel_ms,
+                "kernel_timing": "CUDA events around each of K launches issued back to back on one stream right after the "
+                                 "sweep (the kernel alone, same rotating record sets); inside the sweep two launches overlap "
+                                 "on two streams, so a launch there lasts kernel_ms_overlapped while the sweep completes one "
+                                 "launch every ms_per_step",
+                "kernel_ms_overlapped": kernel_ms_overlapped, "sweep_frac": value / world * FLOPS_PER_ROBOT_STEP / 1e12 / peak32,
                 "flops_per_robot_step": FLOPS_PER_ROBOT_STEP,
                 "peak_source": "FMA micro-benchmark (mrf_fma_peak) measured in this run; MEASURED_PEAKS.json has no "
                                "FP32/FP64 CUDA-core figure",
