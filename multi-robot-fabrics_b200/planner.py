@@ -265,6 +265,33 @@ class ForwardFabricsPlanner:
         return qn, qdn, qddn
 
 
+    def rollouts_numerical_obstacles(self, inputs_action):
+        """-> (x, v, a) dicts keyed 'robot_i': per horizon step k an array (3, 8 (R-1)) with the positions / velocities /
+        accelerations of the OTHER robots' collision-link spheres as robot i sees them in step k (ascending other robot,
+        link1..8) -- the numeric twin of x_obsts_N_fun / v_obsts_N_fun / a_obsts_N_fun
+        (forward_planner_Jointspace.py:234-243,283-290,425-511).  Step k evaluates FK at the stepped position q_k with
+        the stale velocity qdot_{k-1} (:197-209), v = J qdot, a = Jdot qdot with the reference's sign (utils.py:28);
+        STATIC_OR_DYN_FABRICS = 0 zeroes v and a (:215-217)."""
+        R, N = self.nr_robots, self.N_horizon
+        rec = self._records(inputs_action)
+        out = self.fab.rollout_host(rec, N, dtype=self.dtype, trajectories=True)
+        self.last = out
+        q = np.asarray(out["qN"][0], dtype=np.float64)                                  # (R, N, 7): q_k
+        qd_prev = np.concatenate([rec[0, :, None, QD:QD + 7], np.asarray(out["qdN"][0], dtype=np.float64)[:, :-1]], axis=1)
+        x, v, a = self.fab.kinematics_host(np.ascontiguousarray(q.transpose(1, 0, 2)),
+                                           np.ascontiguousarray(qd_prev.transpose(1, 0, 2)))       # (N, R, 8, 3)
+        if not self.fab.cfg.static_or_dyn:
+            v, a = np.zeros_like(v), np.zeros_like(a)
+        xs, vs, as_ = {}, {}, {}
+        for i in range(R):
+            others = [j for j in range(R) if j != i]
+            cat = lambda arr, k: np.concatenate([arr[k, j] for j in others], axis=0).T.copy()       # (3, 8 (R-1))
+            xs[f"robot_{i}"] = [cat(x, k) for k in range(N)]
+            vs[f"robot_{i}"] = [cat(v, k) for k in range(N)]
+            as_[f"robot_{i}"] = [cat(a, k) for k in range(N)]
+        return xs, vs, as_
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class _DM:
     """Minimal stand-in for the casadi DM returned by avg_vel_fun (callers use ``.full()[0]``)."""
@@ -283,6 +310,7 @@ class FabricsRollouts:
                  collision_links_nrs=(7,), nr_constraints=0, radius_sphere=0.08, constraints=None, nr_goals=3,
                  dtype: str = "f64"):
         self.N, self.dt, self.dof = N, dt, dof
+        self.Ts, self.nx, self.nu, self.ring = dt, nx, nu, bool_ring
         self.nr_obsts, self.nr_obsts_dyn = nr_obsts, nr_obsts_dyn
         self.v_obsts_dyn = list(v_obsts_dyn)
         self.a_obsts_dyn = [np.zeros((3,))] * len(self.v_obsts_dyn)
@@ -299,8 +327,116 @@ class FabricsRollouts:
         if fabrics_mode != "vel":
             raise MrfError("the CUDA Cartesian rollout implements fabrics_mode 'vel' (the reference's setting)")
 
+    # ---- environment-dictionary readers (forward_planner_Cartesian.py:49-69,94-130): host glue, same keys ----
+    def preset_radii(self, ob_robot):
+        if self.nr_obsts + self.nr_obsts_dyn > 0:
+            obst = ob_robot["FullSensor"]["obstacles"]
+            first = list(obst.keys())[0]
+            self.radius_obsts = [obst[first + i]["size"] for i in range(self.nr_obsts)]
+            self.radius_obsts_dyn = [obst[first + self.nr_obsts + i]["size"] for i in range(self.nr_obsts_dyn)]
+        else:
+            self.radius_obsts_dyn, self.radius_obsts = [], []
+
+    def get_x_obsts(self, ob_robot) -> list:
+        obst = ob_robot["FullSensor"]["obstacles"]
+        first = list(obst.keys())[0]
+        return [obst[first + i]["position"] for i in range(self.nr_obsts)]
+
+    def get_x_obsts_dyn_current(self, ob_robot) -> list:
+        obst = ob_robot["FullSensor"]["obstacles"]
+        first = list(obst.keys())[0]
+        return [obst[first + self.nr_obsts + i]["position"] for i in range(self.nr_obsts_dyn)]
+
+    def get_goal_x_weight(self, ob_robot, goal):
+        goals = ob_robot["FullSensor"]["goals"]
+        first = list(goals.keys())[0]
+        x_goals = [goals[first + i]["position"] for i in range(self.nr_goals)]
+        weight_goals = [goal.sub_goals()[i].weight() for i in range(self.nr_goals)]
+        return x_goals, weight_goals
+
     def preset_radii_obsts_dyn(self, radii_obst_dyn):
         self.radius_obsts_dyn = radii_obst_dyn
+
+    def system_step(self, pos, vel, input, dt: float, fabrics_mode="vel"):  # noqa: A002 (the reference's argument name)
+        """forward_planner_Cartesian.py:77-92."""
+        pos = np.asarray(pos, dtype=np.float64)
+        inp = np.asarray(input, dtype=np.float64)
+        if fabrics_mode == "acc":
+            vel = np.asarray(vel, dtype=np.float64)
+            return pos + dt * vel + 0.5 * dt ** 2 * inp, vel + dt * inp
+        if fabrics_mode == "vel":
+            return pos + dt * inp, inp
+        print("nonexisting fabrics mode inserted, should be vel or acc")
+        return [], []
+
+    def get_action(self, planner, pos, vel, x_obsts: list, x_obsts_dyn: list, x_goals: list, weight_goals: list):
+        """One planner.compute_action with this rollout object's constants (forward_planner_Cartesian.py:132-191)."""
+        x_goals, weight_goals = list(x_goals), list(weight_goals)
+        for _ in range(3 - self.nr_goals):              # "append some zeros" (:145-149)
+            x_goals.append(0)
+            weight_goals.append(0)
+        return planner.compute_action(
+            q=pos, qdot=vel, angle_goal_1=self.rotation_matrix_panda, x_goal_0=x_goals[0], x_goal_1=x_goals[1],
+            x_goal_2=x_goals[2], weight_goal_0=weight_goals[0], weight_goal_1=weight_goals[1], weight_goal_2=weight_goals[2],
+            x_obsts=x_obsts, radius_obsts=self.radius_obsts, x_obsts_dynamic=x_obsts_dyn, xdot_obsts_dynamic=self.v_obsts_dyn,
+            xddot_obsts_dynamic=[np.array([0.0, 0.0, 0.0])] * self.nr_obsts_dyn, radius_obsts_dynamic=self.radius_obsts_dyn,
+            radius_body_panda_links=self.radius_body_panda_links, radius_body_panda_hand=np.array([0.08]),
+            constraint_0=self.constraints)
+
+    def get_x_obsts_dyn_N(self, x_obsts_dyn):
+        """Constant-velocity obstacle positions along the horizon, both forms of forward_planner_Cartesian.py:195-216:
+        a list of N+1 arrays (3, nr_obsts_dyn) (k = 0..N) and a list of N lists of per-obstacle positions (k = 0..N-1)."""
+        x0 = np.stack(x_obsts_dyn).transpose()
+        v = np.stack(self.v_obsts_dyn).transpose()
+        x_N = [x0]
+        for _ in range(self.N):
+            x_N.append(x_N[-1] + v * self.dt)
+        x_list = [[[] for _ in range(self.nr_obsts_dyn)] for _ in range(self.N)]
+        x_list[0] = np.array(x_obsts_dyn)
+        for i in range(self.N - 1):
+            for o in range(self.nr_obsts_dyn):
+                x_list[i + 1][o] = x_list[i][o] + self.v_obsts_dyn[o] * self.dt
+        return x_N, x_list
+
+    def forward_fabrics(self, planner, pos_k, vel_k, ob_robot, goal, x_obsts_dyn_0=None, x_goals_struct=None,
+                        weight_goals_struct=None):
+        """"The Python rollout loop" (forward_planner_Cartesian.py:218-273): N x (compute_action, system_step) with the
+        obstacles at x0 + k dt v.  Every action comes from the CUDA action kernel through planner.compute_action.
+        -> (q_stacked, qdot_stacked, qddot_stacked) lists over the horizon."""
+        u_k = []
+        q_stacked, qdot_stacked, qddot_stacked = [], [], []
+        for i in range(self.N):
+            x_obsts = self.get_x_obsts(ob_robot) if self.nr_obsts > 0 else []
+            if self.nr_obsts_dyn > 0:
+                x_dyn = self.get_x_obsts_dyn_current(ob_robot) if x_obsts_dyn_0 is None else x_obsts_dyn_0
+                _, x_dyn_list = self.get_x_obsts_dyn_N(x_dyn)
+            else:
+                x_dyn_list = [[] for _ in range(self.N)]
+            if x_goals_struct is None:
+                x_goals, weight_goals = self.get_goal_x_weight(ob_robot, goal)
+            else:
+                x_goals, weight_goals = list(x_goals_struct.values()), list(weight_goals_struct.values())
+            u_k[0:self.dof] = self.get_action(planner, pos_k, vel_k, x_obsts=x_obsts, x_obsts_dyn=x_dyn_list[i],
+                                              x_goals=x_goals, weight_goals=weight_goals)
+            pos_k, vel_k = self.system_step(pos_k, vel_k, u_k[0:self.dof], dt=self.dt, fabrics_mode=self.fabrics_mode)
+            if self.fabrics_mode == "acc":
+                qddot_stacked.append(u_k.copy())
+                qdot_stacked.append(vel_k.copy())
+            else:
+                qdot_stacked.append(u_k.copy())
+            q_stacked.append(pos_k.copy())
+        return q_stacked, qdot_stacked, qddot_stacked
+
+    def x_obsts_dyn_numerical(self, pos_obsts_dyn):
+        """-> list over k = 0..N-1 of arrays (3, nr_obsts_dyn): obstacle positions AFTER step k
+        (x_obsts_dyn_N_fun, forward_planner_Cartesian.py:448-458,471-474,491-505)."""
+        x = np.stack([np.asarray(p, dtype=np.float64).reshape(3) for p in pos_obsts_dyn])
+        v = np.stack([np.asarray(p, dtype=np.float64).reshape(3) for p in self.v_obsts_dyn])
+        out = []
+        for _ in range(self.N):
+            x = x + self.dt * v
+            out.append(x.T.copy())
+        return out
 
     def reset_v_obsts_dyn(self, v_obsts_dyn):
         self.v_obsts_dyn = v_obsts_dyn
@@ -395,10 +531,19 @@ class deadlockprevention:  # noqa: N801 (the reference's class name)
     """deadlock_prevention.py drop-in; the check itself runs in the CUDA deadlock kernel (B = 1)."""
 
     def __init__(self, dof, n_robots, N_horizon, device: int = 0):
-        if dof[0] == 2:
-            raise MrfError("the point-mass constants of deadlock_prevention.py:12-19 are not part of the Panda hot path")
         self.dof, self.n_robots, self.N_horizon = dof, n_robots, N_horizon
-        self.fab = Fabrics(config=default_config(n_robots), device=device)
+        if dof[0] == 2:      # point-mass constants (deadlock_prevention.py:12-19)
+            kw = dict(dl_avg_vel_constant=0.03, dl_dist_constant=1.0, dl_goal_weight_follower=10.0, dl_goal_weight_leader=1.0,
+                      dl_time_wait=50, dl_nr_goal_scale=100.0)
+        else:                # manipulators (:20-27) = the library defaults
+            kw = {}
+        self.avg_vel_constant = kw.get("dl_avg_vel_constant", 0.16)
+        self.dist_constant = kw.get("dl_dist_constant", 0)
+        self.goal_weight_follower = int(kw.get("dl_goal_weight_follower", 2))
+        self.goal_weight_leader = int(kw.get("dl_goal_weight_leader", 3))
+        self.time_wait = kw.get("dl_time_wait", 300)
+        self.nr_goal_scale = int(kw.get("dl_nr_goal_scale", 2))
+        self.fab = Fabrics(config=default_config(n_robots, **kw), device=device)
         self._st_int = np.array([[0, 1, 0, 1]], dtype=np.int32)      # i_leader, i_follower, i_robots_dead (:10-11,33)
         self._st_goal = np.zeros((1, 3))
         self.deadlock = False
@@ -415,9 +560,34 @@ class deadlockprevention:  # noqa: N801 (the reference's class name)
     def goal_robot0(self):
         return self._st_goal[0].copy()
 
+    def compute_velocity_average(self, q_dot_robots_N):
+        """deadlock_prevention.py:36-43 (mean ABSOLUTE joint velocity; unused by the examples, host arithmetic)."""
+        avg_sum = 0
+        for i in range(self.n_robots):
+            for df in range(self.dof[i]):
+                q = np.abs(np.asarray(q_dot_robots_N["robot_" + str(i)][df], dtype=np.float64))
+                avg_sum = avg_sum + q.sum() / (self.N_horizon * self.dof[i])
+        return avg_sum
+
+    def compute_distance_to_goal(self, x_robot, goal_robot):
+        return np.linalg.norm(np.asarray(x_robot) - np.asarray(goal_robot))
+
     def deadlock_checking(self, x_robots, goal_robots, goal_weights, time_step, time_deadlock_out, avg_sum,
                           state_machine_robots=()):
         R = self.n_robots
+        dim = int(np.asarray(x_robots[0]).size)
+        if dim == 2:       # planar point robots: pad z = 0 (norms unchanged bit for bit) and strip it again below
+            pad = lambda seq: [np.append(np.asarray(v, dtype=np.float64).reshape(2), 0.0) for v in seq]
+            g3 = pad(goal_robots)
+            out_g, out_w, tdo = self.deadlock_checking(pad(x_robots), g3, goal_weights, time_step, time_deadlock_out, avg_sum,
+                                                       state_machine_robots)
+            if self.deadlock:
+                # the reference reads goal_robot0[2] (deadlock_prevention.py:99) -- an IndexError for 2-D positions
+                raise IndexError("index 2 is out of bounds for axis 0 with size 2")
+            for i in range(R):
+                if out_g[i][:2].tolist() != np.asarray(goal_robots[i], dtype=np.float64).reshape(2).tolist():
+                    goal_robots[i] = out_g[i][:2].copy()
+            return goal_robots, out_w, tdo
         # the reference indexes state_machine_robots[z[0]] for every pair (deadlock_prevention.py:62): a short list is an
         # IndexError there, and would be an out-of-bounds read in the kernel
         if len(state_machine_robots) != R or len(x_robots) != R or len(goal_robots) != R or len(goal_weights) != R:

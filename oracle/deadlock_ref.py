@@ -14,13 +14,17 @@ import numpy as np
 
 
 class DeadlockOracle:
-    def __init__(self, n_robots: int, dist_endeff: float = 0.35):
+    def __init__(self, n_robots: int, dist_endeff: float = 0.35, point: bool = False):
         self.n = n_robots
         self.dist_endeff = dist_endeff   # :64 (a literal in the reference; a knob here so tests can provoke deadlocks)
-        # deadlock_prevention.py:20-27 (manipulator branch)
-        self.avg_vel_constant, self.dist_constant = 0.16, 0.0
-        self.w_follower, self.w_leader = 2, 3
-        self.time_wait, self.goal_scale = 300, 2
+        if point:   # deadlock_prevention.py:12-19 (dof[0] == 2, point masses)
+            self.avg_vel_constant, self.dist_constant = 0.03, 1
+            self.w_follower, self.w_leader = 10, 1
+            self.time_wait, self.goal_scale = 50, 100
+        else:       # :20-27 (manipulator branch)
+            self.avg_vel_constant, self.dist_constant = 0.16, 0.0
+            self.w_follower, self.w_leader = 2, 3
+            self.time_wait, self.goal_scale = 300, 2
         self.goal_robot0 = np.zeros(3)
         self.combos = list(itertools.combinations(range(n_robots), 2))   # :29-30
         self.i_leader, self.i_follower, self.dead = 0, 1, [0, 1]          # :10-11,33

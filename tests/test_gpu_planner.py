@@ -121,6 +121,87 @@ def test_fabrics_rollouts_cartesian_dropin(built):
         assert abs(fr.get_velocity_rollouts(args).full()[0][0] - ravg) < 1e-9
 
 
+def test_cartesian_python_rollout_loop_and_obstacle_helpers(built):
+    """FabricsRollouts.forward_fabrics ("the Python rollout loop", forward_planner_Cartesian.py:218-273), get_action
+    (:132-191), get_x_obsts_dyn_N (:195-216), x_obsts_dyn_numerical (:491-505) and system_step (:77-92): N actions through
+    the CUDA action kernel reproduce the oracle's decoupled rollout, and the constant-velocity obstacle propagation has the
+    reference's shapes and values."""
+    N, S = 8, 8
+    rng = np.random.default_rng(5)
+    rec = m.scenarios.generate(1, 2, seed=57, weight_goal_1=20.0)
+    obst = random_obstacles(rng, 1, 2, S, rec)
+    ocfg = o2.default_config(2)
+    for robot in (0, 1):
+        pl, goal = P.set_planner_panda(7, 0, S, LINKS, {}, MOUNT, robot)
+        r, o = rec[0, robot], obst[0, robot]
+        fr = P.FabricsRollouts(N=N, dt=0.01, nx=7, nu=7, dof=7, nr_obsts=0, bool_ring=False, nr_obsts_dyn=S,
+                               v_obsts_dyn=[o[i, 3:6] for i in range(S)], fabrics_mode="vel", collision_links_nrs=LINKS,
+                               nr_constraints=1, constraints=np.array([0, 0, 1, -0.65]), nr_goals=3)
+        fr.preset_radii_obsts_dyn([0.08] * S)
+        fr.symbolic_forward_fabrics(pl, goal)
+        x0 = [o[i, 0:3] for i in range(S)]
+        x_goals = {"subgoal0": r[14:17], "subgoal1": np.array([0.107, 0, 0]), "subgoal2": np.array([np.pi / 4])}
+        w_goals = {"subgoal0": r[17], "subgoal1": 20.0, "subgoal2": 1.0}
+        q_st, qd_st, qdd_st = fr.forward_fabrics(planner=pl, pos_k=r[0:7], vel_k=r[7:14], ob_robot={}, goal=goal,
+                                                 x_obsts_dyn_0=x0, x_goals_struct=x_goals, weight_goals_struct=w_goals)
+        rq, rqd, _ = o2.rollout_cartesian(ocfg, robot, r, o[:, 0:3], o[:, 3:6], o[:, 9], N)
+        assert len(q_st) == N and len(qd_st) == N and qdd_st == []
+        assert np.abs(np.array(q_st) - rq).max() < 1e-9 and np.abs(np.array(qd_st) - rqd).max() < 1e-9
+        # one action, and the symbolic twin of the same horizon
+        a0 = fr.get_action(pl, r[0:7], r[7:14], x_obsts=[], x_obsts_dyn=x0, x_goals=list(x_goals.values()),
+                           weight_goals=list(w_goals.values()))
+        assert np.abs(a0 - rqd[0]).max() < 1e-9
+        args = fr.define_arguments_numerical(q_robot=r[0:7], q_dot_robot=r[7:14], weight_goals=w_goals, x_goals=x_goals,
+                                             x_obsts=[], x_obsts_dyn=x0, v_obsts_dyn=fr.v_obsts_dyn,
+                                             constraints=np.array([0, 0, 1, -0.65]))
+        q_n, _, _ = fr.rollouts_numerical(args)
+        assert np.abs(q_n - np.array(q_st).T).max() < 1e-9
+        # constant-velocity obstacle propagation
+        x_N, x_list = fr.get_x_obsts_dyn_N(x0)
+        assert len(x_N) == N + 1 and x_N[0].shape == (3, S) and len(x_list) == N
+        for k in range(N):
+            assert np.abs(x_N[k] - (o[:, 0:3] + k * 0.01 * o[:, 3:6]).T).max() < 1e-15
+            assert np.abs(np.array(list(x_list[k])) - (o[:, 0:3] + k * 0.01 * o[:, 3:6])).max() < 1e-15
+        xs = fr.x_obsts_dyn_numerical(x0)
+        assert len(xs) == N and xs[0].shape == (3, S)
+        assert np.abs(xs[N - 1] - (o[:, 0:3] + N * 0.01 * o[:, 3:6]).T).max() < 1e-15
+        p1, v1 = fr.system_step(r[0:7], r[7:14], a0, dt=0.01, fabrics_mode="vel")
+        assert np.array_equal(p1, r[0:7] + 0.01 * a0) and np.array_equal(v1, a0)
+
+
+def test_jointspace_rollouts_numerical_obstacles(built):
+    """ForwardFabricsPlanner.rollouts_numerical_obstacles (forward_planner_Jointspace.py:425-511): the other robots'
+    sphere positions / velocities / accelerations along the horizon, against FK of the oracle's trajectories."""
+    R, N = 3, 6
+    rec = m.scenarios.generate(1, R, seed=58)
+    params = types.SimpleNamespace(N_HORIZON=N, dt=0.01, dof=[7] * R, nr_obsts=[0] * R, fabrics_mode="vel",
+                                   r_robots=[[0.08] * 8] * R, rotation_matrix_pandas=[P.ROT_PANDA] * R,
+                                   collision_links_nrs=[LINKS] * R, STATIC_OR_DYN_FABRICS=1)
+    mounts = {"mount_positions": [np.array([0.0, 0.0, 0.65]), np.array([1.0, 0.0, 0.65]), np.array([0.7, 0.6, 0.65])]}
+    planners = [P.set_planner_panda(7, 0, 8 * (R - 1), LINKS, {}, mounts, i)[0] for i in range(R)]
+    fwd = P.ForwardFabricsPlanner(params, planners, N_steps=N)
+    ia = {"q_robots": [rec[0, i, 0:7] for i in range(R)], "q_dot_robots": [rec[0, i, 7:14] for i in range(R)],
+          "x_obsts": [[] for _ in range(R)], "x_goals0": [rec[0, i, 14:17] for i in range(R)],
+          "x_goals1": [rec[0, i, 18:21] for i in range(R)], "x_goals2": [rec[0, i, 22:23] for i in range(R)],
+          "weight_goals0": [rec[0, i, 17] for i in range(R)], "weight_goals1": [rec[0, i, 21] for i in range(R)],
+          "weight_goals2": [rec[0, i, 23] for i in range(R)], "constraints": [rec[0, i, 33:37] for i in range(R)]}
+    xs, vs, as_ = fwd.rollouts_numerical_obstacles(ia)
+    ocfg = o2.default_config(R)
+    qN, qdN, _, _ = o2.rollout_jointspace(ocfg, rec[0], N)
+    for i in range(R):
+        others = [j for j in range(R) if j != i]
+        assert len(xs[f"robot_{i}"]) == N and xs[f"robot_{i}"][0].shape == (3, 8 * (R - 1))
+        for k in range(N):
+            ex, ev, ea = [], [], []
+            for j in others:
+                qd_prev = rec[0, j, 7:14] if k == 0 else qdN[j, k - 1]
+                x, v, c, _ = o2.kinematics(ocfg, j, qN[j, k], qd_prev)
+                ex.append(x); ev.append(v); ea.append(ocfg.jdot_ref_sign * c)
+            assert np.abs(xs[f"robot_{i}"][k] - np.concatenate(ex).T).max() < 1e-9
+            assert np.abs(vs[f"robot_{i}"][k] - np.concatenate(ev).T).max() < 1e-9
+            assert np.abs(as_[f"robot_{i}"][k] - np.concatenate(ea).T).max() < 1e-8
+
+
 def test_deadlock_dropin_matches_reference_golden(built):
     """The CUDA deadlock kernel behind the reference's class interface replays the reference's own outputs bit for bit
     (goals, weights, time_deadlock_out) -- 'deadlock flags identical'."""
@@ -145,6 +226,39 @@ def test_deadlock_dropin_matches_reference_golden(built):
             assert tdo == g[p + "tdo_out"][t]
             assert go is goals and wo is weights            # mutated in place like the reference
     assert raised > 50
+
+
+def test_deadlock_dropin_point_mass_branch(built):
+    """deadlockprevention with dof[0] == 2 (deadlock_prevention.py:12-19): the kernel with the point-mass constants
+    replays sequences produced by the reference's own class bit for bit; planar (2-D) positions behave like the
+    reference too: they work until a deadlock fires, then the reference's goal_robot0[2] access raises IndexError."""
+    g = np.load(os.path.join(GOLD, "deadlock_point_golden.npz"))
+    raised = 0
+    for c in range(int(g["n_cases"])):
+        p = f"c{c}_"
+        R = int(g[p + "R"])
+        dl = P.deadlockprevention([2] * R, R, 20)
+        assert (dl.avg_vel_constant, dl.dist_constant, dl.goal_weight_follower, dl.goal_weight_leader, dl.time_wait,
+                dl.nr_goal_scale) == (0.03, 1.0, 10, 1, 50, 100)
+        tdo = 1000
+        for t in range(len(g[p + "x"])):
+            goals = [v.copy() for v in g[p + "goals"][t]]
+            weights = [float(w) for w in g[p + "weights"][t]]
+            go, wo, tdo = dl.deadlock_checking([v.copy() for v in g[p + "x"][t]], goals, weights, int(g[p + "time_step"][t]),
+                                               tdo, float(g[p + "avg"][t]), list(g[p + "states"][t]))
+            raised += int(dl.deadlock)
+            assert np.array_equal(np.array(go), g[p + "goals_out"][t]), (c, t)
+            assert np.array_equal(np.array(wo, dtype=float), g[p + "weights_out"][t]), (c, t)
+            assert tdo == g[p + "tdo_out"][t]
+    assert raised > 50
+    dl = P.deadlockprevention([2, 2], 2, 20)
+    x2 = [np.array([0.0, 0.0]), np.array([0.1, 0.0])]
+    go, wo, tdo = dl.deadlock_checking(x2, [np.array([2.0, 0.0]), np.array([-2.0, 0.0])], [1.0, 1.0], 5, 1000, 0.01, [0, 0])
+    assert tdo == 1000 and np.asarray(go[0]).shape == (2,)                       # time gate closed: nothing happens
+    with pytest.raises(IndexError):
+        dl.deadlock_checking(x2, [np.array([2.0, 0.0]), np.array([-2.0, 0.0])], [1.0, 1.0], 50, 1000, 0.01, [0, 0])
+    with pytest.raises(IndexError):
+        dl.deadlock_checking(x2, [np.array([2.0, 0.0])], [1.0, 1.0], 50, 1000, 0.01, [0, 0])   # short list
 
 
 def test_batched_deadlock_from_rollout_flags_identical(built):

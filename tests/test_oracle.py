@@ -126,6 +126,24 @@ def test_deadlock_restatement_matches_reference_golden():
     assert raised > 50
 
 
+def test_deadlock_restatement_point_mass_branch_matches_reference_golden():
+    """dof[0] == 2 constants (deadlock_prevention.py:12-19), sequences produced by the reference's own class."""
+    g = np.load(os.path.join(GOLD, "deadlock_point_golden.npz"))
+    raised = 0
+    for c in range(int(g["n_cases"])):
+        p = f"c{c}_"
+        dl = DeadlockOracle(int(g[p + "R"]), point=True)
+        tdo = 1000
+        for t in range(len(g[p + "x"])):
+            go, wo, tdo, flag = dl.step(g[p + "x"][t], g[p + "goals"][t], g[p + "weights"][t], int(g[p + "time_step"][t]),
+                                        tdo, float(g[p + "avg"][t]), list(g[p + "states"][t]))
+            raised += int(flag)
+            assert np.array_equal(np.array(go), g[p + "goals_out"][t])
+            assert np.array_equal(np.array(wo, dtype=float), g[p + "weights_out"][t])
+            assert tdo == g[p + "tdo_out"][t]
+    assert raised > 50
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/multi_robot_fabrics/others_planner/deadlock_prevention.py"),
                     reason="reference tree only exists in the build container")
 def test_deadlock_restatement_matches_live_reference():
