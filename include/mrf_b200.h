@@ -56,6 +56,7 @@ extern "C" {
 #define MRF_REC 44     /* scalars per robot record */
 #define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
 #define MRF_GUARD_SLOTS 4   /* scratch slots of the mrf_rfcv_post_dev_f32 re-roll (concurrent post steps on different streams) */
+#define MRF_MAX_STATIC 16   /* static spheres per robot in a coupled rollout (nr_obsts of the rollout planners) */
 #define MRF_MAX_SPHERES_PER_LINK 8   /* n_obst_per_link, examples/configs/panda_config.yaml:8 (reference default 4) */
 
 /* Per-robot record = the numeric arguments of one fabric action / of get_velocity_rollouts
@@ -93,6 +94,10 @@ typedef struct MrfConfig {
     double dl_avg_vel_constant, dl_dist_constant, dl_goal_weight_follower, dl_goal_weight_leader;
     double dl_nr_goal_scale, dl_dist_endeff, dl_backoff;
     int32_t dl_time_wait, dl_time_gate;
+    /* collision_links_nr of set_planner_panda (example_pandas_Jointspace.py:64,91-96,141-166) per robot: bit l-1 set <=>
+     * panda_link l is a collision link.  As ego links only link3..8 carry leaves (link1/2 have a constant fk); as
+     * obstacles of the other robots' rollouts every listed link is a sphere.  Default 0xFF (all eight links). */
+    int32_t collision_link_mask[MRF_MAX_ROBOTS];
 } MrfConfig;
 
 typedef struct MrfHandle_* mrf_handle_t;
@@ -126,6 +131,15 @@ int mrf_rollout_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel,
 
 /* Cartesian (decoupled) rollout of robot `robot`: obstacles move with constant velocity, xddot = 0.
  *   rec [MRF_REC][B]  obst [S][MRF_OBST][B] (xddot ignored)  avg_vel [B]  qN,qdN [N][MRF_DOF][B] */
+/* Coupled rollout whose planners also carry n_static STATIC spheres per robot -- x_obst_i / radius_obst_i of
+ * define_rollout_planners(nr_obst = params.nr_obsts[i]) (example_pandas_Jointspace.py:172-193), the x_obsts /
+ * radius_obsts arguments of get_velocity_rollouts (forward_planner_Jointspace.py:319-322): the same collision leaf with
+ * a sphere at rest.   stat [n_static][4][R][B] = x, y, z, radius of sphere o of robot r; 0 <= n_static <= MRF_MAX_STATIC. */
+int mrf_rollout_static_dev_f64(mrf_handle_t h, const double* rec, int N, int n_static, const double* stat, double* avg_vel,
+                               double* x_ee, double* goal_est, double* qN, double* qdN, int64_t B, void* stream);
+int mrf_rollout_static_dev_f32(mrf_handle_t h, const float* rec, int N, int n_static, const float* stat, float* avg_vel,
+                               float* x_ee, float* goal_est, float* qN, float* qdN, int64_t B, void* stream);
+
 int mrf_rollout_cart_dev_f64(mrf_handle_t h, int robot, const double* rec, int S, const double* obst, int N,
                              double* avg_vel, double* qN, double* qdN, int64_t B, void* stream);
 int mrf_rollout_cart_dev_f32(mrf_handle_t h, int robot, const float* rec, int S, const float* obst, int N,

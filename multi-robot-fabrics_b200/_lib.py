@@ -35,6 +35,7 @@ class MrfConfig(C.Structure):
         ("dl_goal_weight_follower", C.c_double), ("dl_goal_weight_leader", C.c_double),
         ("dl_nr_goal_scale", C.c_double), ("dl_dist_endeff", C.c_double), ("dl_backoff", C.c_double),
         ("dl_time_wait", C.c_int32), ("dl_time_gate", C.c_int32),
+        ("collision_link_mask", C.c_int32 * MAX_ROBOTS),
     ]
 
 
@@ -72,7 +73,7 @@ EXPORTS = [
     "mrf_rollout_host_submit_f64", "mrf_rollout_host_submit_f32", "mrf_rollout_host_wait",
     "mrf_rollout_host_submit_compact_f64", "mrf_rollout_host_submit_compact_f32",
     "mrf_rfcv_post_dev_f32", "mrf_rfcv_post_dev_f64", "mrf_rollout_risk_dev_f32", "mrf_rollout_risk_dev_f64",
-    "mrf_set_guard", "mrf_guard_stats",
+    "mrf_set_guard", "mrf_guard_stats", "mrf_rollout_static_dev_f32", "mrf_rollout_static_dev_f64",
 ]
 
 
@@ -108,6 +109,7 @@ def lib():
         getattr(L, f"mrf_rollout_host_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i64]
         getattr(L, f"mrf_rollout_cart_host_{p}").argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, i64]
         getattr(L, f"mrf_rfcv_post_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32]
+        getattr(L, f"mrf_rollout_static_dev_{p}").argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_rollout_risk_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, vp]
     L.mrf_set_guard.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, i64]
     L.mrf_guard_stats.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -146,6 +148,9 @@ def default_config(n_robots: int, **overrides) -> MrfConfig:
         elif k == "limits":
             for i, (lo, hi) in enumerate(v):
                 cfg.limits[i][0], cfg.limits[i][1] = lo, hi
+        elif k == "collision_links":          # per robot a list of link numbers 1..8 (collision_links_nrs)
+            for r, links in enumerate(v):
+                cfg.collision_link_mask[r] = sum(1 << (int(l) - 1) for l in set(links))
         elif k == "r_robots":
             for r, row in enumerate(v):
                 for l, x in enumerate(row):

@@ -210,6 +210,28 @@ class Fabrics:
                  self._tp(qdN), B, self._stream()), "mrf_rollout_dev")
         return avg_vel
 
+    def rollout_static_dev(self, rec, stat, N: int, avg_vel=None, x_ee=None, goal_est=None, qN=None, qdN=None):
+        """Coupled rollout with static spheres per robot: rec (44,R,B), stat (S,4,R,B) = x, y, z, radius
+        (mrf_rollout_static_dev; forward_planner_Jointspace.py:319-322)."""
+        import torch
+        p = self._prec(rec)
+        _, R, B = rec.shape
+        dt, dev = rec.dtype, rec.device
+        _chk("rec", rec, (REC, self.n_robots, B), optional=False)
+        S = 0 if stat is None else stat.shape[0]
+        _chk("stat", stat, (S, 4, R, B), dt, dev)
+        if avg_vel is None:
+            avg_vel = torch.empty((R, B), dtype=dt, device=dev)
+        _chk("avg_vel", avg_vel, (R, B), dt, dev)
+        _chk("x_ee", x_ee, (R, 3, B), dt, dev)
+        _chk("goal_est", goal_est, (3, B), dt, dev)
+        _chk("qN", qN, (R, N, DOF, B), dt, dev)
+        _chk("qdN", qdN, (R, N, DOF, B), dt, dev)
+        fn = getattr(lib(), f"mrf_rollout_static_dev_{p}")
+        check(fn(self.handle.ptr, self._tp(rec), N, S, self._tp(stat), self._tp(avg_vel), self._tp(x_ee), self._tp(goal_est),
+                 self._tp(qN), self._tp(qdN), B, self._stream()), "mrf_rollout_static_dev")
+        return avg_vel
+
     def rfcv_post_dev(self, rec, N: int, x_ee, rec_work, goal_est, avg_vel, sm_state, time_step, time_deadlock_out, st_int,
                       st_goal, risk=None, flag=None, result=None, slot: int = 0):
         """Post step of an RF-CV sweep (mrf_rfcv_post_dev): deadlock heuristic in place on rec_work, per-scenario results

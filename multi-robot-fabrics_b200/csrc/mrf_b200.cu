@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
                    unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail,
                    T* __restrict__ risk, unsigned* __restrict__ n_live, const float* __restrict__ rec_f32,
-                   const int* __restrict__ list, long long B_src) {
+                   const int* __restrict__ list, long long B_src, int n_static, const T* __restrict__ stat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // STRIDE (FP64 re-roll of the guard band): the scenarios are the first min(*n_live, B) entries of `list` -- produced
     // on the device by guard_select_kernel -- read from the FP32 records rec_f32 [44][R][B_src] (exact promotion); results
@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         qd[i] = ld(MRF_QD + i);
     }
     load_params<T>(ld, prm, NT, tid);
+    // static spheres of this robot's rollout planner (generic kernel only): stat [n_static][4][R][B] = x, y, z, radius
+    T* st_sph = prm + P_N * NT;
+    if (!UNIFORM && !AOS && n_static > 0) {
+        for (int i = 0; i < 4 * n_static; ++i) st_sph[i * NT + tid] = stat[((long long)i * R + r) * B + bb];
+    }
     Chain<T> ch;
     const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
     T acc = T(0);
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
             SmemSrcUniform<T, R> src{kin, lane, r, vref, aref, cfg.r_obst};
             fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act, &stiff);
         } else {
-            SmemSrc<T> src{cfg, kin, NT, lane, r, vref, aref};
+            SmemSrc<T> src{cfg, kin, NT, lane, r, vref, aref, st_sph, AOS ? 0 : n_static, tid};
             fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act, &stiff);
         }
         prm[P_RISK * NT + tid] = Mth<T>::max(prm[P_RISK * NT + tid], stiff);
@@ -264,9 +269,14 @@ __global__ void __launch_bounds__(kActThreads, sizeof(T) == 4 ? MRF_ACTION_MINBL
             fabric_action(cfg, r, q, qd, ch, kin, prm, NT, tid, src, act);
 #pragma unroll
             for (int i = 0; i < kDof; ++i) {
-                qd[i] = act[i];
-                q[i] += cfg.dt * act[i];
-                acc += act[i] * act[i];
+                if (cfg.mode == 1) { // 'vel': the action is the new velocity (system_step, forward_planner_Cartesian.py:85-87)
+                    qd[i] = act[i];
+                    q[i] += cfg.dt * act[i];
+                } else {             // 'acc': the action is qdd (:81-84)
+                    q[i] += cfg.dt * qd[i] + T(0.5) * cfg.dt * cfg.dt * act[i];
+                    qd[i] += cfg.dt * act[i];
+                }
+                acc += qd[i] * qd[i];
             }
             if (live) {
 #pragma unroll
@@ -948,6 +958,7 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
         T[0] = cos(yaw); T[1] = -sin(yaw); T[4] = sin(yaw); T[5] = cos(yaw); T[10] = 1.0; T[15] = 1.0;
         T[3] = pos[r][0]; T[7] = pos[r][1]; T[11] = pos[r][2];
         for (int l = 0; l < MRF_NLINKS; ++l) c->r_robots[r][l] = 0.08; // parameters_manipulators.py:23
+        c->collision_link_mask[r] = 0xFF;                              // collision_links_nrs = [1..8], :25
     }
     static const double lim[7][2] = {{-2.8973, 2.8973}, {-1.7628, 1.7628}, {-2.8973, 2.8973}, {-3.0718, -0.0698},
                                      {-2.8973, 2.8973}, {-0.0175, 3.7525}, {-2.8973, 2.8973}};
@@ -1097,7 +1108,7 @@ template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
                        void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr,
                        T* risk = nullptr, unsigned* n_live = nullptr, const float* rec_f32 = nullptr,
-                       const int* list = nullptr, long long B_src = 0) {
+                       const int* list = nullptr, long long B_src = 0, int n_static = 0, const T* stat = nullptr) {
     if (!h || (!rec && !n_live)) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -1106,7 +1117,9 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
     if (aos && (qN || qdN)) return fail(MRF_EINVAL, "mrf_rollout: record-order input has no trajectory output");
-    if (!aos && R >= 2 && B <= h->coop_max_batch && !risk && !n_live) {
+    if (n_static < 0 || n_static > MRF_MAX_STATIC || (n_static > 0 && (!stat || aos || n_live)))
+        return fail(MRF_EINVAL, "mrf_rollout: bad static-obstacle arguments");
+    if (!aos && R >= 2 && B <= h->coop_max_batch && !risk && !n_live && n_static == 0) {
         // few scenarios: latency matters, not throughput -> one CTA per scenario, one warp per robot (mrf_coop.cuh)
         switch (R) {
             case 2: rollout_coop_kernel<T, 2><<<(unsigned)B, 64, 0, (cudaStream_t)stream>>>(devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B); break;
@@ -1118,7 +1131,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         h->launches += 1;
         return MRF_OK;
     }
-    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N) * NT;
+    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N + 4 * n_static) * NT;
     long long grid = (B + kTile - 1) / kTile;
     if (n_live != nullptr && grid > 16) grid = 16; // device-side count: a few CTAs stride over the tiles (see the kernel)
     int rc = MRF_OK;
@@ -1128,11 +1141,11 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA, SS><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                       \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
-            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live, rec_f32, list, B_src);                            \
+            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live, rec_f32, list, B_src, n_static, stat);            \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
-        if (devcfg<T>(h).uniform_obst) {                                                                             \
+        if (devcfg<T>(h).uniform_obst && n_static == 0) {                                                            \
             if (aos) MRF_LAUNCH_ROLLOUT_K(RR, true, true, false)                                                     \
             else if (stride) MRF_LAUNCH_ROLLOUT_STRIDE(RR, true)                                                     \
             else MRF_LAUNCH_ROLLOUT_K(RR, true, false, false)                                                        \
@@ -1171,7 +1184,7 @@ static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, 
     if (!h || !rec || (S > 0 && !obst)) return fail(MRF_EINVAL, "mrf_action: null argument");
     if (B <= 0 || S < 0 || n_rob < 1 || robot_first < 0 || robot_first + n_rob > h->cfg.n_robots)
         return fail(MRF_EINVAL, "mrf_action: bad sizes");
-    if (CART && (N <= 0 || h->cfg.mode != 1)) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0 and mode 'vel'");
+    if (CART && N <= 0) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0");
     MRF_CUDA(cudaSetDevice(h->device));
     const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N + kObstRing * MRF_OBST) * kActThreads;
     int rc = set_smem(action_kernel<T, CART>, smem);
@@ -1238,6 +1251,18 @@ extern "C" int mrf_rollout_dev_f64(mrf_handle_t h, const double* rec, int N, dou
 extern "C" int mrf_rollout_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg_vel, float* x_ee, float* goal_est,
                                    float* qN, float* qdN, int64_t B, void* stream) {
     return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream);
+}
+extern "C" int mrf_rollout_static_dev_f64(mrf_handle_t h, const double* rec, int N, int n_static, const double* stat,
+                                          double* avg_vel, double* x_ee, double* goal_est, double* qN, double* qdN, int64_t B,
+                                          void* stream) {
+    return rollout_dev<double>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, 0, n_static, stat);
+}
+extern "C" int mrf_rollout_static_dev_f32(mrf_handle_t h, const float* rec, int N, int n_static, const float* stat,
+                                          float* avg_vel, float* x_ee, float* goal_est, float* qN, float* qdN, int64_t B,
+                                          void* stream) {
+    return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, 0, n_static, stat);
 }
 extern "C" int mrf_action_dev_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S,
                                   const double* obst, double* action, int64_t B, void* stream) {

@@ -124,9 +124,18 @@ __device__ __forceinline__ void fabric_action_coop(const DevCfg<T>& cfg, int r, 
         T rb = prm[(P_RB + rb_first) * NT + tid];
         T we = T(1);
         int passes = 1;
+        const int em = cfg.ego_mask[r]; // which of panda_link3..8 are collision links (see fabric_action)
         if (e == 2) {
             T rb2 = prm[(P_RB + rb_first + 1) * NT + tid];
-            if (rb2 == rb) we = T(2); else passes = 2;
+            if (((em >> rb_first) & 3) == 3) {
+                if (rb2 == rb) we = T(2); else passes = 2;
+            } else if ((em >> (rb_first + 1)) & 1) {
+                rb = rb2;
+            } else if (!((em >> rb_first) & 1)) {
+                passes = 0;
+            }
+        } else if (!((em >> rb_first) & 1)) {
+            passes = 0;
         }
         for (int pass = 0; pass < passes; ++pass) {
             if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];

@@ -165,7 +165,9 @@ template <typename T> struct DevCfg {
     int pt_n[MRF_MAX_ROBOTS][kPts];
     T pt_w[MRF_MAX_ROBOTS][kPts];
     T pt_rad[MRF_MAX_ROBOTS][kPts][2];
-    int uniform_obst;           // every r_robots[j][l] equal -> SmemSrcUniform fast path with radius r_obst
+    int ego_mask[MRF_MAX_ROBOTS]; // bit k: panda_link(3+k) of robot r carries collision leaves (collision_links_nr)
+    int uniform_obst;           // every r_robots[j][l] equal and every link of every robot in its collision set ->
+                                // SmemSrcUniform fast path with radius r_obst
     T r_obst;
     int ent_n[MRF_MAX_ROBOTS];
     int ent_rob[MRF_MAX_ROBOTS][kMaxEnt];
@@ -659,6 +661,10 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         // pairs (link3|link4, link5|link6, link7|link8) -- the ego-major loop below would re-read the list five times
         // (measured: the S = 64 action was bound by that traffic).  FP32 only (pairs in registers).
         constexpr bool kObstMajor = Src::kObstacleMajor && sizeof(T) == 4;
+        // which of panda_link3..8 carry leaves (collision_links_nr of set_planner_panda); the uniform fast path is only
+        // taken when every link of every robot is in its set
+        int em = 0x3F;
+        if constexpr (!Src::kFullLinks) em = cfg.ego_mask[r];
         PointAcc2<T> om[3];
         if (kObstMajor) {
             V3<P2<T>> pp[3], vv[3], cp[3];
@@ -678,11 +684,12 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
                 const V3<P2<T>> xo2{psplat(xo.x), psplat(xo.y), psplat(xo.z)}, vo2{psplat(vo.x), psplat(vo.y), psplat(vo.z)},
                     co2{psplat(co.x), psplat(co.y), psplat(co.z)};
-                const P2<T> ro2 = psplat(ro), wo2 = psplat(wo);
+                const P2<T> ro2 = psplat(ro);
 #pragma unroll
                 for (int ps = 0; ps < 3; ++ps)
                     sphere_leaf2<T, false>(pp[ps], vv[ps], cp[ps], xo2, vo2, co2, src.vref, src.aref, padd(ro2, rbp[ps]), ro2,
-                                           pmul(wo2, psplat(T(0.02))), sigma, om[ps]);
+                                           pmk(T(0.02) * wo * T((em >> (2 * ps)) & 1), T(0.02) * wo * T((em >> (2 * ps + 1)) & 1)),
+                                           sigma, om[ps]);
             });
         }
 #pragma unroll 1
@@ -698,8 +705,17 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             int passes = 1;
             if (e == 2) { // link5 and link6 share the point; identical leaves if their radii agree
                 T rb2 = prm[(P_RB + rb_first + 1) * NT + tid];
-                if (rb2 == rb) we = T(2); else passes = 2;
+                if (Src::kFullLinks || ((em >> rb_first) & 3) == 3) {
+                    if (rb2 == rb) we = T(2); else passes = 2;
+                } else if ((em >> (rb_first + 1)) & 1) {
+                    rb = rb2;                       // only link6 is a collision link
+                } else if (!((em >> rb_first) & 1)) {
+                    passes = 0;                     // neither
+                }
+            } else if (!Src::kFullLinks && !((em >> rb_first) & 1)) {
+                passes = 0;
             }
+            if (!Src::kFullLinks && passes == 0) continue; // no collision link at this point: no leaves, nothing to pull back
             PointAcc2<T> acc2;
             acc2_zero(acc2);
             if (kObstMajor) {
@@ -741,6 +757,13 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                         sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
                     });
                 }
+                // static spheres of the rollout planners (x_obst_i, radius_obst_i; forward_planner_Jointspace.py:319-322):
+                // the same leaf with a sphere at rest
+                if constexpr (Src::kHasStatic)
+                    src.each_static([&](V3<T> xo, T ro) {
+                        const V3<T> z0 = mk(T(0), T(0), T(0));
+                        sphere_leaf(p, v, cc, xo, z0, z0, T(0), T(0), ro + rb, we, sigma, acc, num);
+                    });
                 plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
             }
             acc.A.xx += plo(acc2.A.xx) + phi(acc2.A.xx); acc.A.xy += plo(acc2.A.xy) + phi(acc2.A.xy);
@@ -875,12 +898,22 @@ constexpr int kTile = 32; // scenarios per CTA in the rollout kernel (one lane e
 // other robots of the same scenario, read from the CTA's shared kinematics table (generic: table driven, any radii)
 template <typename T> struct SmemSrc {
     static constexpr bool kUniformRadius = false;
+    static constexpr bool kFullLinks = false;     // ego leaves follow cfg.ego_mask
+    static constexpr bool kHasStatic = true;      // + n_static spheres at rest per robot, staged at stat[(o*4+c)*NT + tid]
+    template <typename F> MRF_HD void each_static(F f) const {
+        for (int o = 0; o < n_static; ++o) {
+            const T* b = stat + (o * 4) * NT + tid_s;
+            f(mk(b[0], b[NT], b[2 * NT]), b[3 * NT]);
+        }
+    }
     static constexpr bool kObstacleMajor = false; // shared-memory points: re-reading per ego point is cheap
     MRF_HD bool collide(bool has) const { return has; }
     const DevCfg<T>& cfg;
     const T* kin;
     int NT, lane, r;
     T vref, aref;
+    const T* stat = nullptr;
+    int n_static = 0, tid_s = 0;
     template <typename F> MRF_HD void each(F f) const {
         const int ne = cfg.ent_n[r];
 #pragma unroll 2
@@ -912,6 +945,8 @@ template <typename T> struct SmemSrc {
 // with their multiplicities (link3, link4, link5==6 [x2], link7, link8, link1==2 [x2]) as compile-time constants.
 template <typename T, int R> struct SmemSrcUniform {
     static constexpr bool kUniformRadius = true;  // every sphere has radius ro: rho = ro + radius_body is per ego point
+    static constexpr bool kFullLinks = true;      // all of panda_link3..8 carry leaves (the reference's set-up)
+    static constexpr bool kHasStatic = false;
     static constexpr bool kObstacleMajor = false;
     MRF_HD bool collide(bool has) const { return has; }
     const T* kin;
@@ -971,6 +1006,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 #endif
 template <typename T, bool CART> struct GlobalSrc {
     static constexpr bool kUniformRadius = false;
+    static constexpr bool kFullLinks = false;
+    static constexpr bool kHasStatic = false;     // static spheres arrive in the same list with zero velocity
     static constexpr bool kObstacleMajor = true; // global-memory spheres: load each once (see fabric_action)
     const T* obst;
     long long stride, off;

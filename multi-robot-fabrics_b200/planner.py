@@ -76,14 +76,22 @@ class PandaFabricPlanner:
         self.mount = np.asarray(mount, dtype=np.float64).reshape(4, 4)
         self.i_robot = i_robot
         self.nr_obst, self.nr_obst_dyn = int(nr_obst), int(nr_obst_dyn)
-        # links with constant fk (panda_link1/2) carry no leaves; an empty list is the grasp planner
-        self.collision_links_nr = [l for l in collision_links_nr if l > 2]
-        missing = sorted(set(range(3, 9)) - set(min(l, 8) for l in self.collision_links_nr))
-        if self.collision_links_nr and missing:
-            raise MrfError(f"the CUDA path implements the reference's full link set 3..8 (or none); missing {missing}")
+        # Any subset of panda_link1..8 (the reference's signature default is [5]); links with constant fk (panda_link1/2)
+        # carry no leaves, an empty list is the grasp planner.  Numbers >= 9 mean 'panda_hand'
+        # (example_pandas_Jointspace.py:91-96), whose origin is panda_link8's: accepted in place of link 8 only.
+        links = [int(l) for l in collision_links_nr]
+        if any(l >= 9 for l in links):
+            if 8 in links:
+                raise MrfError("panda_hand next to panda_link8 (two leaves at one point) is not implemented")
+            links = [min(l, 8) for l in links]
+        if any(l < 1 for l in links):
+            raise MrfError(f"collision_links_nr must be link numbers >= 1, got {collision_links_nr}")
+        self.collision_links_all = sorted(set(links))
+        self.collision_links_nr = [l for l in self.collision_links_all if l > 2]
         self.dtype = dtype
         cfg = default_config(1, mode=1 if mode == "vel" else 0, dt=time_step,
-                             has_collision_links=1 if self.collision_links_nr else 0, mount=[self.mount], limits=limits)
+                             has_collision_links=1 if self.collision_links_nr else 0, mount=[self.mount], limits=limits,
+                             collision_links=[self.collision_links_all])
         self.fab = Fabrics(config=cfg, device=device)
 
     # fabrics' CasadiFunctionWrapper expands list / dict kwargs into per-index parameters
@@ -108,8 +116,8 @@ class PandaFabricPlanner:
                 rec[RB + i] = float(np.asarray(links[str(l)]).reshape(-1)[0])
             elif l in links:
                 rec[RB + i] = float(np.asarray(links[l]).reshape(-1)[0])
-            elif self.collision_links_nr:
-                raise KeyError(key)
+            elif l in self.collision_links_nr:
+                raise KeyError(key)        # a collision link needs its radius_body parameter, as in fabrics
         if not self.collision_links_nr:
             # no collision links -> fabrics creates no obstacle leaves, so no obstacle parameter exists in the function
             # (the grasp planner is built with nr_obst = nr_obst_dyn = i_robot, example_pandas_Jointspace.py:160-166)
@@ -215,15 +223,22 @@ class ForwardFabricsPlanner:
         self.dtype = dtype
         if self.fabrics_mode != "vel":
             raise MrfError("joint-space rollouts are defined for fabrics_mode 'vel' (forward_planner_Jointspace.py:233)")
-        if any(n != 0 for n in self.nr_obsts):
-            raise MrfError("static obstacles in the rollout planners are not used by the reference (nr_obsts = 0)")
-        # radius bodies of links > 2 (forward_planner_Jointspace.py:37-40)
+        if len(set(self.nr_obsts)) > 1:
+            raise MrfError("the CUDA rollout takes the same number of static spheres for every robot")
+        self.radius_obsts = getattr(params, "radius_obsts", None)
+        # radius bodies of links > 2 (forward_planner_Jointspace.py:37-40); r_robots[i][z] belongs to link collision_links_nrs[i][z]
         self.r_robots_args = [[self.r_robots[i][z] for z, c in enumerate(self.collision_links_nrs[i]) if c > 2]
                               for i in range(self.nr_robots)]
+        r_full = [[0.0] * 8 for _ in range(self.nr_robots)]
+        for i in range(self.nr_robots):
+            for z, c in enumerate(self.collision_links_nrs[i]):
+                if not 1 <= int(c) <= 8:
+                    raise MrfError(f"collision link numbers must be 1..8, got {c}")
+                r_full[i][int(c) - 1] = float(self.r_robots[i][z])
         mounts = [np.asarray(p.mount) for p in planners]
         cfg = default_config(self.nr_robots, dt=self.dt, static_or_dyn=int(params.STATIC_OR_DYN_FABRICS),
-                             mount=mounts, r_robots=[list(map(float, r)) for r in self.r_robots],
-                             estimate_goal=int(estimate_goal))
+                             mount=mounts, r_robots=r_full, estimate_goal=int(estimate_goal),
+                             collision_links=[list(c) for c in self.collision_links_nrs])
         self.fab = Fabrics(config=cfg, device=device)
 
     def forward_multi_fabrics_symbolic(self):
@@ -244,18 +259,60 @@ class ForwardFabricsPlanner:
             rec[0, i, G0:G0 + 3] = _vec(inputs_action["x_goals0"][i], 3)
             rec[0, i, G1:G1 + 3] = _vec(inputs_action["x_goals1"][i], 3)
             rec[0, i, G2] = _vec(inputs_action["x_goals2"][i])[0]
-            rec[0, i, RB:RB + 6] = np.asarray(self.r_robots_args[i], dtype=np.float64)
+            k = 0
+            for l in range(3, 9):                # radius_body_panda_link{l} of the links in the robot's collision set
+                if l in self.collision_links_nrs[i]:
+                    rec[0, i, RB + l - 3] = float(self.r_robots_args[i][k])
+                    k += 1
         return rec
+
+    def _static(self, inputs_action):
+        """x_obsts / radius_obsts of the rollout planners (:319-322) -> (1, R, S, 4) or None."""
+        S = int(self.nr_obsts[0]) if len(self.nr_obsts) else 0
+        if S == 0:
+            return None
+        if self.radius_obsts is None:
+            raise MrfError("params.radius_obsts is needed for rollouts with static obstacles (forward_planner_Jointspace.py:322)")
+        st = np.zeros((1, self.nr_robots, S, 4))
+        for i in range(self.nr_robots):
+            for o in range(S):
+                st[0, i, o, 0:3] = _vec(inputs_action["x_obsts"][i][o], 3)
+                st[0, i, o, 3] = float(np.asarray(self.radius_obsts[i][o]).reshape(-1)[0])
+        return st
+
+    def _rollout(self, inputs_action, trajectories: bool):
+        rec, st = self._records(inputs_action), self._static(inputs_action)
+        if st is None:
+            return self.fab.rollout_host(rec, self.N_horizon, dtype=self.dtype, trajectories=trajectories)
+        # static spheres: device entry mrf_rollout_static_dev (tensor hand-off through torch)
+        import torch
+        from .api import to_soa
+        R, N = self.nr_robots, self.N_horizon
+        tdt = torch.float64 if self.dtype == "f64" else torch.float32
+        dev = f"cuda:{self.fab.device}"
+        d_rec = torch.from_numpy(to_soa(rec)).to(dev, dtype=tdt)
+        d_st = torch.from_numpy(np.ascontiguousarray(st.transpose(2, 3, 1, 0))).to(dev, dtype=tdt)      # (S,4,R,1)
+        t = lambda *shape: torch.empty(shape, dtype=tdt, device=dev)
+        avg, xee, gest = t(R, 1), t(R, 3, 1), t(3, 1)
+        qN, qdN = (t(R, N, DOF, 1), t(R, N, DOF, 1)) if trajectories else (None, None)
+        self.fab.rollout_static_dev(d_rec, d_st, N, avg_vel=avg, x_ee=xee, goal_est=gest, qN=qN, qdN=qdN)
+        torch.cuda.synchronize()
+        out = {"avg_vel": avg.double().cpu().numpy().T.copy(), "x_ee": xee.double().cpu().numpy().transpose(2, 0, 1).copy(),
+               "goal_est": gest.double().cpu().numpy().T.copy()}
+        if trajectories:
+            out["qN"] = qN.double().cpu().numpy().transpose(3, 0, 1, 2).copy()
+            out["qdN"] = qdN.double().cpu().numpy().transpose(3, 0, 1, 2).copy()
+        return out
 
     def get_velocity_rollouts(self, inputs_action):
         """-> list of R arrays of shape (1,): mean square joint velocity over the horizon (:298-336)."""
-        out = self.fab.rollout_host(self._records(inputs_action), self.N_horizon, dtype=self.dtype)
+        out = self._rollout(inputs_action, False)
         self.last = out
         return [np.array([float(out["avg_vel"][0, i])]) for i in range(self.nr_robots)]
 
     def rollouts_numerical(self, inputs_action=None, **_ignored):
         """-> (q_N, qdot_N, qddot_N) dicts keyed 'robot_i', each [array(7, N)] (:338-423)."""
-        out = self.fab.rollout_host(self._records(inputs_action), self.N_horizon, dtype=self.dtype, trajectories=True)
+        out = self._rollout(inputs_action, True)
         self.last = out
         qn, qdn, qddn = {}, {}, {}
         for i in range(self.nr_robots):
@@ -274,7 +331,7 @@ class ForwardFabricsPlanner:
         STATIC_OR_DYN_FABRICS = 0 zeroes v and a (:215-217)."""
         R, N = self.nr_robots, self.N_horizon
         rec = self._records(inputs_action)
-        out = self.fab.rollout_host(rec, N, dtype=self.dtype, trajectories=True)
+        out = self._rollout(inputs_action, True)
         self.last = out
         q = np.asarray(out["qN"][0], dtype=np.float64)                                  # (R, N, 7): q_k
         qd_prev = np.concatenate([rec[0, :, None, QD:QD + 7], np.asarray(out["qdN"][0], dtype=np.float64)[:, :-1]], axis=1)
@@ -285,7 +342,8 @@ class ForwardFabricsPlanner:
         xs, vs, as_ = {}, {}, {}
         for i in range(R):
             others = [j for j in range(R) if j != i]
-            cat = lambda arr, k: np.concatenate([arr[k, j] for j in others], axis=0).T.copy()       # (3, 8 (R-1))
+            sel = {j: [int(c) - 1 for c in self.collision_links_nrs[j]] for j in others}                # their collision links
+            cat = lambda arr, k: np.concatenate([arr[k, j][sel[j]] for j in others], axis=0).T.copy()   # (3, sum of links)
             xs[f"robot_{i}"] = [cat(x, k) for k in range(N)]
             vs[f"robot_{i}"] = [cat(v, k) for k in range(N)]
             as_[f"robot_{i}"] = [cat(a, k) for k in range(N)]
@@ -324,8 +382,8 @@ class FabricsRollouts:
         self.nr_goals = nr_goals
         self.dtype = dtype
         self.radius_body_panda_links = {str(l): np.array(radius_sphere) for l in self.collision_links_nrs if l > 2}
-        if fabrics_mode != "vel":
-            raise MrfError("the CUDA Cartesian rollout implements fabrics_mode 'vel' (the reference's setting)")
+        if fabrics_mode not in ("vel", "acc"):
+            raise MrfError("fabrics_mode must be 'vel' or 'acc'")
 
     # ---- environment-dictionary readers (forward_planner_Cartesian.py:49-69,94-130): host glue, same keys ----
     def preset_radii(self, ob_robot):
@@ -444,6 +502,8 @@ class FabricsRollouts:
     def symbolic_forward_fabrics(self, planner, goal_struct):
         self.planner = planner
         self.nr_subgoals = len(goal_struct._config)
+        if (planner.fab.cfg.mode == 1) != (self.fabrics_mode == "vel"):
+            raise MrfError("the planner was concretized in a different mode than fabrics_mode of the rollouts")
         return {}
 
     def define_arguments_numerical(self, q_robot, q_dot_robot, weight_goals, x_goals, x_obsts, x_obsts_dyn, v_obsts_dyn,
@@ -516,10 +576,16 @@ class FabricsRollouts:
         return self.planner.fab.rollout_cart_host(0, rec[None], obst[None], self.N, dtype=self.dtype)
 
     def rollouts_numerical(self, arguments):
-        """-> q_N, qdot_N, qddot_N, each array (7, N) (forward_planner_Cartesian.py:538-559)."""
+        """-> q_N, qdot_N, qddot_N, each array (7, N) (forward_planner_Cartesian.py:538-559).  'vel' mode: q_ddot is
+        identically 0 (:431-433); 'acc' mode: the actions, recovered from the velocity steps (vel += dt * action, :84)."""
+        rec, _ = self._unpack(arguments)
         _, qN, qdN = self._run(arguments)
-        return (np.asarray(qN[0], dtype=np.float64).T.copy(), np.asarray(qdN[0], dtype=np.float64).T.copy(),
-                np.zeros((DOF, self.N)))
+        q = np.asarray(qN[0], dtype=np.float64).T.copy()
+        qd = np.asarray(qdN[0], dtype=np.float64).T.copy()
+        if self.fabrics_mode == "vel":
+            return q, qd, np.zeros((DOF, self.N))
+        prev = np.concatenate([rec[QD:QD + 7, None], qd[:, :-1]], axis=1)
+        return q, qd, (qd - prev) / self.dt
 
     def get_velocity_rollouts(self, arguments):
         avg, _, _ = self._run(arguments)

@@ -69,6 +69,7 @@ void mrfo_config_default(mrfo_config* c, int n_robots) {
         T[0] = cos(yaw); T[1] = -sin(yaw); T[4] = sin(yaw); T[5] = cos(yaw); T[10] = 1; T[15] = 1;
         T[3] = p[0]; T[7] = p[1]; T[11] = p[2];
         for (int l = 0; l < MRFO_NLINKS; l++) c->r_robots[r][l] = 0.08; /* parameters_manipulators.py:23 */
+        c->link_mask[r] = 0xFF;                                            /* collision_links_nrs = [1..8], :25 */
     }
     static const double lim[7][2] = {{-2.8973, 2.8973}, {-1.7628, 1.7628}, {-2.8973, 2.8973}, {-3.0718, -0.0698},
                                      {-2.8973, 2.8973}, {-0.0175, 3.7525}, {-2.8973, 2.8973}};
@@ -221,7 +222,7 @@ static int cholesky_solve(const double A[DOF][DOF], double eps, const double b[D
     return 0;
 }
 
-static int action_from_kin(const mrfo_config* c, const kin_t* k, const double* rec, int S, const double* xo,
+static int action_from_kin(const mrfo_config* c, int link_mask, const kin_t* k, const double* rec, int S, const double* xo,
                            const double* vo, const double* ao, const double* ro, double* action, double* diag) {
     const double* q = rec + MRFO_Q;
     const double* qd = rec + MRFO_QD;
@@ -235,6 +236,7 @@ static int action_from_kin(const mrfo_config* c, const kin_t* k, const double* r
         double nn = sqrt(con[0] * con[0] + con[1] * con[1] + con[2] * con[2]);
         double nh[3] = {con[0] / nn, con[1] / nn, con[2] / nn};
         for (int l = 2; l < 8; l++) { /* panda_link3..8: links 1,2 have constant fk and are skipped */
+            if (!((link_mask >> l) & 1)) continue; /* not in collision_links_nr (example_pandas_Jointspace.py:91-96) */
             double rb = rec[MRFO_RB + (l - 2)];
             const double* p = k->p[l];
             const double* v = k->v[l];
@@ -375,12 +377,18 @@ int mrfo_action(const mrfo_config* c, int robot, const double* rec, int S, const
                 const double* ao, const double* ro, double* action, double* diag) {
     kin_t k;
     kinematics(c->mount[robot], rec + MRFO_Q, rec + MRFO_QD, &k);
-    return action_from_kin(c, &k, rec, S, xo, vo, ao, ro, action, diag);
+    return action_from_kin(c, c->link_mask[robot], &k, rec, S, xo, vo, ao, ro, action, diag);
 }
 
 int mrfo_rollout_jointspace(const mrfo_config* c, const double* rec_in, int N, double* qN, double* qdN,
                             double* avg_vel, double* x_ee) {
-    const int R = c->n_robots, S = 8 * (R - 1);
+    return mrfo_rollout_jointspace_static(c, rec_in, N, 0, 0, 0, qN, qdN, avg_vel, x_ee);
+}
+
+int mrfo_rollout_jointspace_static(const mrfo_config* c, const double* rec_in, int N, int n_static, const double* xs,
+                                   const double* rs, double* qN, double* qdN, double* avg_vel, double* x_ee) {
+    const int R = c->n_robots;
+    if (n_static < 0 || n_static > MRFO_MAX_STATIC) return 2;
     double rec[MRFO_MAX_ROBOTS][MRFO_ROBOT_IN];
     kin_t kin[MRFO_MAX_ROBOTS];
     double acc[MRFO_MAX_ROBOTS] = {0};
@@ -397,22 +405,32 @@ int mrfo_rollout_jointspace(const mrfo_config* c, const double* rec_in, int N, d
             kinematics(c->mount[i], rec[i] + MRFO_Q, rec[i] + MRFO_QD, &kin[i]);
         }
         double act[MRFO_MAX_ROBOTS][DOF];
-        for (int i = 0; i < R; i++) { /* Phase B (:211-249): others ascending j, all 8 links */
-            double xo[8 * (MRFO_MAX_ROBOTS - 1)][3], vo[8 * (MRFO_MAX_ROBOTS - 1)][3], ao[8 * (MRFO_MAX_ROBOTS - 1)][3],
-                ro[8 * (MRFO_MAX_ROBOTS - 1)];
+        for (int i = 0; i < R; i++) { /* Phase B (:211-249): others ascending j, their collision links */
+            enum { SMAX = 8 * (MRFO_MAX_ROBOTS - 1) + MRFO_MAX_STATIC };
+            double xo[SMAX][3], vo[SMAX][3], ao[SMAX][3], ro[SMAX];
             int o = 0;
+            for (int s = 0; s < n_static; s++, o++) { /* x_obst_s, radius_obst_s of robot i (:319-322): spheres at rest */
+                for (int a = 0; a < 3; a++) {
+                    xo[o][a] = xs[(i * n_static + s) * 3 + a];
+                    vo[o][a] = ao[o][a] = 0.0;
+                }
+                ro[o] = rs[i * n_static + s];
+            }
             for (int j = 0; j < R; j++) {
                 if (j == i) continue;
-                for (int l = 0; l < 8; l++, o++)
+                for (int l = 0; l < 8; l++) {
+                    if (!((c->link_mask[j] >> l) & 1)) continue; /* collision_links_nrs[j] */
                     for (int a = 0; a < 3; a++) {
                         xo[o][a] = kin[j].p[l][a];
                         vo[o][a] = c->static_or_dyn ? kin[j].v[l][a] : 0.0;
                         /* a = J qdd + Jdot qdot, qdd = 0, Jdot = jdot_ref_sign * d(J qdot)/dq (utils.py:28,37) */
                         ao[o][a] = c->static_or_dyn ? c->jdot_ref_sign * kin[j].c[l][a] : 0.0;
-                        ro[o] = c->r_robots[j][l];
                     }
+                    ro[o] = c->r_robots[j][l];
+                    o++;
+                }
             }
-            rc |= action_from_kin(c, &kin[i], rec[i], S, &xo[0][0], &vo[0][0], &ao[0][0], ro, act[i], 0);
+            rc |= action_from_kin(c, c->link_mask[i], &kin[i], rec[i], o, &xo[0][0], &vo[0][0], &ao[0][0], ro, act[i], 0);
         }
         for (int i = 0; i < R; i++)
             for (int a = 0; a < DOF; a++) {
@@ -438,11 +456,16 @@ int mrfo_rollout_cartesian(const mrfo_config* c, int robot, const double* rec_in
     for (int k = 0; k < N; k++) {
         rc |= mrfo_action(c, robot, rec, S, xo, vo, ao, ro, act, 0);
         for (int a = 0; a < DOF; a++) {
-            rec[MRFO_QD + a] = act[a];
-            rec[MRFO_Q + a] += c->dt * act[a];
-            acc += act[a] * act[a];
+            if (c->mode == 1) { /* 'vel': the action is the new velocity (forward_planner_Cartesian.py:85-87) */
+                rec[MRFO_QD + a] = act[a];
+                rec[MRFO_Q + a] += c->dt * act[a];
+            } else {            /* 'acc': the action is qdd (:81-84) */
+                rec[MRFO_Q + a] += c->dt * rec[MRFO_QD + a] + 0.5 * c->dt * c->dt * act[a];
+                rec[MRFO_QD + a] += c->dt * act[a];
+            }
+            acc += rec[MRFO_QD + a] * rec[MRFO_QD + a];
             if (qN) qN[k * DOF + a] = rec[MRFO_Q + a];
-            if (qdN) qdN[k * DOF + a] = act[a];
+            if (qdN) qdN[k * DOF + a] = rec[MRFO_QD + a];
         }
         for (int o = 0; o < 3 * S; o++) xo[o] += c->dt * vo[o];
     }

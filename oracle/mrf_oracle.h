@@ -19,6 +19,7 @@ extern "C" {
 #define MRFO_DOF 7
 #define MRFO_NLINKS 8          /* panda_link1..8 (parameters_manipulators.py:25-26) */
 #define MRFO_ROBOT_IN 44       /* packed per-robot rollout input record, see below */
+#define MRFO_MAX_STATIC 16     /* static spheres per robot in a coupled rollout */
 
 /* Per-robot record (doubles), the arguments of get_velocity_rollouts
  * (forward_planner_Jointspace.py:303-329) in a fixed order:
@@ -42,6 +43,8 @@ typedef struct {
     double limits[MRFO_DOF][2];            /* example_pandas_Jointspace.py:97-105 */
     double r_robots[MRFO_MAX_ROBOTS][MRFO_NLINKS]; /* other-robot sphere radii, compile-time in the
                                                       reference graph (forward_planner_Jointspace.py:221) */
+    int link_mask[MRFO_MAX_ROBOTS];               /* bit l-1: panda_link l in collision_links_nr of the robot
+                                                      (example_pandas_Jointspace.py:64,91-96); default 0xFF */
 } mrfo_config;
 
 void mrfo_config_default(mrfo_config* c, int n_robots);
@@ -60,6 +63,11 @@ int mrfo_action(const mrfo_config* c, int robot, const double* rec, int S, const
  * rec [R][44]; outputs (nullable): qN, qdN [R][N][7]; avg_vel [R]; x_ee [R][3] = hand at the input q. */
 int mrfo_rollout_jointspace(const mrfo_config* c, const double* rec, int N, double* qN, double* qdN,
                             double* avg_vel, double* x_ee);
+
+/* The same with n_static static spheres per robot (x_obst_s, radius_obst_s of the rollout planners,
+ * forward_planner_Jointspace.py:319-322): xs [R][n_static][3], rs [R][n_static]. */
+int mrfo_rollout_jointspace_static(const mrfo_config* c, const double* rec, int N, int n_static, const double* xs,
+                                   const double* rs, double* qN, double* qdN, double* avg_vel, double* x_ee);
 
 /* FabricsRollouts decoupled rollout (forward_planner_Cartesian.py:421-458), one robot. */
 int mrfo_rollout_cartesian(const mrfo_config* c, int robot, const double* rec, int S, const double* xo,

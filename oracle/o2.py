@@ -26,6 +26,7 @@ class Config(C.Structure):
         ("mount", (C.c_double * 16) * MAX_ROBOTS),
         ("limits", (C.c_double * 2) * DOF),
         ("r_robots", (C.c_double * NLINKS) * MAX_ROBOTS),
+        ("link_mask", C.c_int * MAX_ROBOTS),
     ]
 
 
@@ -51,6 +52,7 @@ def lib():
         _lib.mrfo_endeffector.argtypes = [cp, C.c_int, d, d, C.c_int, d, d]
         _lib.mrfo_action.argtypes = [cp, C.c_int, d, C.c_int, d, d, d, d, d, d]
         _lib.mrfo_rollout_jointspace.argtypes = [cp, d, C.c_int, d, d, d, d]
+        _lib.mrfo_rollout_jointspace_static.argtypes = [cp, d, C.c_int, C.c_int, d, d, d, d, d, d]
         _lib.mrfo_rollout_cartesian.argtypes = [cp, C.c_int, d, C.c_int, d, d, d, C.c_int, d, d, d]
         _lib.mrfo_rollout_jointspace_batch.argtypes = [cp, d, C.c_long, C.c_int, d, d, d, d, C.c_int]
         _lib.mrfo_action_batch.argtypes = [cp, C.c_int, d, C.c_long, C.c_int, d, d, d, d, d, C.c_int]
@@ -127,6 +129,25 @@ def rollout_jointspace(cfg, rec, N, n_threads=0):
     if single:
         return qN[0], qdN[0], avg[0], xee[0]
     return qN, qdN, avg, xee
+
+
+def rollout_jointspace_static(cfg, rec, N, xs, rs):
+    """One scenario: rec (R,44), static spheres xs (R,S,3), rs (R,S) per robot -> qN, qdN (R,N,7), avg_vel (R,), x_ee (R,3)."""
+    rec, xs, rs = _c(rec), _c(xs), _c(rs)
+    R = cfg.n_robots
+    S = rs.shape[1]
+    qN, qdN, avg, xee = np.zeros((R, N, 7)), np.zeros((R, N, 7)), np.zeros(R), np.zeros((R, 3))
+    rc = lib().mrfo_rollout_jointspace_static(C.byref(cfg), _p(rec), N, S, _p(xs), _p(rs), _p(qN), _p(qdN), _p(avg), _p(xee))
+    if rc == 2:
+        raise ValueError("too many static spheres")
+    return qN, qdN, avg, xee
+
+
+def set_collision_links(cfg, links_per_robot):
+    """collision_links_nrs: per robot a list of link numbers 1..8 -> cfg.link_mask."""
+    for r, links in enumerate(links_per_robot):
+        cfg.link_mask[r] = sum(1 << (int(l) - 1) for l in set(links))
+    return cfg
 
 
 def rollout_jointspace_avg(cfg, rec, N, n_threads=0):

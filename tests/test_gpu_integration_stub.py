@@ -20,7 +20,7 @@ class MrfConfig(C.Structure):          # field order of include/mrf_b200.h (as i
                 ("dl_avg_vel_constant", C.c_double), ("dl_dist_constant", C.c_double),
                 ("dl_goal_weight_follower", C.c_double), ("dl_goal_weight_leader", C.c_double),
                 ("dl_nr_goal_scale", C.c_double), ("dl_dist_endeff", C.c_double), ("dl_backoff", C.c_double),
-                ("dl_time_wait", C.c_int32), ("dl_time_gate", C.c_int32)]
+                ("dl_time_wait", C.c_int32), ("dl_time_gate", C.c_int32), ("collision_link_mask", C.c_int32 * 4)]
 
 
 def test_integration_md_stub(built):

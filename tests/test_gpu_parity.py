@@ -514,3 +514,103 @@ def test_submit_wait_pipeline_equals_blocking_call(built):
         for k in ref:
             assert np.array_equal(out[k].view(np.uint8), ref[k].view(np.uint8)), k
     fab.close()
+
+
+@pytest.mark.parametrize("kernel", ["throughput", "cooperative"])
+@pytest.mark.parametrize("links", [[[5], [5]], [[3, 6, 8], [1, 2, 4, 7]], [[1, 2, 3, 4, 5, 6, 7, 8], [2, 6]]])
+def test_rollout_collision_link_subsets(fabs, kernel, links):
+    """arbitrary collision_links_nr per robot (signature default [5],
+    example_pandas_Jointspace.py:64).  The links in a robot's set are its ego leaves (link3..8) AND the spheres the other
+    robots see; different radii on link5 / link6 exercise the shared-point logic."""
+    R, N, B = 2, 10, 48
+    rec = m.scenarios.generate(B, R, seed=31)
+    rr = [[0.08, 0.06, 0.08, 0.08, 0.07, 0.09, 0.08, 0.08], [0.05, 0.05, 0.08, 0.1, 0.08, 0.08, 0.06, 0.08]]
+    for r in range(R):
+        rec[:, r, o2.RB:o2.RB + 6] = [0.08 if (l in links[r]) else 0.0 for l in range(3, 9)]
+    rec[:, 0, o2.RB + 3] = 0.07 if 6 in links[0] else 0.0       # link6 radius differs from link5
+    fab = Fabrics(R, device=0, collision_links=links, r_robots=rr)
+    fab.handle.set_coop_max_batch(0 if kernel == "throughput" else 1 << 20)
+    ocfg = o2.set_collision_links(o2.default_config(R), links)
+    for r in range(R):
+        for l in range(8):
+            ocfg.r_robots[r][l] = rr[r][l]
+    qN, qdN, avg, _ = o2.rollout_jointspace(ocfg, rec, N)
+    ok = np.isfinite(qdN).all(axis=(1, 2, 3)) & (np.abs(qdN).max(axis=(1, 2, 3)) < 3)
+    assert ok.sum() > 0.8 * B
+    out = fab.rollout_host(rec, N, dtype="f64", trajectories=True)
+    assert rel_ps(out["qdN"], qdN, ok) < F64_RTOL and rel_ps(out["avg_vel"], avg, ok) < F64_RTOL
+    out32 = fab.rollout_host(rec, N, dtype="f32", trajectories=True)
+    assert np.quantile(np.abs(out32["qdN"] - qdN).max(axis=(1, 2, 3))[ok], 0.9) < 1e-4
+    # the executed action with the same subsets (action kernel: ego-major FP64 and obstacle-major FP32 paths)
+    rng = np.random.default_rng(4)
+    obst = random_obstacles(rng, B, R, 9, rec)
+    ref = np.full((B, R, 7), np.nan)
+    for b in range(B):
+        for r in range(R):
+            o = obst[b, r]
+            try:
+                ref[b, r] = o2.action(ocfg, r, rec[b, r], o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+            except FloatingPointError:
+                pass
+    okb = np.isfinite(ref).all(axis=(1, 2))
+    act = fab.action_host(rec, obst, dtype="f64")
+    assert rel_ps(act, ref, okb) < F64_RTOL
+    act32 = fab.action_host(rec, obst, dtype="f32")
+    assert np.abs(act32 - ref)[okb].max() < 2e-3
+    fab.close()
+
+
+@pytest.mark.parametrize("R,S", [(2, 2), (3, 5)])
+def test_rollout_with_static_spheres(fabs, R, S):
+    """static spheres inside the coupled rollouts (x_obsts / radius_obsts of the rollout planners,
+    forward_planner_Jointspace.py:319-322) through mrf_rollout_static_dev, against the oracle."""
+    import torch
+    N, B = 12, 40
+    rec = m.scenarios.generate(B, R, seed=33)
+    rng = np.random.default_rng(6)
+    stat = np.zeros((B, R, S, 4))
+    stat[..., 0:3] = rng.uniform([-0.4, -1.0, 1.5], [1.4, 1.0, 2.2], size=(B, R, S, 3))     # above the arms' workspace
+    stat[:, :, 0, 0:3] = rng.uniform([0.0, -0.6, 0.9], [1.0, 0.6, 1.4], size=(B, R, 3))      # one inside it
+    stat[..., 3] = rng.uniform(0.05, 0.12, size=(B, R, S))
+    ocfg = o2.default_config(R)
+    qdN, avg = np.zeros((B, R, N, 7)), np.zeros((B, R))
+    for b in range(B):
+        _, qdN[b], avg[b], _ = o2.rollout_jointspace_static(ocfg, rec[b], N, stat[b, :, :, 0:3], stat[b, :, :, 3])
+    plain = o2.rollout_jointspace(ocfg, rec, N)[1]
+    with np.errstate(invalid="ignore"):
+        ok = np.isfinite(qdN).all(axis=(1, 2, 3)) & (np.abs(qdN).max(axis=(1, 2, 3)) < 3)
+    assert ok.sum() > 0.6 * B and np.abs(plain - qdN)[ok].max() > 1e-4       # the static spheres matter
+    fab = get_fab(fabs, R)
+    for dt, tol in ((torch.float64, None), (torch.float32, 1e-4)):
+        dev = "cuda:0"
+        d_rec = torch.from_numpy(to_soa(rec)).to(dev, dtype=dt)
+        d_st = torch.from_numpy(np.ascontiguousarray(stat.transpose(2, 3, 1, 0))).to(dev, dtype=dt)
+        q_o = torch.empty((R, N, 7, B), dtype=dt, device=dev)
+        a_o = fab.rollout_static_dev(d_rec, d_st, N, qdN=q_o)
+        torch.cuda.synchronize()
+        got = q_o.permute(3, 0, 1, 2).double().cpu().numpy()
+        if tol is None:
+            assert rel_ps(got, qdN, ok) < F64_RTOL and rel_ps(a_o.T.cpu().numpy(), avg, ok) < F64_RTOL
+        else:
+            assert np.quantile(np.abs(got - qdN).max(axis=(1, 2, 3))[ok], 0.9) < tol
+    with pytest.raises(m.MrfError):
+        fab.rollout_static_dev(d_rec, torch.zeros((17, 4, R, B), dtype=dt, device=dev), N)     # > MRF_MAX_STATIC
+
+
+def test_cartesian_rollout_acc_mode(fabs):
+    """decoupled rollouts in fabrics_mode 'acc' (FabricsRollouts' constructor default,
+    forward_planner_Cartesian.py:20,81-84): the action is qdd, pos += dt vel + dt^2/2 qdd, vel += dt qdd."""
+    N, S, B = 10, 6, 32
+    rng = np.random.default_rng(8)
+    rec = m.scenarios.generate(B, 2, seed=35, weight_goal_1=20.0)[:, :1]
+    obst = random_obstacles(rng, B, 1, S, rec)
+    fab = Fabrics(2, device=0, mode=0)
+    ocfg = o2.default_config(2, mode=0)
+    avg, qN, qdN = fab.rollout_cart_host(0, rec[:, 0], obst[:, 0], N, dtype="f64")
+    for b in range(B):
+        rq, rqd, ravg = o2.rollout_cartesian(ocfg, 0, rec[b, 0], obst[b, 0, :, 0:3], obst[b, 0, :, 3:6], obst[b, 0, :, 9], N)
+        if not np.isfinite(rqd).all() or np.abs(rqd).max() > 3:
+            continue
+        assert np.abs(qdN[b] - rqd).max() < 1e-9 * max(1.0, np.abs(rqd).max()) and np.abs(qN[b] - rq).max() < 1e-9
+        assert abs(avg[b] - ravg) < 1e-9 * max(1.0, abs(ravg))
+    fab.close()

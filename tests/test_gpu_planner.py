@@ -228,6 +228,53 @@ def test_deadlock_dropin_matches_reference_golden(built):
     assert raised > 50
 
 
+def test_dropin_collision_link_subset_and_static_rollout_obstacles(built):
+    """The reference's signature default collision_links_nr=[5] (example_pandas_Jointspace.py:64) through
+    set_planner_panda / compute_action, and rollout planners with static obstacles (nr_obsts > 0,
+    forward_planner_Jointspace.py:319-322) through ForwardFabricsPlanner -- both against the oracle."""
+    rng = np.random.default_rng(12)
+    rec = m.scenarios.generate(1, 2, seed=59, weight_goal_1=20.0)
+    S = 4
+    obst = random_obstacles(rng, 1, 2, S, rec)
+    for links in ([5], [4, 7, 8]):
+        pl, _ = P.set_planner_panda(7, 0, S, links, {}, MOUNT, 1)
+        r, o = rec[0, 1], obst[0, 1]
+        kw = dict(q=r[0:7], qdot=r[7:14], x_goal_0=r[14:17], weight_goal_0=r[17], angle_goal_1=P.ROT_PANDA,
+                  x_goal_1=r[18:21], weight_goal_1=20.0, x_goal_2=r[22:23], weight_goal_2=1.0, x_obsts=[], radius_obsts=[],
+                  constraint_0=r[33:37], radius_body_panda_links={str(l): np.array(0.08) for l in links},
+                  radius_body_panda_hand=np.array(0.02), x_obsts_dynamic=[o[k, 0:3] for k in range(S)],
+                  xdot_obsts_dynamic=[o[k, 3:6] for k in range(S)], xddot_obsts_dynamic=[o[k, 6:9] for k in range(S)],
+                  radius_obsts_dynamic=[o[k, 9] for k in range(S)])
+        act = pl.compute_action(**kw)
+        ocfg = o2.set_collision_links(o2.default_config(2), [LINKS, links])
+        rr = r.copy()
+        rr[37:43] = [0.08 if l in links else 0.0 for l in range(3, 9)]
+        ref = o2.action(ocfg, 1, rr, o[:, 0:3], o[:, 3:6], o[:, 6:9], o[:, 9])
+        assert np.abs(act - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+        with pytest.raises(KeyError):
+            pl.compute_action(**dict(kw, radius_body_panda_links={}))
+    # rollouts with two static spheres per robot
+    R, N, Ss = 2, 8, 2
+    rec = m.scenarios.generate(1, R, seed=60)
+    params = make_params(R, N)
+    params.nr_obsts = [Ss] * R
+    params.radius_obsts = [[0.1, 0.07]] * R
+    planners = [P.set_planner_panda(7, Ss, 8 * (R - 1), LINKS, {}, MOUNT, i)[0] for i in range(R)]
+    fwd = P.ForwardFabricsPlanner(params, planners, N_steps=N)
+    xs = rng.uniform([0.1, -0.5, 0.95], [0.9, 0.5, 1.4], size=(R, Ss, 3))
+    ia = {"q_robots": [rec[0, i, 0:7] for i in range(R)], "q_dot_robots": [rec[0, i, 7:14] for i in range(R)],
+          "x_obsts": [[xs[i, o] for o in range(Ss)] for i in range(R)], "x_goals0": [rec[0, i, 14:17] for i in range(R)],
+          "x_goals1": [rec[0, i, 18:21] for i in range(R)], "x_goals2": [rec[0, i, 22:23] for i in range(R)],
+          "weight_goals0": [rec[0, i, 17] for i in range(R)], "weight_goals1": [rec[0, i, 21] for i in range(R)],
+          "weight_goals2": [rec[0, i, 23] for i in range(R)], "constraints": [rec[0, i, 33:37] for i in range(R)]}
+    qN, qdN, avg, _ = o2.rollout_jointspace_static(o2.default_config(R), rec[0], N, xs, np.array(params.radius_obsts))
+    va = fwd.get_velocity_rollouts(ia)
+    assert np.abs(np.array([v[0] for v in va]) - avg).max() < 1e-9
+    q_n, qd_n, _ = fwd.rollouts_numerical(ia)
+    for i in range(R):
+        assert np.abs(qd_n[f"robot_{i}"][0] - qdN[i].T).max() < 1e-9 and np.abs(q_n[f"robot_{i}"][0] - qN[i].T).max() < 1e-9
+
+
 def test_deadlock_dropin_point_mass_branch(built):
     """deadlockprevention with dof[0] == 2 (deadlock_prevention.py:12-19): the kernel with the point-mass constants
     replays sequences produced by the reference's own class bit for bit; planar (2-D) positions behave like the

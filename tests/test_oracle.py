@@ -100,6 +100,37 @@ def test_o1_live_matches_o2_small(built):
     assert np.abs(a1 - a2).max() < 1e-11
 
 
+def test_o1_matches_o2_link_subset_and_static_spheres(built):
+    """Generic leaf set: an arbitrary collision_links_nr subset (the reference's signature default is
+    [5], example_pandas_Jointspace.py:64) and static spheres x_obst_i next to dynamic ones -- closed form (O2) against the
+    autodiff derivation (O1)."""
+    from oracle import o1_fabrics as o1
+    rng = np.random.default_rng(5)
+    rec = o2.make_record([0.9, 0.2, 0.1, -1.6, 0.2, 1.8, 0.5], rng.uniform(-0.5, 0.5, 7), [0.5, 0.1, 1.0], 2.0)
+    dyn = np.array([[0.6, 0.2, 1.2, 0.1, -0.2, 0.05, 0.3, 0.1, -0.2, 0.08]])
+    stat = np.array([[0.3, -0.4, 1.1, 0.07], [0.9, 0.5, 1.3, 0.1]])
+    for links in ([5], [3, 6, 8], [1, 2, 4, 7]):
+        cfg = o2.set_collision_links(o2.default_config(2), [[1, 2, 3, 4, 5, 6, 7, 8], links])
+        pl = o1.make_panda_planner(o2.mount_of(cfg, 1), n_dyn=1, n_static=2,
+                                   collision_links=[f"panda_link{l}" for l in links])
+        r = rec.copy()
+        r[o2.RB:o2.RB + 6] = [0.08 if (l in links) else 0.0 for l in range(3, 9)]
+        p = o2.record_to_params(r)
+        p.update(x_obst_dynamic_0=dyn[0, 0:3], xdot_obst_dynamic_0=dyn[0, 3:6], xddot_obst_dynamic_0=dyn[0, 6:9],
+                 radius_obst_dynamic_0=dyn[0, 9], x_obst_0=stat[0, 0:3], radius_obst_0=stat[0, 3], x_obst_1=stat[1, 0:3],
+                 radius_obst_1=stat[1, 3])
+        a1, _ = pl.action_raw(r[0:7], r[7:14], p)
+        # O2: static spheres are spheres at rest in the same list
+        xo = np.vstack([stat[:, 0:3], dyn[:, 0:3]])
+        vo = np.vstack([np.zeros((2, 3)), dyn[:, 3:6]])
+        ao = np.vstack([np.zeros((2, 3)), dyn[:, 6:9]])
+        ro = np.concatenate([stat[:, 3], dyn[:, 9]])
+        a2 = o2.action(cfg, 1, r, xo, vo, ao, ro)
+        assert np.abs(a1 - a2).max() < 1e-11, links
+    full = o2.action(o2.default_config(2), 1, rec, xo, vo, ao, ro)
+    assert np.abs(full - a2).max() > 1e-6                    # the subset really changes the action
+
+
 def test_jdot_sign_and_eps_are_live_knobs(built):
     """The restatement assumptions are configuration, not constants: changing them changes the action."""
     rec = o2.make_record([0.9, 0.2, 0.1, -1.6, 0.2, 1.8, 0.5], [0.3, -0.2, 0.4, 0.1, -0.3, 0.2, 0.1], [0.5, 0.1, 1.0])
