@@ -417,7 +417,7 @@ def ours(a):
     launches0 = fab.handle.launches
     torch.cuda.synchronize()
     sampler.start()
-    if os.environ.get("MRF_BENCH_GUARD_BANDS"):      # diagnostics: override the guard tiers, e.g. "0,0,0"
+    if os.environ.get("MRF_BENCH_GUARD_BANDS"):      # diagnostics: override the guard tiers, e.g. "0,0,0,0,0,0"
         fab.set_guard(bands=[float(v) for v in os.environ["MRF_BENCH_GUARD_BANDS"].split(",")])
     sw = _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup,
                 with_risk=os.environ.get("MRF_BENCH_NORISK", "0") != "1")

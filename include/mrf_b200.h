@@ -240,12 +240,13 @@ int mrf_rollout_risk_dev_f32(mrf_handle_t h, const float* rec, int N, float* avg
                              float* risk, int64_t B, void* stream);
 int mrf_rollout_risk_dev_f64(mrf_handle_t h, const double* rec, int N, double* avg_vel, double* x_ee, double* goal_est,
                              double* risk, int64_t B, void* stream);
-/* Guard bands of mrf_rfcv_post_dev_f32 (NULL / negative = keep).  A scenario is re-rolled in FP64 when
- * |vel_avg_tot - dl_avg_vel_constant| <= bands[t], t = (risk >= risk_edges[0]) + (risk >= risk_edges[1]) -- three
- * stiffness tiers; defaults bands = {2e-5, 4e-3, 0.5}, risk_edges = {40, 200}, calibrated against the FP64 kernel on
- * 4 x 65536 random scenarios (profiles/r2_guard_calibration.md) -- or when an end-effector distance is within band_dist
- * (1e-5) of dl_dist_endeff / of a competing distance, or when the FP32 result is non-finite.  cap = most scenarios
- * re-rolled per call (0 = max(256, B / 16)); the excess is counted as overflow and decided in FP32. */
+/* Guard bands of mrf_rfcv_post_dev_f32 (NULL / negative = keep).  A scenario with a candidate pair is re-rolled in FP64
+ * when |vel_avg_tot - dl_avg_vel_constant| <= bands[t] + bands[3 + t] * vel_avg_tot, with the stiffness tier
+ * t = (risk >= risk_edges[0]) + (risk >= risk_edges[1]); defaults bands = {2e-5, 4e-3, 4e-3, 0, 0.02, 0.4} (absolute,
+ * relative), risk_edges = {40, 200}, calibrated against the FP64 kernel on 4 x 65536 random scenarios
+ * (profiles/r2_guard_calibration.md) -- or when an end-effector distance is within band_dist (1e-5) of dl_dist_endeff / of
+ * a competing distance, or when the FP32 result is non-finite.  cap = most scenarios re-rolled per call
+ * (0 = max(256, B / 16)); the excess is counted as overflow and decided in FP32. */
 int mrf_set_guard(mrf_handle_t h, const double* bands, const double* risk_edges, double band_dist, int64_t cap);
 /* out[0] = scenarios re-rolled in FP64 so far, out[1] = overflow so far, out[2] = listed by the last call.  Synchronise
  * the streams the post steps ran on first. */

@@ -265,8 +265,8 @@ class Fabrics:
         return flag
 
     def set_guard(self, bands=None, risk_edges=None, band_dist=-1.0, cap=-1):
-        """mrf_set_guard: bands (3,), risk_edges (2,) of the FP64 re-roll tiers; None / negative = keep."""
-        b = None if bands is None else (C.c_double * 3)(*[float(v) for v in bands])
+        """mrf_set_guard: bands (6,) = absolute then relative band per tier, risk_edges (2,); None / negative = keep."""
+        b = None if bands is None else (C.c_double * 6)(*[float(v) for v in bands])
         e = None if risk_edges is None else (C.c_double * 2)(*[float(v) for v in risk_edges])
         check(lib().mrf_set_guard(self.handle.ptr, b, e, band_dist, cap), "mrf_set_guard")
 

@@ -478,7 +478,7 @@ __global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restri
 struct GuardCfg {
     int R, est_robot;
     double c_avg, c_dist, band_dist;
-    double band[3], edge[2]; // |vel_avg_tot - c_avg| <= band[t], tier t = (risk >= edge[0]) + (risk >= edge[1])
+    double band[3], rel[3], edge[2]; // |vel_avg_tot - c_avg| <= band[t] + rel[t] vel_avg_tot, tier t = (risk >= edge[0]) + (risk >= edge[1])
     unsigned cap;
 };
 // counters: [0] listed this call (may exceed cap), [1] not used, [2] cumulative re-rolled, [3] cumulative overflow
@@ -532,7 +532,8 @@ __global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, c
     bool guard = false;
     if (cand) {
         const double da = fabs(s - c.c_avg);
-        const double band = c.band[(rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0)];
+        const int tier = (rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0);
+        const double band = c.band[tier] + c.rel[tier] * fabs(s);
         guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk);   // non-finite FP32 rollout
         guard = guard || da <= band;                                   // velocity knife edge, widened by stiffness tier
         guard = guard || (knife && s < c.c_avg + band);                // geometric knife edges matter if the velocity test can pass
@@ -916,7 +917,7 @@ struct MrfHandle_ {
     int zc_pending[2];        // submissions in flight per pipeline slot
     int zc_oldest;
     // FP64 re-roll of guard-band scenarios (mrf_rfcv_post_dev_f32)
-    double guard_band[3], guard_edge[2], guard_band_dist;
+    double guard_band[3], guard_rel[3], guard_edge[2], guard_band_dist;
     long long guard_cap;      // 0 = max(256, B / 16)
     long long guard_coop_max; // capacities up to this re-roll with the cooperative kernel
     void* guard_buf[MRF_GUARD_SLOTS];   // per scratch slot: list, slot_of, compact FP64 records and results
@@ -1030,11 +1031,15 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->d_tail[0] = h->d_tail[1] = nullptr;
     // defaults calibrated on B200 (tools/guard_probe.py, profiles/r2_guard_calibration.md)
     // FP32 error of vel_avg_tot against FP64 over 4 x 65536 random scenarios, by stiffness tier: risk < 40: max 7e-6;
-    // 40..200: max 9.3e-4; >= 200: up to O(1) (explicit-Euler blow-ups near contact).  A flag can only flip if
-    // |vel_avg_tot - 0.16| <= 2 x that error, hence the bands.
+    // 40..200: max 9.3e-4; >= 200: max 3.1e-4 while the rollout stays calm (vel_avg_tot < 1), and up to 15 % of
+    // vel_avg_tot when it blows up in both precisions (explicit Euler near contact, vel_avg_tot 2..160).  A flag can only
+    // flip if |vel_avg_tot - 0.16| <= that error, hence an absolute plus a relative band per tier (margins: 3x, 4x, 13x / 2.7x).
     h->guard_band[0] = 2e-5;
     h->guard_band[1] = 4e-3;
-    h->guard_band[2] = 0.5;
+    h->guard_band[2] = 4e-3;
+    h->guard_rel[0] = 0.0;
+    h->guard_rel[1] = 0.02;
+    h->guard_rel[2] = 0.4;
     h->guard_edge[0] = 40.0;
     h->guard_edge[1] = 200.0;
     h->guard_band_dist = 1e-5;
@@ -1371,7 +1376,8 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
         int* slot_of = list + cap;
         unsigned* counters = h->d_sync + 8 + 4 * slot; // [0] is zero on entry: reset by the previous call's deadlock kernel
         GuardCfg g{R, est ? h->cfg.estimate_robot : -1, h->cfg.dl_avg_vel_constant, h->cfg.dl_dist_endeff, h->guard_band_dist,
-                   {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
+                   {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_rel[0], h->guard_rel[1], h->guard_rel[2]},
+                   {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
         const long long sel_blocks = (B + 255) / 256;
         guard_select_kernel<T><<<(unsigned)(sel_blocks < 64 ? sel_blocks : 64), 256, 0, st>>>(
             g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk, sm_state, time_step, h->cfg.dl_time_gate,
@@ -1415,7 +1421,10 @@ extern "C" int mrf_rollout_risk_dev_f64(mrf_handle_t h, const double* rec, int N
 extern "C" int mrf_set_guard(mrf_handle_t h, const double* bands, const double* risk_edges, double band_dist, int64_t cap) {
     if (!h) return fail(MRF_EINVAL, "mrf_set_guard: null handle");
     if (bands)
-        for (int i = 0; i < 3; ++i) h->guard_band[i] = bands[i];
+        for (int i = 0; i < 3; ++i) {
+            h->guard_band[i] = bands[i];
+            h->guard_rel[i] = bands[3 + i];
+        }
     if (risk_edges) {
         if (!(risk_edges[0] <= risk_edges[1])) return fail(MRF_EINVAL, "mrf_set_guard: risk_edges must be ascending");
         h->guard_edge[0] = risk_edges[0];
