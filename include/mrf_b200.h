@@ -369,6 +369,9 @@ typedef struct MrfEpisode {
     void* fsm_above;            /* T [R][3][B] in/out */
     int32_t* fsm_st;            /* [6][R][B] in/out, rows as in mrf_fsm_dev_*; state initial 1 */
     void* grip_action;          /* T [R][2][B] out */
+    int32_t* nonfinite_steps;   /* [B] in/out, nullable: control steps in which an executed action was non-finite (the arm
+                                   then holds still for that step); FP32 near-contact divergence shows up here instead of
+                                   vanishing into the success / clearance metrics */
 } MrfEpisode;
 int mrf_episode_step_dev_f64(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);
 int mrf_episode_step_dev_f32(mrf_handle_t h, const MrfEpisode* ep, int64_t B, void* stream);

@@ -53,7 +53,7 @@ class MrfEpisode(C.Structure):
         ("done_at", C.c_void_p), ("deadlock_steps", C.c_void_p), ("min_clearance", C.c_void_p),
         ("pick_and_place", C.c_int32), ("n_blocks", C.c_int32), ("blocks", C.c_void_p), ("start_goal", C.c_void_p),
         ("q_grip", C.c_void_p), ("goal_block", C.c_void_p), ("fsm_above", C.c_void_p), ("fsm_st", C.c_void_p),
-        ("grip_action", C.c_void_p),
+        ("grip_action", C.c_void_p), ("nonfinite_steps", C.c_void_p),
     ]
 
 

@@ -2167,11 +2167,12 @@ __global__ void episode_post_kernel(T* __restrict__ rec, const T* __restrict__ a
                                     const T* __restrict__ goal0, const T* __restrict__ sx, int S, const int32_t* __restrict__ flag,
                                     EpLimits lim, T dt, T eps, T rsum, int32_t* __restrict__ tstep, int32_t* __restrict__ done_at,
                                     int32_t* __restrict__ deadlock_steps, T* __restrict__ min_clear, int R, long long B,
-                                    const int32_t* __restrict__ sm, T* __restrict__ q_grip, const T* __restrict__ grip_action) {
+                                    const int32_t* __restrict__ sm, T* __restrict__ q_grip, const T* __restrict__ grip_action,
+                                    int32_t* __restrict__ nonfinite_steps) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const long long RB = (long long)R * B;
-    bool reached = true;
+    bool reached = true, bad = false;
     for (int r = 0; r < R; ++r) {
         const long long idx = (long long)r * B + b;
         const int state = sm != nullptr ? sm[idx] : 0;
@@ -2180,7 +2181,7 @@ __global__ void episode_post_kernel(T* __restrict__ rec, const T* __restrict__ a
             const T l = (T)lim.v[i];
             T a = act[(long long)i * RB + idx];
             a = a < -l ? -l : (a > l ? l : a);
-            if (!(a - a == T(0))) a = T(0); // non-finite action: hold still
+            if (!(a - a == T(0))) { a = T(0); bad = true; } // non-finite action: hold still, and count the step
             if (state == 3 || state == 5) a = T(0); // gripping / releasing: the arm holds still (:418-419)
             rec[(MRF_QD + i) * RB + idx] = a;
             rec[(MRF_Q + i) * RB + idx] += a * dt;
@@ -2225,6 +2226,7 @@ __global__ void episode_post_kernel(T* __restrict__ rec, const T* __restrict__ a
         min_clear[b] = mc;
     }
     if (flag != nullptr && deadlock_steps != nullptr) deadlock_steps[b] += flag[b];
+    if (nonfinite_steps != nullptr && bad) nonfinite_steps[b] += 1;
     tstep[b] = t + 1;
 }
 
@@ -2313,7 +2315,8 @@ template <typename T> static int episode_step_dev(mrf_handle_t h, const MrfEpiso
         rec, (const T*)ep->action, xee, link_major, (const T*)ep->goal0, R > 1 ? (const T*)ep->spheres_x : nullptr, S1,
         (ep->rollout_fabrics && ep->resolve_deadlocks && R >= 2) ? ep->flag : nullptr, lim, (T)h->cfg.dt, (T)ep->epsilon,
         (T)ep->clearance_radius_sum, ep->time_step, ep->done_at, ep->deadlock_steps, (T*)ep->min_clearance, R, (long long)B,
-        pnp ? sm_state : nullptr, pnp ? (T*)ep->q_grip : nullptr, pnp ? (const T*)ep->grip_action : nullptr);
+        pnp ? sm_state : nullptr, pnp ? (T*)ep->q_grip : nullptr, pnp ? (const T*)ep->grip_action : nullptr,
+        ep->nonfinite_steps);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
     return MRF_OK;

@@ -58,6 +58,7 @@ class BatchedEpisodes:
         # metrics
         self.done_at = torch.full((B,), -1, dtype=torch.int32, device=self.dev)
         self.deadlock_steps = z(B, dt=torch.int32)
+        self.nonfinite_steps = z(B, dt=torch.int32)     # control steps with a non-finite executed action (arm held still)
         self.min_clear = torch.full((B,), 100.0, dtype=self.tdt, device=self.dev)   # :231 min_clearance = 100
         self.sx = z(8 * self.n_per_link, 3, R, B)
         # pick-and-place task: blocks (B, n_blocks, R, 3) rest positions, start_goal (B, R, 3)
@@ -100,6 +101,7 @@ class BatchedEpisodes:
         ep.kin_scratch = p(getattr(self, "kin_scratch", None))
         ep.sm_state, ep.time_step, ep.time_deadlock_out, ep.st_int, ep.st_goal = p(self.sm), p(self.tstep), p(self.tdo), p(self.st_int), p(self.st_goal)
         ep.flag, ep.done_at, ep.deadlock_steps, ep.min_clearance = p(self.flag), p(self.done_at), p(self.deadlock_steps), p(self.min_clear)
+        ep.nonfinite_steps = p(self.nonfinite_steps)
         if self.pick_and_place:
             ep.pick_and_place, ep.n_blocks = 1, self.n_blocks
             ep.blocks, ep.start_goal, ep.q_grip, ep.goal_block = p(self.blocks), p(self.start_goal), p(self.q_grip), p(self.goal_block)
@@ -147,6 +149,7 @@ class BatchedEpisodes:
                      "q_grip": self.q_grip.permute(2, 0, 1).double().cpu().numpy()}
         return {**extra, "steps": self.steps_done, "success": done >= 0, "steps_to_success": done,
                 "deadlock_steps": self.deadlock_steps.cpu().numpy(),
+                "nonfinite_steps": self.nonfinite_steps.cpu().numpy(),
                 "min_clearance": self.min_clear.double().cpu().numpy(),
                 "q": self.rec[Q:Q + 7].permute(2, 1, 0).double().cpu().numpy(),
                 "x_ee": (self.xee.permute(2, 0, 1) if (self.rollout_fabrics or self.pick_and_place) else

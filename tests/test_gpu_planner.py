@@ -492,7 +492,14 @@ def test_closed_loop_episodes_match_cpu_loop(built, R, kw):
         n_cmp += 1
         assert np.abs(res["q"][b] - q).max() < 1e-7, b
         assert res["deadlock_steps"][b] == n_flags and res["steps_to_success"][b] == done_at
+        assert res["nonfinite_steps"][b] == 0          # an episode the oracle follows has no non-finite action
     assert n_cmp >= B - 3 and res["steps"] == T
+    # a scenario started beyond a joint limit loses positive definiteness (NaN action): the arm holds still and the step
+    # is COUNTED instead of silently vanishing from the metrics
+    bad = rec[:2].copy()
+    bad[0, 0, 3], bad[0, 0, 10] = 0.5, 0.3               # joint 4 above its upper limit (-0.0698), moving further out
+    rb = BatchedEpisodes(bad, n_horizon=N, dtype="f64", n_obst_per_link=2, use_graph=False, **kw).run(3).results()
+    assert rb["nonfinite_steps"][0] >= 1
 
 
 def test_deadlock_in_place_on_record_tensor(built):
