@@ -1191,12 +1191,18 @@ static int action_dev(mrf_handle_t h, int robot_first, int n_rob, const T* rec, 
         return fail(MRF_EINVAL, "mrf_action: bad sizes");
     if (CART && N <= 0) return fail(MRF_EINVAL, "mrf_rollout_cart: needs N > 0");
     MRF_CUDA(cudaSetDevice(h->device));
-    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N + kObstRing * MRF_OBST) * kActThreads;
+    // FP64: the per-thread tables (point table + axes + parameters + sphere ring: 142 doubles) bound the occupancy through
+    // shared memory -- 128-thread CTAs fit once per SM (4 warps, one per scheduler: the FP64 pipe idles on every dependent
+    // DFMA), one-warp CTAs six times (6 warps).  Measured (65 536 scenarios, Cartesian rollout S = 32 / 64): 6.09 / 30.9 ms
+    // at 128 threads, 4.77 / 23.8 at 64, 4.63 / 23.0 at 32.
+    static const int env_thr = getenv("MRF_ACTION_THREADS_F64") ? atoi(getenv("MRF_ACTION_THREADS_F64")) : 32;
+    const int threads = sizeof(T) == 8 ? env_thr : kActThreads;
+    const size_t smem = sizeof(T) * (size_t)(kKinRows<T> + P_N + kObstRing * MRF_OBST) * threads;
     int rc = set_smem(action_kernel<T, CART>, smem);
     if (rc) return rc;
     const long long total = (long long)n_rob * B;
-    const long long grid = (total + kActThreads - 1) / kActThreads;
-    action_kernel<T, CART><<<(unsigned)grid, kActThreads, smem, (cudaStream_t)stream>>>(
+    const long long grid = (total + threads - 1) / threads;
+    action_kernel<T, CART><<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(
         devcfg<T>(h), robot_first, n_rob, rec, S, obst, N, out, qN, qdN, (long long)B, sm_state);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
