@@ -614,3 +614,39 @@ def test_cartesian_rollout_acc_mode(fabs):
         assert np.abs(qdN[b] - rqd).max() < 1e-9 * max(1.0, np.abs(rqd).max()) and np.abs(qN[b] - rq).max() < 1e-9
         assert abs(avg[b] - ravg) < 1e-9 * max(1.0, abs(ravg))
     fab.close()
+
+
+
+def test_full_size_c5_properties(fabs):
+    """BASELINE config C5 at full size (65 536 scenarios x 3 Pandas x horizon 50) through size-independent properties:
+    idempotence (the same batch twice -> bitwise equal), sharding (the halves rolled separately concatenate bitwise to the
+    whole), agreement of the FP32 kernel with the FP64 kernel in distribution, and the oracle on a sample of the batch."""
+    import torch
+    R, N, B = 3, 50, 65536
+    rec = m.scenarios.generate(B, R, seed=2025).astype(np.float32)
+    fab = get_fab(fabs, R, estimate_goal=1)
+    dev = "cuda:0"
+    d = torch.from_numpy(to_soa(rec)).to(dev)
+    a1 = fab.rollout_dev(d, N)
+    a2 = fab.rollout_dev(d, N)
+    h = B // 2
+    lo = fab.rollout_dev(d[:, :, :h].contiguous(), N)
+    hi = fab.rollout_dev(d[:, :, h:].contiguous(), N)
+    a64 = fab.rollout_dev(d.double(), N)
+    torch.cuda.synchronize()
+    assert torch.equal(a1.view(torch.int32), a2.view(torch.int32))
+    assert torch.equal(torch.cat([lo, hi], dim=1).view(torch.int32), a1.view(torch.int32))
+    # over 50 explicit-Euler steps ~1 % of random scenarios blow up to non-finite values -- in BOTH precisions (the reference
+    # would, too); FP32 must not lose more than a few per mille beyond those
+    f32ok = torch.isfinite(a1).all(dim=0).cpu().numpy()
+    f64ok = torch.isfinite(a64).all(dim=0).cpu().numpy()
+    assert f64ok.mean() > 0.97 and (f32ok | ~f64ok).mean() > 0.997
+    both = f32ok & f64ok
+    e = (a1.double() - a64).abs().amax(dim=0).cpu().numpy()[both]
+    assert np.median(e) < 1e-6 and np.quantile(e, 0.99) < 1e-3
+    idx = np.arange(0, B, B // 256)
+    ref = o2.rollout_rfcv(o2.default_config(R), rec[idx].astype(np.float64), N)
+    got = a64[:, torch.from_numpy(idx).to(dev)].T.cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        ok = np.isfinite(ref["avg_vel"]).all(axis=1) & (ref["avg_vel"].max(axis=1) < 2.0)
+    assert ok.sum() > 200 and rel_ps(got, ref["avg_vel"], ok) < F64_RTOL

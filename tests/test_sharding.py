@@ -25,6 +25,17 @@ def _worker(rank, world, port, B, q):
     avg, _ = o2.rollout_jointspace_avg(o2.default_config(2), rec[lo:hi], 3)
     local = torch.from_numpy(np.ascontiguousarray(avg.T))            # (R, B_local), scenario last like the kernels
     full = gather_results(local, B)
+    # the preallocated, equal-shard form bench.py uses for the sweep's one final exchange ([K][R+1][B] per rank)
+    from multi_robot_fabrics_b200.sharding import gather_into
+    mine = torch.full((3, 2, 4), float(rank))
+    out = torch.empty((world, 3, 2, 4))
+    gather_into(out, mine)
+    assert all(bool((out[r] == r).all()) for r in range(world))
+    try:
+        gather_into(torch.empty((world, 3, 2, 5)), mine)
+        raise AssertionError("shape mismatch not caught")
+    except ValueError:
+        pass
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()
