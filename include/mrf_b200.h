@@ -305,6 +305,19 @@ int mrf_rollout_host_submit_compact_f64(mrf_handle_t h, const double* rec_var, c
 int mrf_rollout_host_submit_compact_f32(mrf_handle_t h, const float* rec_var, const float* rec_shared, int N,
                                         float* avg_vel, float* x_ee, float* goal_est, int64_t B);
 int mrf_rollout_host_wait(mrf_handle_t h, int all);
+
+/* One RF-CV control step of a sweep END TO END from host memory, asynchronous like mrf_rollout_host_submit_* (same
+ * two-deep pipeline, same mrf_rollout_host_wait): get_velocity_rollouts -> vel_avg_tot -> deadlock_checking
+ * (example_pandas_Jointspace.py:354-385) for B scenarios.  The in-place rollout kernel reads the page-locked records
+ * (rec_shared == NULL: rec [B][R][MRF_REC]; else compact rec [B][R][18] + rec_shared [R][MRF_REC]) over PCIe and keeps its
+ * results on the device; the post step of mrf_rfcv_post_dev_f32 (FP64 guard re-roll -- the listed scenarios are read
+ * from the same host records -- and the deadlock heuristic) follows on the same stream; only
+ *   result    [R+1][B]  rows 0..R-1 = avg_vel per robot, row R = deadlock flag (page-locked, required)
+ *   goals_out [4][R][B] x_goal_0 (3 rows) and weight_goal_0 of every robot AFTER the heuristic (page-locked, nullable)
+ * travel back.  Stateless per batch: state-machine codes 0, the given time_step for every scenario, no deadlock history
+ * (time_deadlock_out = 1000).  n_robots >= 2. */
+int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const float* rec_shared, int N, int32_t time_step,
+                             float* result, float* goals_out, int64_t B);
 /*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */
 int mrf_kinematics_host_f64(mrf_handle_t h, const double* q, const double* qdot, double* x, double* v, double* a,
                             int64_t B);

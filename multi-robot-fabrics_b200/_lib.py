@@ -74,6 +74,7 @@ EXPORTS = [
     "mrf_rollout_host_submit_compact_f64", "mrf_rollout_host_submit_compact_f32",
     "mrf_rfcv_post_dev_f32", "mrf_rfcv_post_dev_f64", "mrf_rollout_risk_dev_f32", "mrf_rollout_risk_dev_f64",
     "mrf_set_guard", "mrf_guard_stats", "mrf_rollout_static_dev_f32", "mrf_rollout_static_dev_f64",
+    "mrf_rfcv_host_submit_f32",
 ]
 
 
@@ -111,6 +112,7 @@ def lib():
         getattr(L, f"mrf_rfcv_post_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32]
         getattr(L, f"mrf_rollout_static_dev_{p}").argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
         getattr(L, f"mrf_rollout_risk_dev_{p}").argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, vp]
+    L.mrf_rfcv_host_submit_f32.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64]
     L.mrf_set_guard.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, i64]
     L.mrf_guard_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mrf_point_action_dev_f64.argtypes = [vp, vp, i32, vp, i32, vp, vp, i64, vp]

@@ -112,6 +112,22 @@ class Fabrics:
         check(fn(self.handle.ptr, hptr(rec), N, hptr(out.get("avg_vel")), hptr(out.get("x_ee")), hptr(out.get("goal_est")),
                  rec.shape[0]), "mrf_rollout_host_submit")
 
+    def rfcv_host_submit(self, rec, N: int, result, shared=None, time_step: int = 100, goals_out=None):
+        """One whole RF-CV step of a sweep from host memory (mrf_rfcv_host_submit_f32): page-locked float32 records
+        rec (B,R,44) -- or compact (B,R,18) with shared (R,44) -- -> page-locked result (R+1,B): avg_vel rows + deadlock
+        flag; goals_out (4,R,B) optional.  Asynchronous: rollout_host_wait() before reading the results."""
+        R = self.n_robots
+        if rec.ndim != 3:
+            raise MrfError(f"rfcv_host_submit: rec must be (B,{R},F), got {rec.shape}")
+        B = rec.shape[0]
+        _chk_np("rec", rec, (B, R, 18 if shared is not None else REC), np.float32)
+        _chk_np("result", result, (R + 1, B), np.float32)
+        _chk_np("goals_out", goals_out, (4, R, B), np.float32)
+        if shared is not None:
+            shared = np.ascontiguousarray(shared, dtype=np.float32).reshape(R, REC)
+        check(lib().mrf_rfcv_host_submit_f32(self.handle.ptr, hptr(rec), hptr(shared), N, int(time_step), hptr(result),
+                                             hptr(goals_out), B), "mrf_rfcv_host_submit")
+
     def rollout_host_wait(self, all: bool = False):
         check(lib().mrf_rollout_host_wait(self.handle.ptr, 1 if all else 0), "mrf_rollout_host_wait")
 

@@ -49,14 +49,36 @@ namespace mrf {
 // tiles with the horizons of earlier ones.  Tiles are handed out by an atomic ticket and admitted to the bus in ticket
 // order, `window` tiles at a time (sync[0] = tickets, sync[1] = tiles loaded): without that every CTA of a wave would
 // share the bus, all would start -- and later finish -- together, and each wave would stall for its whole transfer.
+// the rarely used arguments of rollout_kernel
+template <typename T> struct RollExtra {
+    // STRIDE (FP64 re-roll of the guard band): count, list, and the FP32 records the listed scenarios are read from --
+    // element (field f, robot r, scenario b) at src[f * sf + r * sr + b * sb] (SoA device tensor or the caller's AoS host
+    // records); fields >= src_nvar come from src_tail [R][MRF_REC] (compact host records)
+    unsigned* n_live;
+    const float* src;
+    const int* list;
+    long long sf, sr, sb;
+    int src_nvar;
+    const float* src_tail;
+    // static spheres of the rollout planners (generic kernel): stat [n_static][4][R][B]
+    int n_static;
+    const T* stat;
+    // host-record mode feeding the device post step: results in the SoA layout of the device entries (not the caller's
+    // record order), and the goals / weight_goal_0 of every record into gw [4][R][B] for the deadlock heuristic
+    int out_soa;
+    T* gw;
+};
+
 template <typename T, int R, bool UNIFORM, bool AOS, bool STRIDE = false>
 __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROLLOUT_MINBLOCKS : MRF_ROLLOUT_MINBLOCKS_F64)
     rollout_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                    T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN, long long B,
                    unsigned* __restrict__ sync, unsigned window, int n_var, const T* __restrict__ rec_tail,
-                   T* __restrict__ risk, unsigned* __restrict__ n_live, const float* __restrict__ rec_f32,
-                   const int* __restrict__ list, long long B_src, int n_static, const T* __restrict__ stat) {
+                   T* __restrict__ risk, const __grid_constant__ RollExtra<T> ex) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* const n_live = ex.n_live;
+    const int n_static = ex.n_static;
+    const bool rec_order_out = AOS && !ex.out_soa; // results in the caller's record order (AoS) or in the device SoA layout
     // STRIDE (FP64 re-roll of the guard band): the scenarios are the first min(*n_live, B) entries of `list` -- produced
     // on the device by guard_select_kernel -- read from the FP32 records rec_f32 [44][R][B_src] (exact promotion); results
     // go to compact arrays of stride B.  The grid is a handful of CTAs that stride over the tiles, so only a few
@@ -111,9 +133,10 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         ld_stride = 1;
         tail += r * MRF_REC;
     }
-    const long long b_src = STRIDE ? (long long)list[bb] : 0;
+    const long long b_src = STRIDE ? (long long)ex.list[bb] : 0;
     auto ld = [&](int f) {
-        if (STRIDE) return (T)rec_f32[((long long)f * R + r) * B_src + b_src];
+        if (STRIDE)
+            return f < ex.src_nvar ? (T)ex.src[f * ex.sf + r * ex.sr + b_src * ex.sb] : (T)ex.src_tail[r * MRF_REC + f];
         return AOS ? (f < n_var ? ld_base[f] : tail[f]) : rec[((long long)f * R + r) * B + bb];
     };
     (void)ld_stride;
@@ -128,7 +151,12 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     // static spheres of this robot's rollout planner (generic kernel only): stat [n_static][4][R][B] = x, y, z, radius
     T* st_sph = prm + P_N * NT;
     if (!UNIFORM && !AOS && n_static > 0) {
-        for (int i = 0; i < 4 * n_static; ++i) st_sph[i * NT + tid] = stat[((long long)i * R + r) * B + bb];
+        for (int i = 0; i < 4 * n_static; ++i) st_sph[i * NT + tid] = ex.stat[((long long)i * R + r) * B + bb];
+    }
+    if (AOS && ex.gw != nullptr && live) { // x_goal_0, weight_goal_0 of the record for the device post step
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ex.gw[((long long)k * R + r) * B + b] = prm[(P_G0 + k) * NT + tid];
+        ex.gw[((long long)3 * R + r) * B + b] = prm[P_W0 * NT + tid];
     }
     Chain<T> ch;
     const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
@@ -150,8 +178,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
             // constant-velocity goal estimate of one robot (:346-348)
             V3<T> p8 = kin_load(kin, NT, tid, 4, 0);
             if (x_ee != nullptr && live) {
-                T* o = AOS ? x_ee + (b * R + r) * 3 : x_ee + (long long)r * 3 * B + b;
-                const long long st = AOS ? 1 : B;
+                T* o = rec_order_out ? x_ee + (b * R + r) * 3 : x_ee + (long long)r * 3 * B + b;
+                const long long st = rec_order_out ? 1 : B;
                 o[0] = p8.x;
                 o[st] = p8.y;
                 o[2 * st] = p8.z;
@@ -168,8 +196,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
                     prm[(P_G0 + 2) * NT + tid] = g.z;
                 }
                 if (goal_est != nullptr && live) {
-                    T* o = AOS ? goal_est + b * 3 : goal_est + b;
-                    const long long st = AOS ? 1 : B;
+                    T* o = rec_order_out ? goal_est + b * 3 : goal_est + b;
+                    const long long st = rec_order_out ? 1 : B;
                     o[0] = g.x;
                     o[st] = g.y;
                     o[2 * st] = g.z;
@@ -203,9 +231,9 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
         }
     }
     // compute_velocity_average (:102-116): mean SQUARE joint velocity over the horizon
-    if (avg_vel != nullptr && live) avg_vel[AOS ? b * R + r : (long long)r * B + b] = acc / (T(N) * T(kDof));
+    if (avg_vel != nullptr && live) avg_vel[rec_order_out ? b * R + r : (long long)r * B + b] = acc / (T(N) * T(kDof));
     // stiffness indicator (maximum over the horizon of fabric_action's sum of leaf metrics), see mrf_rfcv_post_dev_f32
-    if (risk != nullptr && live) risk[AOS ? b * R + r : (long long)r * B + b] = prm[P_RISK * NT + tid];
+    if (risk != nullptr && live) risk[rec_order_out ? b * R + r : (long long)r * B + b] = prm[P_RISK * NT + tid];
     if (STRIDE) {
         __syncthreads(); // the next tile of this CTA overwrites the tables
         tile_first += gridDim.x;
@@ -920,6 +948,8 @@ struct MrfHandle_ {
     double guard_band[3], guard_rel[3], guard_edge[2], guard_band_dist;
     long long guard_cap;      // 0 = max(256, B / 16)
     long long guard_coop_max; // capacities up to this re-roll with the cooperative kernel
+    void* rf_buf[2];          // per pipeline slot: device buffers of mrf_rfcv_host_submit
+    size_t rf_bytes[2];
     void* guard_buf[MRF_GUARD_SLOTS];   // per scratch slot: list, slot_of, compact FP64 records and results
     size_t guard_bytes[MRF_GUARD_SLOTS];
 };
@@ -1070,6 +1100,8 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_sync) cudaFree(h->d_sync);
+    for (int i = 0; i < 2; ++i)
+        if (h->rf_buf[i]) cudaFree(h->rf_buf[i]);
     for (int i = 0; i < MRF_GUARD_SLOTS; ++i)
         if (h->guard_buf[i]) cudaFree(h->guard_buf[i]);
     for (int i = 0; i < 2; ++i)
@@ -1112,8 +1144,10 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
 template <typename T>
 static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee, T* goal_est, T* qN, T* qdN, int64_t B,
                        void* stream, bool aos = false, int sync_slot = 0, int n_var = MRF_REC, const T* rec_tail = nullptr,
-                       T* risk = nullptr, unsigned* n_live = nullptr, const float* rec_f32 = nullptr,
-                       const int* list = nullptr, long long B_src = 0, int n_static = 0, const T* stat = nullptr) {
+                       T* risk = nullptr, RollExtra<T> ex = RollExtra<T>{}) {
+    unsigned* const n_live = ex.n_live;
+    const int n_static = ex.n_static;
+    const T* const stat = ex.stat;
     if (!h || (!rec && !n_live)) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
     if (h->cfg.mode != 1)
@@ -1146,7 +1180,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA, SS><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                       \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
-            (unsigned)h->zc_window, n_var, rec_tail, risk, n_live, rec_f32, list, B_src, n_static, stat);            \
+            (unsigned)h->zc_window, n_var, rec_tail, risk, ex);                                                      \
     }
 #define MRF_LAUNCH_ROLLOUT(RR)                                                                                       \
     case RR:                                                                                                         \
@@ -1266,14 +1300,18 @@ extern "C" int mrf_rollout_dev_f32(mrf_handle_t h, const float* rec, int N, floa
 extern "C" int mrf_rollout_static_dev_f64(mrf_handle_t h, const double* rec, int N, int n_static, const double* stat,
                                           double* avg_vel, double* x_ee, double* goal_est, double* qN, double* qdN, int64_t B,
                                           void* stream) {
-    return rollout_dev<double>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, 0, n_static, stat);
+    RollExtra<double> ex{};
+    ex.n_static = n_static;
+    ex.stat = stat;
+    return rollout_dev<double>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr, ex);
 }
 extern "C" int mrf_rollout_static_dev_f32(mrf_handle_t h, const float* rec, int N, int n_static, const float* stat,
                                           float* avg_vel, float* x_ee, float* goal_est, float* qN, float* qdN, int64_t B,
                                           void* stream) {
-    return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, 0, n_static, stat);
+    RollExtra<float> ex{};
+    ex.n_static = n_static;
+    ex.stat = stat;
+    return rollout_dev<float>(h, rec, N, avg_vel, x_ee, goal_est, qN, qdN, B, stream, false, 0, MRF_REC, nullptr, nullptr, ex);
 }
 extern "C" int mrf_action_dev_f64(mrf_handle_t h, int robot_first, int n_rob, const double* rec, int S,
                                   const double* obst, double* action, int64_t B, void* stream) {
@@ -1356,7 +1394,10 @@ static int guard_reserve(mrf_handle_t h, int slot, size_t bytes) {
 template <typename T>
 static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* rec_work, const T* goal_est,
                          const T* avg_vel, const T* risk, const int32_t* sm_state, const int32_t* time_step, int32_t* tdo,
-                         int32_t* st_int, T* st_goal, int32_t* flag, T* result, int64_t B, void* stream, int slot) {
+                         int32_t* st_int, T* st_goal, int32_t* flag, T* result, int64_t B, void* stream, int slot,
+                         const RollExtra<double>* src_records = nullptr) {
+    // src_records: where the FP64 re-roll reads the listed scenarios' records from when that is not the SoA tensor `rec`
+    // (host-record sweeps: the caller's AoS records in page-locked memory); `rec` then only has to expose the goal rows
     if (!h || !rec || !rec_work || !x_ee || !avg_vel || !sm_state || !time_step)
         return fail(MRF_EINVAL, "mrf_rfcv_post: null argument");
     if (slot < 0 || slot >= MRF_GUARD_SLOTS) return fail(MRF_EINVAL, "mrf_rfcv_post: slot out of range");
@@ -1392,8 +1433,20 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
         h->launches += 1;
         // FP64 re-roll of the listed scenarios by the throughput kernel, straight from the FP32 records through the list;
         // the kernel reads the count from device memory (grid: a few CTAs striding over the tiles)
+        RollExtra<double> ex{};
+        if (src_records) {
+            ex = *src_records;
+        } else {
+            ex.src = (const float*)rec;
+            ex.sf = (long long)R * B;
+            ex.sr = (long long)B;
+            ex.sb = 1;
+            ex.src_nvar = MRF_REC;
+        }
+        ex.n_live = counters;
+        ex.list = list;
         rc = rollout_dev<double>(h, nullptr, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
-                                 nullptr, counters, (const float*)rec, list, (long long)B);
+                                 nullptr, ex);
         if (rc) return rc;
         ov = DlOverride{slot_of, avg64, xee64, gest64, cap, counters};
     }
@@ -1779,6 +1832,109 @@ extern "C" int mrf_rollout_host_submit_compact_f32(mrf_handle_t h, const float* 
                                                    float* avg_vel, float* x_ee, float* goal_est, int64_t B) {
     if (!rec_shared) return fail(MRF_EINVAL, "mrf_rollout_host_submit_compact: null argument");
     return rollout_host_submit<float>(h, rec_var, N, avg_vel, x_ee, goal_est, B, rec_shared);
+}
+
+// One RF-CV step of a sweep END TO END from host memory: the in-place rollout kernel reads the caller's page-locked
+// records over PCIe and leaves its results on the device (SoA); the post step -- guard select, FP64 re-roll of the listed
+// scenarios (read from the same host records through the list), deadlock heuristic -- follows on the same stream, and
+// only the per-scenario result [R+1][B] (and optionally the resolved goals / weights [4][R][B]) travels back.  Stateless:
+// every batch is a fresh control step (no deadlock history: time_deadlock_out = 1000, leader / follower at their
+// defaults), state-machine codes 0, one time step for the batch.
+__global__ void rfcv_state_init_kernel(int32_t* __restrict__ sm, int32_t* __restrict__ ts, int32_t* __restrict__ tdo,
+                                       int32_t* __restrict__ st_int, float* __restrict__ st_goal, int32_t time_step, int R,
+                                       long long B) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        for (int r = 0; r < R; ++r) sm[(long long)r * B + b] = 0;
+        ts[b] = time_step;
+        tdo[b] = 1000;
+        st_int[0 * B + b] = 0; st_int[1 * B + b] = 1; st_int[2 * B + b] = 0; st_int[3 * B + b] = 1;
+        st_goal[0 * B + b] = 0.f; st_goal[1 * B + b] = 0.f; st_goal[2 * B + b] = 0.f;
+    }
+}
+
+extern "C" int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const float* rec_shared, int N, int32_t time_step,
+                                        float* result, float* goals_out, int64_t B) {
+    if (!h || !rec || !result) return fail(MRF_EINVAL, "mrf_rfcv_host_submit: null argument");
+    if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rfcv_host_submit: B and N must be positive");
+    const int R = h->cfg.n_robots;
+    if (R < 2) return fail(MRF_EINVAL, "mrf_rfcv_host_submit: the deadlock heuristic needs n_robots >= 2");
+    MRF_CUDA(cudaSetDevice(h->device));
+    const float* view = (const float*)pinned_view(rec);
+    if (!view) return fail(MRF_EINVAL, "mrf_rfcv_host_submit: records must be page-locked host memory, 16-byte aligned");
+    for (const void* p : {(const void*)result, (const void*)goals_out}) {
+        if (!p) continue;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+            (void)cudaGetLastError();
+            return fail(MRF_EINVAL, "mrf_rfcv_host_submit: result buffers must be page-locked host memory");
+        }
+    }
+    const int s = h->zc_slot;
+    if (h->zc_pending[s]) {
+        int rc = rollout_wait_oldest(h);
+        if (rc) return rc;
+    }
+    cudaStream_t st = h->s_chunk[s];
+    const long long RB = (long long)R * B;
+    // per-slot device buffers: avg, risk [R][B]; x_ee [R][3][B]; goal_est [3][B]; gw [4][R][B]; st_goal [3][B]; result [R+1][B];
+    // int: sm [R][B], ts, tdo, flag [B], st_int [4][B]
+    const size_t nf = (size_t)(2 * RB + 3 * RB + 3 * B + 4 * RB + 3 * B + (R + 1) * B), ni = (size_t)(RB + 3 * B + 4 * B);
+    if (h->rf_bytes[s] < 4 * (nf + ni)) {
+        if (h->rf_buf[s]) MRF_CUDA(cudaFree(h->rf_buf[s]));
+        h->rf_buf[s] = nullptr;
+        h->rf_bytes[s] = 0;
+        if (cudaMalloc(&h->rf_buf[s], 4 * (nf + ni)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MRF_ENOMEM, "mrf_rfcv_host_submit: device allocation failed");
+        }
+        h->rf_bytes[s] = 4 * (nf + ni);
+    }
+    float* avg = (float*)h->rf_buf[s];
+    float* risk = avg + RB;
+    float* xee = risk + RB;
+    float* gest = xee + 3 * RB;
+    float* gw = gest + 3 * B;
+    float* st_goal = gw + 4 * RB;
+    float* d_result = st_goal + 3 * B;
+    int32_t* sm = (int32_t*)(d_result + (R + 1) * B);
+    int32_t* ts = sm + RB;
+    int32_t* tdo = ts + B;
+    int32_t* flag = tdo + B;
+    int32_t* st_int = flag + B;
+    const float* d_tail = nullptr;
+    if (rec_shared) {
+        MRF_CUDA(cudaMemcpyAsync(h->d_tail[s], rec_shared, sizeof(float) * (size_t)R * MRF_REC, cudaMemcpyHostToDevice, st));
+        d_tail = (const float*)h->d_tail[s];
+    }
+    const long long ib = (B + 255) / 256;
+    rfcv_state_init_kernel<<<(unsigned)(ib < 64 ? ib : 64), 256, 0, st>>>(sm, ts, tdo, st_int, st_goal, time_step, R, (long long)B);
+    MRF_CUDA(cudaGetLastError());
+    h->launches += 1;
+    const int n_var = rec_shared ? MRF_G1 : MRF_REC;
+    RollExtra<float> ex{};
+    ex.out_soa = 1;
+    ex.gw = gw;
+    int rc = rollout_dev<float>(h, view, N, avg, xee, gest, nullptr, nullptr, B, st, true, 1 + s, n_var, d_tail, risk, ex);
+    if (rc) return rc;
+    RollExtra<double> src{};
+    src.src = view;                // the re-roll reads the listed scenarios from the caller's records (AoS [B][R][n_var])
+    src.sf = 1;
+    src.sr = n_var;
+    src.sb = (long long)R * n_var;
+    src.src_nvar = n_var;
+    src.src_tail = d_tail;
+    // the goal rows MRF_G0.. / weight row MRF_W0 of a virtual record tensor live in gw (rows 0..3)
+    float* pseudo_rec = gw - (long long)MRF_G0 * RB;
+    rc = rfcv_post_dev<float>(h, pseudo_rec, N, xee, pseudo_rec, gest, avg, risk, sm, ts, tdo, st_int, st_goal, flag, d_result, B,
+                              st, 2 + s, &src);
+    if (rc) return rc;
+    MRF_CUDA(cudaMemcpyAsync(result, d_result, sizeof(float) * (size_t)(R + 1) * B, cudaMemcpyDeviceToHost, st));
+    if (goals_out) MRF_CUDA(cudaMemcpyAsync(goals_out, gw, sizeof(float) * (size_t)4 * RB, cudaMemcpyDeviceToHost, st));
+    MRF_CUDA(cudaEventRecord(h->ev_chunk[s], st));
+    if (!h->zc_pending[s ^ 1]) h->zc_oldest = s;
+    h->zc_pending[s] = 1;
+    h->zc_slot = s ^ 1;
+    return MRF_OK;
 }
 extern "C" int mrf_rollout_host_wait(mrf_handle_t h, int all) {
     if (!h) return fail(MRF_EINVAL, "mrf_rollout_host_wait: null handle");

@@ -412,6 +412,45 @@ def test_fused_rfcv_step_deadlock_flags_identical(built, R, N, B, seed):
     fab.close()
 
 
+def test_rfcv_host_submit_end_to_end_matches_device_path(built):
+    """mrf_rfcv_host_submit_f32 -- the whole RF-CV step from page-locked host records (in-place rollout kernel, FP64 guard
+    re-roll reading the listed scenarios from the same host records, deadlock heuristic, result back to host) -- returns
+    bit for bit what the device-tensor path (rollout_dev + rfcv_post_dev) returns, with whole and with compact records."""
+    import torch
+    from multi_robot_fabrics_b200.api import to_soa
+    R, N, B = 3, 20, 4099                                   # ragged last tile
+    rec = m.scenarios.generate(B, R, seed=64).astype(np.float32)
+    rec[:, :, 7:14] *= np.float32(0.25)
+    fab = Fabrics(R, device=0, estimate_goal=1, dl_dist_endeff=1.0)
+    dev = "cuda:0"
+    d_rec = torch.from_numpy(to_soa(rec)).to(dev)
+    work = d_rec.clone()
+    t = lambda *shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)
+    a, x, ge, risk, res = t(R, B), t(R, 3, B), t(3, B), t(R, B), t(R + 1, B)
+    fab.rollout_dev(d_rec, N, avg_vel=a, x_ee=x, goal_est=ge, risk=risk)
+    fab.rfcv_post_dev(d_rec, N, x, work, ge, a, torch.zeros((R, B), dtype=torch.int32, device=dev),
+                      torch.full((B,), 100, dtype=torch.int32, device=dev), torch.full((B,), 1000, dtype=torch.int32, device=dev),
+                      torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous(),
+                      torch.zeros((3, B), device=dev), risk=risk, result=res)
+    torch.cuda.synchronize()
+    want = res.cpu().numpy()
+    want_gw = torch.cat([work[14:17], work[17:18]]).cpu().numpy()                       # (4,R,B) after the heuristic
+    listed = fab.guard_stats()[2]
+    assert want[R].sum() > 20 and listed > 0
+    pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).pin_memory().numpy()
+    for compact in (False, True):
+        h_rec = pin(rec[:, :, :18] if compact else rec)
+        h_res, h_gw = pin(np.zeros((R + 1, B))), pin(np.zeros((4, R, B)))
+        for _ in range(3):                                                               # both pipeline slots
+            fab.rfcv_host_submit(h_rec, N, h_res, shared=rec[0] if compact else None, time_step=100, goals_out=h_gw)
+        fab.rollout_host_wait(all=True)
+        assert np.array_equal(h_res.view(np.uint32), want.view(np.uint32)), compact
+        assert np.array_equal(h_gw.view(np.uint32), want_gw.view(np.uint32)), compact
+    with pytest.raises(m.MrfError):
+        fab.rfcv_host_submit(np.ascontiguousarray(rec), N, h_res)                      # pageable records are refused
+    fab.close()
+
+
 def test_point_mass_planner_config_c1(built):
     """BASELINE config C1: the 4-point-mass examples through the drop-in planner, against the O1 golden actions and
     (batched, random states) against oracle O2."""
