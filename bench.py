@@ -20,13 +20,13 @@ integrator update, avg-velocity accumulation).
             in L2 and no flush sits inside the region.
   f64       the same sweep through the FP64 kernels (the parity path: 1e-9 relative against the oracle, checked on the
             timed batch), with its own roofline fraction against the FP64 FMA peak.
-  e2e       the same metric through the host-pointer C-ABI on page-locked buffers; three figures, all stated:
-            value = mrf_rollout_host_submit_compact_f32 / _wait (two batches in flight; per scenario and robot q, qdot,
-            x_goal_0, weight_goal_0 + one shared record per batch), full_records_value = mrf_rollout_host_submit_f32
-            (whole 44-scalar records), synchronous_call_value = one blocking mrf_rollout_host_f32 call per step.  The
-            kernel reads the records in the caller's order straight from host memory over PCIe and writes avg_vel /
-            x_ee / goal_est straight back (what get_velocity_rollouts hands its Python caller); rollout only -- the
-            post step is device-side only.
+  e2e       the same metric AND THE SAME STEP (rollout + FP64 guard + deadlock heuristic) through the host-pointer C-ABI
+            on page-locked buffers: mrf_rfcv_host_submit_f32 / mrf_rollout_host_wait, four batches in flight; the rollout
+            kernel reads the compact records (per scenario and robot q, qdot, x_goal_0, weight_goal_0 + one shared record
+            per batch) in the caller's order straight from host memory over PCIe, the post step runs on the device and
+            the [R+1][B] result comes back.  Beside it, rollout only (what get_velocity_rollouts hands its Python caller:
+            avg_vel / x_ee / goal_est written straight to host memory): compact-record pipeline, whole-record pipeline,
+            and one blocking mrf_rollout_host_f32 call per step.
   roofline  the kernel is compute-bound on the FP32 CUDA-core pipe (arithmetic intensity > 200 FLOP/B, no tensor
             cores): achieved = robot-steps/s x F(S=16) = 13.4 kFLOP over the FMA peak measured in this
             run by the library's micro-benchmark (MEASURED_PEAKS.json holds HBM / bf16 peaks only); the HBM view is
@@ -549,11 +549,18 @@ def ours(a):
         cv = pin((B, R, 18))
         cv[...] = hr[:, :, :18]
         cbufs.append((cv, ho))
-    e2e_value = pipeline(lambda i: fab.rollout_host_submit(cbufs[i % 2][0], H, cbufs[i % 2][1], dtype="f32", shared=shared_tail))
+    e2e_rollout_compact = pipeline(lambda i: fab.rollout_host_submit(cbufs[i % 2][0], H, cbufs[i % 2][1], dtype="f32",
+                                                                     shared=shared_tail))
     assert all(np.array_equal(full_avg[k].view(np.uint8), cbufs[k][1]["avg_vel"].view(np.uint8)) for k in range(2))
     assert np.array_equal(cbufs[0][1]["avg_vel"].view(np.uint8), np.ascontiguousarray(cbufs[1][1]["avg_vel"][::-1]).view(np.uint8))
+    # THE SAME STEP AS `value`, end to end: rollout + FP64 guard + deadlock heuristic from the page-locked compact records,
+    # only the [R+1][B] result (avg_vel rows + flag) travels back (mrf_rfcv_host_submit_f32, two batches in flight)
+    h_res = [pin((R + 1, B)) for _ in range(4)]      # the RF-CV pipeline is four deep: four result buffers cycle
+    e2e_value = pipeline(lambda i: fab.rfcv_host_submit(cbufs[i % 2][0], H, h_res[i % 4], shared=shared_tail, time_step=100))
+    chk = np.isfinite(full_avg[0]).all(axis=1)
+    assert np.abs(h_res[0][:R].T - full_avg[0])[chk].max() < 0.5      # same rollouts (guard rows carry the FP64 values)
     h2d = int(cbufs[0][0].nbytes + shared_tail.nbytes) * world      # whole job, like `value`
-    d2h = int(sum(v.nbytes for v in out.values())) * world
+    d2h = int(h_res[0].nbytes) * world
 
     if rank != 0:
         if world > 1:
@@ -624,13 +631,16 @@ def ours(a):
             "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(a),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "full_records_value": e2e_full, "synchronous_call_value": e2e_sync,
-                    "timing": "host wall clock, max over ranks, page-locked buffers; value = mrf_rollout_host_submit_compact_f32 / "
-                              "_wait (two batches in flight; per scenario and robot q, qdot, x_goal_0, weight_goal_0, the "
-                              "arguments shared by all scenarios once per batch); full_records_value = the same pipeline with "
-                              "whole 44-scalar records; synchronous_call_value = one blocking mrf_rollout_host_f32 call per "
-                              "step.  The kernel reads each step's records in place over PCIe and writes its results back to "
-                              "host memory; rollout only (the post step is device-side)"},
+                    "rollout_only_compact_value": e2e_rollout_compact, "rollout_only_full_records_value": e2e_full,
+                    "rollout_only_synchronous_call_value": e2e_sync,
+                    "timing": "host wall clock, max over ranks, page-locked buffers.  value = THE SAME STEP AS the device-timed "
+                              "`value` (rollout + FP64 guard re-roll + deadlock heuristic) through mrf_rfcv_host_submit_f32 / "
+                              "mrf_rollout_host_wait, four batches in flight: the rollout kernel reads each step's compact records "
+                              "(per scenario and robot q, qdot, x_goal_0, weight_goal_0; the arguments shared by all scenarios once "
+                              "per batch) in place over PCIe, the post step runs on the device, the [R+1][B] result (avg_vel rows + "
+                              "deadlock flag) is copied back.  rollout_only_*: get_velocity_rollouts alone (avg_vel, x_ee, goal_est "
+                              "written straight to host memory; 3.9 MB back per step) with compact records / whole 44-scalar "
+                              "records / one blocking mrf_rollout_host_f32 call per step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "f64": f64,
             "guard": guard, "nonfinite_scenario_fraction": nonfinite, "parity_spot_check": parity,
             "single_rollout_us": {"device_events_median": statistics.median(lat), "wall_back_to_back": lat_wall,

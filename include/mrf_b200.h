@@ -55,7 +55,7 @@ extern "C" {
 #define MRF_NLINKS 8   /* panda_link1..8, examples/parameters_manipulators.py:25-26 */
 #define MRF_REC 44     /* scalars per robot record */
 #define MRF_OBST 10    /* scalars per obstacle sphere: x[3], xdot[3], xddot[3], radius */
-#define MRF_GUARD_SLOTS 4   /* scratch slots of the mrf_rfcv_post_dev_f32 re-roll (concurrent post steps on different streams) */
+#define MRF_GUARD_SLOTS 8   /* scratch slots of the mrf_rfcv_post_dev_f32 re-roll (concurrent post steps on different streams) */
 #define MRF_MAX_STATIC 16   /* static spheres per robot in a coupled rollout (nr_obsts of the rollout planners) */
 #define MRF_MAX_SPHERES_PER_LINK 8   /* n_obst_per_link, examples/configs/panda_config.yaml:8 (reference default 4) */
 
@@ -223,7 +223,7 @@ int mrf_deadlock_rec_dev_f32(mrf_handle_t h, const float* x_ee, float* rec, cons
  * values for them -- the flags then equal those of a float64 evaluation of the same inputs.  mrf_set_guard() tunes the
  * bands; mrf_guard_stats() reports how many scenarios were re-rolled.  risk == NULL: no re-roll (plain FP32 decision).
  * FP64: risk is ignored (nothing to guard).
- * slot (0..MRF_GUARD_SLOTS-1) selects the scratch the re-roll uses: post steps that may run concurrently (different
+ * slot (0..3; 4..7 belong to mrf_rfcv_host_submit_f32's pipeline) selects the scratch the re-roll uses: post steps that may run concurrently (different
  * streams) must use different slots; calls on one stream can share one.  out[2] of mrf_guard_stats refers to slot 0. */
 int mrf_rfcv_post_dev_f32(mrf_handle_t h, const float* rec, int N, const float* x_ee, float* rec_work, const float* goal_est,
                           const float* avg_vel, const float* risk, const int32_t* sm_state, const int32_t* time_step,
@@ -315,7 +315,10 @@ int mrf_rollout_host_wait(mrf_handle_t h, int all);
  *   result    [R+1][B]  rows 0..R-1 = avg_vel per robot, row R = deadlock flag (page-locked, required)
  *   goals_out [4][R][B] x_goal_0 (3 rows) and weight_goal_0 of every robot AFTER the heuristic (page-locked, nullable)
  * travel back.  Stateless per batch: state-machine codes 0, the given time_step for every scenario, no deadlock history
- * (time_deadlock_out = 1000).  n_robots >= 2. */
+ * (time_deadlock_out = 1000).  n_robots >= 2.  Its pipeline is FOUR deep (the post step of a batch runs while the
+ * rollouts of the next two already occupy the GPU): a submission blocks until the one four calls earlier is complete, so a
+ * caller cycling through four sets of buffers never overwrites data in flight; mrf_rollout_host_wait(h, 0) waits for the
+ * oldest batch, (h, 1) for all. */
 int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const float* rec_shared, int N, int32_t time_step,
                              float* result, float* goals_out, int64_t B);
 /*   q, qdot [B][R][MRF_DOF]   x, v, a [B][R][MRF_NLINKS][3] */

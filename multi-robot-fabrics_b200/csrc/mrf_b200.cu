@@ -64,9 +64,10 @@ template <typename T> struct RollExtra {
     int n_static;
     const T* stat;
     // host-record mode feeding the device post step: results in the SoA layout of the device entries (not the caller's
-    // record order), and the goals / weight_goal_0 of every record into gw [4][R][B] for the deadlock heuristic
+    // record order), and the record fields read from the host copied to rec_out [n_var][R][B] on the device (SoA) -- the
+    // post step (goal rows for the heuristic, whole records of the re-rolled scenarios) then never touches the bus
     int out_soa;
-    T* gw;
+    T* rec_out;
 };
 
 template <typename T, int R, bool UNIFORM, bool AOS, bool STRIDE = false>
@@ -153,10 +154,8 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     if (!UNIFORM && !AOS && n_static > 0) {
         for (int i = 0; i < 4 * n_static; ++i) st_sph[i * NT + tid] = ex.stat[((long long)i * R + r) * B + bb];
     }
-    if (AOS && ex.gw != nullptr && live) { // x_goal_0, weight_goal_0 of the record for the device post step
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ex.gw[((long long)k * R + r) * B + b] = prm[(P_G0 + k) * NT + tid];
-        ex.gw[((long long)3 * R + r) * B + b] = prm[P_W0 * NT + tid];
+    if (AOS && ex.rec_out != nullptr && live) { // device SoA copy of the host record fields for the post step
+        for (int f = 0; f < n_var; ++f) ex.rec_out[((long long)f * R + r) * B + b] = ld_base[f];
     }
     Chain<T> ch;
     const T vref = cfg.static_or_dyn ? T(1) : T(0), aref = cfg.static_or_dyn ? cfg.sref : T(0);
@@ -948,8 +947,13 @@ struct MrfHandle_ {
     double guard_band[3], guard_rel[3], guard_edge[2], guard_band_dist;
     long long guard_cap;      // 0 = max(256, B / 16)
     long long guard_coop_max; // capacities up to this re-roll with the cooperative kernel
-    void* rf_buf[2];          // per pipeline slot: device buffers of mrf_rfcv_host_submit
-    size_t rf_bytes[2];
+    void* rf_buf[4];          // per pipeline slot: device buffers of mrf_rfcv_host_submit (its own four-deep pipeline)
+    size_t rf_bytes[4];
+    void* d_tail_rf[4];
+    cudaEvent_t ev_rf[4], ev_rf_roll[4]; // batch complete / its rollout kernel complete
+    cudaStream_t s_rf_post[4];           // high-priority streams of the post steps
+    int rf_roll_valid[4];
+    int rf_head, rf_count;
     void* guard_buf[MRF_GUARD_SLOTS];   // per scratch slot: list, slot_of, compact FP64 records and results
     size_t guard_bytes[MRF_GUARD_SLOTS];
 };
@@ -1008,8 +1012,17 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
 
 static int create_resources(MrfHandle_* h) {
     for (int i = 0; i < 2; ++i) MRF_CUDA(cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC));
-    MRF_CUDA(cudaMalloc(&h->d_sync, (8 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned))); // [0..5] ticket pairs, [8..] guard counters
-    MRF_CUDA(cudaMemset(h->d_sync, 0, (8 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
+    // [0..13] ticket pairs (slot 0 synchronous entry, 1..2 rollout submit pipeline, 3..6 RF-CV submit pipeline), [16..] guard counters
+    MRF_CUDA(cudaMalloc(&h->d_sync, (16 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
+    MRF_CUDA(cudaMemset(h->d_sync, 0, (16 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
+    int prio_lo = 0, prio_hi = 0;
+    MRF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < 4; ++i) {
+        MRF_CUDA(cudaMalloc(&h->d_tail_rf[i], sizeof(float) * MRF_MAX_ROBOTS * MRF_REC));
+        MRF_CUDA(cudaEventCreateWithFlags(&h->ev_rf[i], cudaEventDisableTiming));
+        MRF_CUDA(cudaEventCreateWithFlags(&h->ev_rf_roll[i], cudaEventDisableTiming));
+        MRF_CUDA(cudaStreamCreateWithPriority(&h->s_rf_post[i], cudaStreamNonBlocking, prio_hi));
+    }
     MRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     MRF_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     MRF_CUDA(cudaEventCreate(&h->ev0));
@@ -1100,8 +1113,13 @@ extern "C" int mrf_destroy(mrf_handle_t h) {
     for (int i = 0; i < 8; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_sync) cudaFree(h->d_sync);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i) {
         if (h->rf_buf[i]) cudaFree(h->rf_buf[i]);
+        if (h->d_tail_rf[i]) cudaFree(h->d_tail_rf[i]);
+        if (h->ev_rf[i]) cudaEventDestroy(h->ev_rf[i]);
+        if (h->ev_rf_roll[i]) cudaEventDestroy(h->ev_rf_roll[i]);
+        if (h->s_rf_post[i]) cudaStreamDestroy(h->s_rf_post[i]);
+    }
     for (int i = 0; i < MRF_GUARD_SLOTS; ++i)
         if (h->guard_buf[i]) cudaFree(h->guard_buf[i]);
     for (int i = 0; i < 2; ++i)
@@ -1421,7 +1439,7 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
         double* gest64 = xee64 + (size_t)3 * R * cap;
         int* list = (int*)(gest64 + (size_t)3 * cap);
         int* slot_of = list + cap;
-        unsigned* counters = h->d_sync + 8 + 4 * slot; // [0] is zero on entry: reset by the previous call's deadlock kernel
+        unsigned* counters = h->d_sync + 16 + 4 * slot; // [0] is zero on entry: reset by the previous call's deadlock kernel
         GuardCfg g{R, est ? h->cfg.estimate_robot : -1, h->cfg.dl_avg_vel_constant, h->cfg.dl_dist_endeff, h->guard_band_dist,
                    {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_rel[0], h->guard_rel[1], h->guard_rel[2]},
                    {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
@@ -1497,7 +1515,7 @@ extern "C" int mrf_guard_stats(mrf_handle_t h, int64_t* out) {
     if (!h || !out) return fail(MRF_EINVAL, "mrf_guard_stats: null argument");
     MRF_CUDA(cudaSetDevice(h->device));
     unsigned c[4 * MRF_GUARD_SLOTS];
-    MRF_CUDA(cudaMemcpy(c, h->d_sync + 8, sizeof(c), cudaMemcpyDeviceToHost));
+    MRF_CUDA(cudaMemcpy(c, h->d_sync + 16, sizeof(c), cudaMemcpyDeviceToHost));
     out[0] = out[1] = 0;
     for (int i = 0; i < MRF_GUARD_SLOTS; ++i) {
         out[0] += c[4 * i + 2];
@@ -1840,6 +1858,15 @@ extern "C" int mrf_rollout_host_submit_compact_f32(mrf_handle_t h, const float* 
 // only the per-scenario result [R+1][B] (and optionally the resolved goals / weights [4][R][B]) travels back.  Stateless:
 // every batch is a fresh control step (no deadlock history: time_deadlock_out = 1000, leader / follower at their
 // defaults), state-machine codes 0, one time step for the batch.
+static int rf_wait_oldest(mrf_handle_t h) {
+    if (h->rf_count == 0) return MRF_OK;
+    const int s = (h->rf_head - h->rf_count + 8) & 3;
+    MRF_CUDA(cudaSetDevice(h->device));
+    MRF_CUDA(cudaEventSynchronize(h->ev_rf[s]));
+    h->rf_count -= 1;
+    return MRF_OK;
+}
+
 __global__ void rfcv_state_init_kernel(int32_t* __restrict__ sm, int32_t* __restrict__ ts, int32_t* __restrict__ tdo,
                                        int32_t* __restrict__ st_int, float* __restrict__ st_goal, int32_t time_step, int R,
                                        long long B) {
@@ -1869,17 +1896,18 @@ extern "C" int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const 
             return fail(MRF_EINVAL, "mrf_rfcv_host_submit: result buffers must be page-locked host memory");
         }
     }
-    const int s = h->zc_slot;
-    if (h->zc_pending[s]) {
-        int rc = rollout_wait_oldest(h);
+    if (h->rf_count == 4) { // four batches in flight: the oldest one is in the slot this submission takes
+        int rc = rf_wait_oldest(h);
         if (rc) return rc;
     }
-    cudaStream_t st = h->s_chunk[s];
+    const int s = h->rf_head;
+    cudaStream_t st = h->s_chunk[4 + s];
     const long long RB = (long long)R * B;
-    // per-slot device buffers: avg, risk [R][B]; x_ee [R][3][B]; goal_est [3][B]; gw [4][R][B]; st_goal [3][B]; result [R+1][B];
-    // int: sm [R][B], ts, tdo, flag [B], st_int [4][B]
-    const size_t nf = (size_t)(2 * RB + 3 * RB + 3 * B + 4 * RB + 3 * B + (R + 1) * B), ni = (size_t)(RB + 3 * B + 4 * B);
-    if (h->rf_bytes[s] < 4 * (nf + ni)) {
+    const int n_var = rec_shared ? MRF_G1 : MRF_REC;
+    // per-slot device buffers: avg, risk [R][B]; x_ee [R][3][B]; goal_est [3][B]; rec_out [n_var][R][B]; st_goal [3][B];
+    // result [R+1][B]; int: sm [R][B], ts, tdo, flag [B], st_int [4][B]
+    const size_t nf = (size_t)(2 * RB + 3 * RB + 3 * B + (long long)n_var * RB + 3 * B + (R + 1) * B), ni = (size_t)(RB + 3 * B + 4 * B);
+    if (h->rf_bytes[s] < 4 * (nf + ni)) {  // (the slot is idle: its previous batch was waited for above or long ago)
         if (h->rf_buf[s]) MRF_CUDA(cudaFree(h->rf_buf[s]));
         h->rf_buf[s] = nullptr;
         h->rf_bytes[s] = 0;
@@ -1893,8 +1921,8 @@ extern "C" int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const 
     float* risk = avg + RB;
     float* xee = risk + RB;
     float* gest = xee + 3 * RB;
-    float* gw = gest + 3 * B;
-    float* st_goal = gw + 4 * RB;
+    float* rec_out = gest + 3 * B;
+    float* st_goal = rec_out + (long long)n_var * RB;
     float* d_result = st_goal + 3 * B;
     int32_t* sm = (int32_t*)(d_result + (R + 1) * B);
     int32_t* ts = sm + RB;
@@ -1903,44 +1931,56 @@ extern "C" int mrf_rfcv_host_submit_f32(mrf_handle_t h, const float* rec, const 
     int32_t* st_int = flag + B;
     const float* d_tail = nullptr;
     if (rec_shared) {
-        MRF_CUDA(cudaMemcpyAsync(h->d_tail[s], rec_shared, sizeof(float) * (size_t)R * MRF_REC, cudaMemcpyHostToDevice, st));
-        d_tail = (const float*)h->d_tail[s];
+        MRF_CUDA(cudaMemcpyAsync(h->d_tail_rf[s], rec_shared, sizeof(float) * (size_t)R * MRF_REC, cudaMemcpyHostToDevice, st));
+        d_tail = (const float*)h->d_tail_rf[s];
     }
     const long long ib = (B + 255) / 256;
     rfcv_state_init_kernel<<<(unsigned)(ib < 64 ? ib : 64), 256, 0, st>>>(sm, ts, tdo, st_int, st_goal, time_step, R, (long long)B);
     MRF_CUDA(cudaGetLastError());
     h->launches += 1;
-    const int n_var = rec_shared ? MRF_G1 : MRF_REC;
     RollExtra<float> ex{};
     ex.out_soa = 1;
-    ex.gw = gw;
-    int rc = rollout_dev<float>(h, view, N, avg, xee, gest, nullptr, nullptr, B, st, true, 1 + s, n_var, d_tail, risk, ex);
+    ex.rec_out = rec_out;
+    // at most TWO rollout kernels share the GPU and the bus (the in-place reads are admitted tile window by tile window;
+    // with four kernels resident most CTAs would spin on admission): this rollout starts when the one two batches
+    // earlier has finished -- the post steps of up to four batches still overlap
+    if (h->rf_roll_valid[(s + 2) & 3]) MRF_CUDA(cudaStreamWaitEvent(st, h->ev_rf_roll[(s + 2) & 3], 0));
+    int rc = rollout_dev<float>(h, view, N, avg, xee, gest, nullptr, nullptr, B, st, true, 3 + s, n_var, d_tail, risk, ex);
     if (rc) return rc;
+    MRF_CUDA(cudaEventRecord(h->ev_rf_roll[s], st));
+    h->rf_roll_valid[s] = 1;
+    // post step on the slot's HIGH-PRIORITY stream (its small kernels are placed as soon as a rollout CTA retires), reading
+    // the device copy of the records: rows MRF_G0..MRF_W0 for the heuristic (in place), whole records for the re-roll
+    // (fields >= n_var of compact records from the shared tail)
+    cudaStream_t sp = h->s_rf_post[s];
+    MRF_CUDA(cudaStreamWaitEvent(sp, h->ev_rf_roll[s], 0));
     RollExtra<double> src{};
-    src.src = view;                // the re-roll reads the listed scenarios from the caller's records (AoS [B][R][n_var])
-    src.sf = 1;
-    src.sr = n_var;
-    src.sb = (long long)R * n_var;
+    src.src = rec_out;
+    src.sf = RB;
+    src.sr = (long long)B;
+    src.sb = 1;
     src.src_nvar = n_var;
     src.src_tail = d_tail;
-    // the goal rows MRF_G0.. / weight row MRF_W0 of a virtual record tensor live in gw (rows 0..3)
-    float* pseudo_rec = gw - (long long)MRF_G0 * RB;
-    rc = rfcv_post_dev<float>(h, pseudo_rec, N, xee, pseudo_rec, gest, avg, risk, sm, ts, tdo, st_int, st_goal, flag, d_result, B,
-                              st, 2 + s, &src);
+    rc = rfcv_post_dev<float>(h, rec_out, N, xee, rec_out, gest, avg, risk, sm, ts, tdo, st_int, st_goal, flag, d_result, B, sp,
+                              4 + s, &src);
     if (rc) return rc;
-    MRF_CUDA(cudaMemcpyAsync(result, d_result, sizeof(float) * (size_t)(R + 1) * B, cudaMemcpyDeviceToHost, st));
-    if (goals_out) MRF_CUDA(cudaMemcpyAsync(goals_out, gw, sizeof(float) * (size_t)4 * RB, cudaMemcpyDeviceToHost, st));
-    MRF_CUDA(cudaEventRecord(h->ev_chunk[s], st));
-    if (!h->zc_pending[s ^ 1]) h->zc_oldest = s;
-    h->zc_pending[s] = 1;
-    h->zc_slot = s ^ 1;
+    MRF_CUDA(cudaMemcpyAsync(result, d_result, sizeof(float) * (size_t)(R + 1) * B, cudaMemcpyDeviceToHost, sp));
+    if (goals_out)
+        MRF_CUDA(cudaMemcpyAsync(goals_out, rec_out + (long long)MRF_G0 * RB, sizeof(float) * (size_t)4 * RB, cudaMemcpyDeviceToHost, sp));
+    MRF_CUDA(cudaEventRecord(h->ev_rf[s], sp));
+    h->rf_head = (s + 1) & 3;
+    h->rf_count += 1;
     return MRF_OK;
 }
 extern "C" int mrf_rollout_host_wait(mrf_handle_t h, int all) {
     if (!h) return fail(MRF_EINVAL, "mrf_rollout_host_wait: null handle");
     int rc = rollout_wait_oldest(h);
+    if (rc) return rc;
+    rc = rf_wait_oldest(h);
     if (rc || !all) return rc;
-    return rollout_wait_oldest(h);
+    rc = rollout_wait_oldest(h);
+    while (!rc && h->rf_count > 0) rc = rf_wait_oldest(h);
+    return rc;
 }
 
 template <typename T, bool CART>
