@@ -56,4 +56,23 @@ def test_integration_md_stub(built):
     for k, (rec_var, out) in enumerate(batches):
         want = fab.rollout_host(np.roll(big, k, axis=0).astype(np.float32), N, dtype="f32")["avg_vel"]
         assert np.array_equal(out.view(np.uint8), want.view(np.uint8)), k
+    # RF-CV control-step stub: rollout + vel_avg_tot + deadlock_checking for a batch, result (R+1, B) back
+    cfg2, h2 = MrfConfig(), C.c_void_p()
+    assert L.mrf_config_default(C.byref(cfg2), 3) == 0
+    cfg2.estimate_goal = 1                                   # ESTIMATE_GOAL: RF-CV
+    assert L.mrf_create(C.byref(cfg2), 0, C.byref(h2)) == 0, L.mrf_last_error().decode()
+    results = [pin(np.zeros((R + 1, Bs))) for _ in range(3)]
+    for (rec_var, _), res in zip(batches, results):
+        rc = L.mrf_rfcv_host_submit_f32(h2, p(rec_var), p(shared), C.c_int(N), C.c_int(100), p(res), None, C.c_int64(Bs))
+        assert rc == 0, L.mrf_last_error().decode()
+    assert L.mrf_rollout_host_wait(h2, C.c_int(1)) == 0
+    fab2 = Fabrics(R, estimate_goal=1)
+    for k, res in enumerate(results):
+        want = np.zeros((R + 1, Bs), dtype=np.float32)
+        hr = pin(np.roll(big, k, axis=0))
+        fab2.rfcv_host_submit(hr, N, pin_res := pin(want), time_step=100)
+        fab2.rollout_host_wait(all=True)
+        assert np.array_equal(res.view(np.uint8), pin_res.view(np.uint8)), k
+        assert set(np.unique(res[R])) <= {0.0, 1.0}
+    assert L.mrf_destroy(h2) == 0
     assert L.mrf_destroy(h) == 0
