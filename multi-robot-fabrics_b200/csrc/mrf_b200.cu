@@ -946,7 +946,6 @@ struct MrfHandle_ {
     // FP64 re-roll of guard-band scenarios (mrf_rfcv_post_dev_f32)
     double guard_band[3], guard_rel[3], guard_edge[2], guard_band_dist;
     long long guard_cap;      // 0 = max(256, B / 16)
-    long long guard_coop_max; // capacities up to this re-roll with the cooperative kernel
     void* rf_buf[4];          // per pipeline slot: device buffers of mrf_rfcv_host_submit (its own four-deep pipeline)
     size_t rf_bytes[4];
     void* d_tail_rf[4];
@@ -1087,8 +1086,6 @@ extern "C" int mrf_create(const MrfConfig* cfg, int device, mrf_handle_t* out) {
     h->guard_edge[1] = 200.0;
     h->guard_band_dist = 1e-5;
     h->guard_cap = 0;
-    h->guard_coop_max = 512;
-    if (const char* e = getenv("MRF_GUARD_COOP_MAX")) h->guard_coop_max = atoll(e);
     for (int i = 0; i < MRF_GUARD_SLOTS; ++i) {
         h->guard_buf[i] = nullptr;
         h->guard_bytes[i] = 0;

@@ -303,10 +303,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(32 * R, 1)
     rollout_coop_kernel(const __grid_constant__ DevCfg<T> cfg, const T* __restrict__ rec, int N, T* __restrict__ avg_vel,
                         T* __restrict__ x_ee, T* __restrict__ goal_est, T* __restrict__ qN, T* __restrict__ qdN,
-                        long long B, const unsigned* __restrict__ n_live = nullptr) {
-    // n_live (device memory, optional): only the first *n_live scenarios exist -- the grid was sized for a capacity
-    // known on the host, the actual count was produced on the device (FP64 re-roll of guard-band scenarios)
-    if (n_live != nullptr && blockIdx.x >= *n_live) return;
+                        long long B) {
     __shared__ T kin[kKinRows<T> * R];
     __shared__ T prm[P_N * R];
     __shared__ CoopState<T> sts[R];
