@@ -554,11 +554,14 @@ def ours(a):
     assert all(np.array_equal(full_avg[k].view(np.uint8), cbufs[k][1]["avg_vel"].view(np.uint8)) for k in range(2))
     assert np.array_equal(cbufs[0][1]["avg_vel"].view(np.uint8), np.ascontiguousarray(cbufs[1][1]["avg_vel"][::-1]).view(np.uint8))
     # THE SAME STEP AS `value`, end to end: rollout + FP64 guard + deadlock heuristic from the page-locked compact records,
-    # only the [R+1][B] result (avg_vel rows + flag) travels back (mrf_rfcv_host_submit_f32, two batches in flight)
+    # only the [R+1][B] result (avg_vel rows + flag) travels back (mrf_rfcv_host_submit_f32, four batches in flight)
     h_res = [pin((R + 1, B)) for _ in range(4)]      # the RF-CV pipeline is four deep: four result buffers cycle
     e2e_value = pipeline(lambda i: fab.rfcv_host_submit(cbufs[i % 2][0], H, h_res[i % 4], shared=shared_tail, time_step=100))
+    # same rollouts as the rollout-only pipeline, bit for bit, except the few scenarios the guard re-rolled in FP64
     chk = np.isfinite(full_avg[0]).all(axis=1)
-    assert np.abs(h_res[0][:R].T - full_avg[0])[chk].max() < 0.5      # same rollouts (guard rows carry the FP64 values)
+    differ = int(((h_res[0][:R].T != full_avg[0]).any(axis=1) & chk).sum())
+    assert differ <= 1024 and set(np.unique(h_res[0][R]).tolist()) <= {0.0, 1.0}, differ
+    e2e_flags = int(h_res[0][R].sum())
     h2d = int(cbufs[0][0].nbytes + shared_tail.nbytes) * world      # whole job, like `value`
     d2h = int(h_res[0].nbytes) * world
 
@@ -631,6 +634,7 @@ def ours(a):
             "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config_dict(a),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "deadlock_flags_raised": e2e_flags, "scenarios_carrying_fp64_values": differ,
                     "rollout_only_compact_value": e2e_rollout_compact, "rollout_only_full_records_value": e2e_full,
                     "rollout_only_synchronous_call_value": e2e_sync,
                     "timing": "host wall clock, max over ranks, page-locked buffers.  value = THE SAME STEP AS the device-timed "
