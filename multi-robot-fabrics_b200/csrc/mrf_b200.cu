@@ -42,6 +42,11 @@ namespace mrf {
 #ifndef MRF_ROLLOUT_MINBLOCKS_F64
 #define MRF_ROLLOUT_MINBLOCKS_F64 1
 #endif
+#ifdef MRF_EXP_NOBAR // timing experiment only (racy): what the two per-step CTA barriers cost
+#define MRF_STEP_SYNC() __syncwarp()
+#else
+#define MRF_STEP_SYNC() __syncthreads()
+#endif
 // Host-record mode (AOS): `rec` holds the caller's own records rec[B][R][44] (the reference's argument order), normally
 // in PAGE-LOCKED HOST memory that the kernel reads over PCIe.  A tile's records are one contiguous block, fetched with
 // coalesced 16-byte loads into the (not yet used) point table; results go back in the matching layout (avg[B][R],
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
 #pragma unroll
             for (int i = 0; i < kDof; ++i) q[i] += cfg.dt * qd[i];
         }
-        __syncthreads(); // readers of the previous step are done
+        MRF_STEP_SYNC(); // readers of the previous step are done
         chain_forward(cfg, r, q, qd, ch, kin, NT, tid);
         if (k < 0) {
             // end-effector FK at the measured state (example_pandas_Jointspace.py:236-238,328-329) and the RF-CV
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
             }
             continue;
         }
-        __syncthreads(); // every robot of the tile has published
+        MRF_STEP_SYNC(); // every robot of the tile has published
         // Phase B (:211-249): action against the other robots' published spheres
         T act[kDof], stiff;
         if (UNIFORM) {

@@ -38,7 +38,11 @@ constexpr int kPts = kEgo + 1; // + the constant point link1 == link2 (slot 5), 
 // pullbacks; keeping them out of the register file across the leaf loops removes the FP64 kernel's spills (36
 // registers; measured +2.7 %), while for FP32 (18 registers, no spills) the extra shared-memory reads cost 1.3 %.
 constexpr int kZ = kPts * 9;
+#ifdef MRF_AXES_SMEM_F32
+template <typename T> constexpr bool kAxesInSmem = true;
+#else
 template <typename T> constexpr bool kAxesInSmem = sizeof(T) == 8;
+#endif
 template <typename T> constexpr int kKinRows = kPts * 9 + (kAxesInSmem<T> ? 18 : 0);
 constexpr int kMaxEnt = 8 * (MRF_MAX_ROBOTS - 1); // sphere entries one robot sees (all links of all other robots)
 // parameter block (per thread, shared memory)
@@ -146,6 +150,14 @@ template <typename T> MRF_HD V3<T> cross(V3<T> a, V3<T> b) {
     return V3<T>{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
+// c + a x b as two chained multiply-adds per component (cross() followed by an addition costs three)
+template <typename T> MRF_HD V3<T> cross_add(V3<T> a, V3<T> b, V3<T> c) {
+    return V3<T>{(c.x + a.y * b.z) - a.z * b.y, (c.y + a.z * b.x) - a.x * b.z, (c.z + a.x * b.y) - a.y * b.x};
+}
+// c + a.b and c - a.b as three chained multiply-adds (a separate dot() costs a fourth instruction for the final add)
+template <typename T> MRF_HD T dot_add(V3<T> a, V3<T> b, T c) { return ((c + a.z * b.z) + a.y * b.y) + a.x * b.x; }
+template <typename T> MRF_HD T dot_sub(V3<T> a, V3<T> b, T c) { return ((c - a.z * b.z) - a.y * b.y) - a.x * b.x; }
+
 // ------------------------------------------------------------------------------------------------
 // configuration as the kernels see it (passed by value as a __grid_constant__ kernel parameter)
 // ------------------------------------------------------------------------------------------------
@@ -202,7 +214,7 @@ template <typename T> struct Frame {
 
 template <typename T> MRF_HD void fr_advance(Frame<T>& f, V3<T> r) {
     V3<T> t = cross(f.w, r);
-    f.ac = f.ac + cross(f.al, r) + cross(f.w, t);
+    f.ac = cross_add(f.w, t, cross_add(f.al, r, f.ac));
     f.v = f.v + t;
     f.p = f.p + r;
 }
@@ -224,7 +236,7 @@ template <typename T, int ROLL> MRF_HD V3<T> fr_joint(Frame<T>& f, T q, T qd) {
     f.a = a;
     f.b = b;
     V3<T> zq = f.n * qd;
-    f.al = f.al + cross(f.w, zq);
+    f.al = cross_add(f.w, zq, f.al);
     f.w = f.w + zq;
     return f.n;
 }
@@ -374,7 +386,7 @@ template <typename T> MRF_HD V3<T> symmul(const Sym3<T>& A, V3<T> u) {
 
 // Spec in joint space: 6x6 upper triangle + decoupled joint 7 (no collision point or task map moves with q7)
 template <typename T> struct Spec {
-    T M[6][6];
+    T M[6][6]; // fabric_action accumulates the NEGATED metric here (see chol_solve6n)
     T m7;
     T f[kDof];
 };
@@ -438,34 +450,35 @@ MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>
     V3<P2<T>> w{pfma(vo.x, nvref, v.x), pfma(vo.y, nvref, v.y), pfma(vo.z, nvref, v.z)};
     P2<T> n2 = pdot(d, d);
     P2<T> in1 = prsqrt(n2);
-    P2<T> n = pmul(n2, in1);
     P2<T> gs, ix;
     if (IRHO) {
         gs = pmul(in1, irho);                   // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
-        ix = prcp(pfma(n, irho, m1));           // 1/x, x = n/rho - 1
+        ix = prcp(pfma(n2, gs, m1));            // 1/x, x = n/rho - 1 = n^2/(n rho) - 1
     } else {
         // one reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) and 1/x
+        P2<T> n = pmul(n2, in1);
         P2<T> t = pfma(rho, m1, n);
         P2<T> nr = pmul(n, rho);
         P2<T> u = prcp(pmul(nr, t));
         gs = pmul(u, t);
         ix = pmul(pmul(u, nr), rho);
     }
-    P2<T> dw = pdot(d, w), dc = pdot(d, cc), da = pdot(d, co), dv = pdot(d, v), ww = pdot(w, w);
+    P2<T> dw = pdot(d, w), da = pdot(d, co), dv = pdot(d, v);
+    P2<T> wc = pfma(d.z, cc.z, pfma(d.y, cc.y, pfma(d.x, cc.x, pdot(w, w)))); // |w|^2 + d.c
     P2<T> q = pmul(dw, in1);                                      // component of w along d
-    P2<T> inner = padd(pfma(pmul(q, m1), q, ww), dc);             // (kappa + g.c)/gs = |w|^2 - q^2 + d.c
-    P2<T> xd = pmul(dw, gs);
+    P2<T> inner = pfma(pmul(q, m1), q, wc);                       // (kappa + g.c)/gs = |w|^2 - q^2 + d.c
     P2<T> ix2 = pmul(ix, ix), ix4 = pmul(ix2, ix2);
     P2<T> Ml = pmul(cM, ix4);                                     // d2L/dxdot2 = 0.02 w / x^4
-    P2<T> u1 = pmul(Ml, pmul(xd, xd));
-    P2<T> fl = pmul(pmul(u1, ix4), psplat(T(-0.5)));              // M h, h = -0.5 xdot^2 / x^4
-    P2<T> fel = pmul(pmul(u1, ix), psplat(T(-2)));                // Euler-Lagrange force of the leaf energy
     P2<T> Mg = pmul(Ml, gs);
+    P2<T> k = pmul(Mg, gs);
+    P2<T> u1 = pmul(k, pmul(dw, dw));                             // M xdot^2, xdot = (d.w) gs
+    P2<T> hh = pmul(ix4, psplat(T(-0.5)));
+    P2<T> fl = pmul(u1, hh);                                      // M h, h = -0.5 xdot^2 / x^4
+    P2<T> fd = pmul(u1, pfma(ix, psplat(T(2)), hh));              // f_l - f_e,l (Euler-Lagrange force -2 M xdot^2 / x)
     P2<T> s1 = pfma(psplat(sigma), inner, pmul(psplat(-aref), da));
     P2<T> fq = pfma(Mg, s1, fl);
-    P2<T> e1 = pfma(pmul(Mg, psplat(sigma - T(1))), inner, pfma(fel, m1, fl));
+    P2<T> e1 = pfma(pmul(Mg, psplat(sigma - T(1))), inner, fd);
     acc.num = pfma(pmul(dv, gs), e1, acc.num);
-    P2<T> k = pmul(Mg, gs);
     V3<P2<T>> Md{pmul(d.x, k), pmul(d.y, k), pmul(d.z, k)};
     acc.A.xx = pfma(Md.x, d.x, acc.A.xx); acc.A.xy = pfma(Md.x, d.y, acc.A.xy); acc.A.xz = pfma(Md.x, d.z, acc.A.xz);
     acc.A.yy = pfma(Md.y, d.y, acc.A.yy); acc.A.yz = pfma(Md.y, d.z, acc.A.yz); acc.A.zz = pfma(Md.z, d.z, acc.A.zz);
@@ -586,6 +599,79 @@ template <typename T> MRF_HD void chol_solve6_pair(P2<T> (&M)[6][6], T eps, cons
     }
 }
 
+// Negated convention: the caller accumulates N = -M (free: the subtraction folds into the FMA's operand sign) and the
+// factor is kept as U' = -U, so that every update of the factorisation and of the two triangular solves is a plain
+// multiply-add -- the packed FP32x2 FMA has no operand negation, and the positive convention above spends one FMUL2 per
+// update on it (65 of ~240 packed instructions).  N_jj - eps + sum U'_kj^2 = -s;  U'_ji = (N_ji + sum U'_kj U'_ki) r,
+// r = rsqrt(s);  U^T y = b -> y_i = (b_i + sum U'_ki y_k) r_i;  U x = y -> x_i = (y_i + sum U'_ik x_k) r_i.
+template <typename T> MRF_HD void chol_solve6n(T (&N)[6][6], T eps, const T* b, T* x) {
+    T inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        T s = N[j][j] - eps;
+#pragma unroll
+        for (int k = 0; k < j; ++k) s += N[k][j] * N[k][j];
+        T r = Mth<T>::rsqrt(-s);
+        inv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            T t = N[j][i];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t += N[k][j] * N[k][i];
+            N[j][i] = t * r;
+        }
+    }
+    T y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        T s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s += N[k][i] * y[k];
+        y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        T s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s += N[i][k] * x[k];
+        x[i] = s * inv[i];
+    }
+}
+template <typename T> MRF_HD void chol_solve6n_pair(P2<T> (&N)[6][6], T eps, const P2<T>* b, P2<T>* x) {
+    P2<T> inv[6];
+    const P2<T> ne = psplat(-eps);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        P2<T> s = padd(N[j][j], ne);
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = pfma(N[k][j], N[k][j], s);
+        P2<T> r = pmk(Mth<T>::rsqrt(-plo(s)), Mth<T>::rsqrt(-phi(s)));
+        inv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            P2<T> t = N[j][i];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = pfma(N[k][j], N[k][i], t);
+            N[j][i] = pmul(t, r);
+        }
+    }
+    P2<T> y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        P2<T> s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = pfma(N[k][i], y[k], s);
+        y[i] = pmul(s, inv[i]);
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        P2<T> s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) s = pfma(N[i][k], x[k], s);
+        x[i] = pmul(s, inv[i]);
+    }
+}
+
 template <typename T> MRF_HD void attractor_scalars(T n, T w, T& dpsi, T& m2) {
     // attractor_potential 5(|x| + 0.1 log(1 + exp(-20|x|))): d/d|x| = 5 tanh(10|x|);
     // attractor_metric (1.7 exp(-(0.75|x|)^2) + 0.3) I, L = xdot^T m xdot -> M = 2 m I
@@ -611,7 +697,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) G.M[i][j] = T(0);
-        G.M[i][i] = T(0.2); // base_energy 0.5*0.2*qd.qd
+        G.M[i][i] = T(-0.2); // base_energy 0.5*0.2*qd.qd (G.M, F.M hold -M)
         G.f[i] = T(0);
     }
     G.m7 = T(0.2);
@@ -629,7 +715,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         const P2<T> t = pmul(pmk(sl, T(1) - sl), ix);                          // s/x
         const P2<T> u = pmul(pmul(psplat(qd[i] * qd[i]), ix), t);              // s xdot^2/x^2
         const T Ml = T(0.2) * (plo(t) + phi(t));
-        if (i < 6) G.M[i][i] += Ml; else G.m7 += Ml;
+        if (i < 6) G.M[i][i] -= Ml; else G.m7 += Ml;
         const T du = plo(u) - phi(u);                                           // lower pushes +, upper -
         G.f[i] += T(-0.02) * du;
         num += qd[i] * (T(0.08) * du);
@@ -651,6 +737,12 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         return j < 2 ? mk(cfg.link1[r][0], cfg.link1[r][1], cfg.link1[r][2]) : kin_load(kin, NT, tid, j < 4 ? j - 2 : 2, 0);
     };
 
+    // Jacobian columns of the point being pulled back.  FP32: function scope, so that the hand's columns (link8, the last
+    // point of the loop) are still there for the attractors; FP64 recomputes them (18 doubles held across the attractor
+    // scalars would spill).
+    constexpr bool kKeepJ8 = sizeof(T) == 4;
+    V3<T> Jc[6];
+    bool have_j8 = false;
     // ---- collision leaves per distinct ego point (runtime loop: one copy of the leaf code keeps the kernel
     //      inside the instruction cache; the column count K of each point is warp-uniform) ----
     if (src.collide(cfg.has_coll != 0)) {
@@ -773,7 +865,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             acc.b.z += plo(acc2.b.z) + phi(acc2.b.z);
             num += plo(acc2.num) + phi(acc2.num);
             stiff_sum += (acc.A.xx + acc.A.yy) + acc.A.zz;
-            V3<T> Jc[6];
+            if (kKeepJ8 && e == kEgo - 1) have_j8 = true;
 #pragma unroll
             for (int j = 0; j < 6; ++j)
                 if (j < K) Jc[j] = cross(axis_of(ch, kin, NT, tid, j), p - org(j));
@@ -781,9 +873,9 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             for (int j = 0; j < 6; ++j) {
                 if (j < K) {
                     V3<T> AJ = symmul(acc.A, Jc[j]);
-                    G.f[j] += dot(Jc[j], acc.b);
+                    G.f[j] = dot_add(Jc[j], acc.b, G.f[j]);
 #pragma unroll
-                    for (int i = 0; i <= j; ++i) G.M[i][j] += dot(Jc[i], AJ);
+                    for (int i = 0; i <= j; ++i) G.M[i][j] = dot_sub(Jc[i], AJ, G.M[i][j]);
                 }
             }
         }
@@ -794,10 +886,11 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     // ---- q^T M_g q ----
     T qMq = G.m7 * qd[6] * qd[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        qMq += G.M[i][i] * qd[i] * qd[i];
+    for (int i = 0; i < 6; ++i) { // row sums first: one multiply-add per entry
+        T row = G.M[i][i] * qd[i];
 #pragma unroll
-        for (int j = i + 1; j < 6; ++j) qMq += T(2) * G.M[i][j] * qd[i] * qd[j];
+        for (int j = i + 1; j < 6; ++j) row += G.M[i][j] * (qd[j] + qd[j]);
+        qMq -= row * qd[i];
     }
     const T e = cfg.eps;
     const T a_geom = -num * Mth<T>::rcp(e + qMq);
@@ -829,15 +922,25 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         T dpsi1, m1;
         attractor_scalars(n1, prm[P_W1 * NT + tid], dpsi1, m1);
         V3<T> t1 = (x1 * (dpsi1 * Mth<T>::rcp(n1)) + rot(c8 - c7) * sigma) * m1;
-        V3<T> J8[6], Jr[6];
-        jac_cols<T, 6>(ch, kin, NT, tid, p8, org, J8);
+        // Both attractors are point loads.  Sub-goal 0 acts at the hand: columns J8_j, metric m0 I, force t0.  Sub-goal 1
+        // acts on the direction hand - link7, columns Jd_j = z_j x (p8 - p7), metric m1 R^T R, force R^T t1 (the rotation
+        // angle_goal_1 is folded into metric and force once instead of rotating every column).
+        const V3<T> u1{Rg[0] * t1.x + Rg[3] * t1.y + Rg[6] * t1.z, Rg[1] * t1.x + Rg[4] * t1.y + Rg[7] * t1.z,
+                       Rg[2] * t1.x + Rg[5] * t1.y + Rg[8] * t1.z};
+        const T nm1 = -m1, nm0 = -m0;
+        const Sym3<T> nW{nm1 * (Rg[0] * Rg[0] + Rg[3] * Rg[3] + Rg[6] * Rg[6]), nm1 * (Rg[0] * Rg[1] + Rg[3] * Rg[4] + Rg[6] * Rg[7]),
+                         nm1 * (Rg[0] * Rg[2] + Rg[3] * Rg[5] + Rg[6] * Rg[8]), nm1 * (Rg[1] * Rg[1] + Rg[4] * Rg[4] + Rg[7] * Rg[7]),
+                         nm1 * (Rg[1] * Rg[2] + Rg[4] * Rg[5] + Rg[7] * Rg[8]), nm1 * (Rg[2] * Rg[2] + Rg[5] * Rg[5] + Rg[8] * Rg[8])};
+        if (!kKeepJ8 || !have_j8) jac_cols<T, 6>(ch, kin, NT, tid, p8, org, Jc);
+        V3<T> Jd[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) Jr[j] = rot(cross(axis_of(ch, kin, NT, tid, j), d87));
+        for (int j = 0; j < 6; ++j) Jd[j] = cross(axis_of(ch, kin, NT, tid, j), d87);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-            F.f[j] += dot(J8[j], t0) + dot(Jr[j], t1);
+            const V3<T> A0 = Jc[j] * nm0, A1 = symmul(nW, Jd[j]);
+            F.f[j] = dot_add(Jc[j], t0, dot_add(Jd[j], u1, F.f[j]));
 #pragma unroll
-            for (int i = 0; i <= j; ++i) F.M[i][j] += m0 * dot(J8[i], J8[j]) + m1 * dot(Jr[i], Jr[j]);
+            for (int i = 0; i <= j; ++i) F.M[i][j] = dot_add(Jc[i], A0, dot_add(Jd[i], A1, F.M[i][j]));
         }
         // sub-goal 2: joint 7 -> x_goal_2
         T x2 = q[6] - prm[P_G2 * NT + tid];
@@ -857,15 +960,15 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
 #pragma unroll
             for (int i = 0; i <= j; ++i) M2[i][j] = pmk(G.M[i][j], F.M[i][j]);
         }
-        chol_solve6_pair(M2, e, b2, x2);
+        chol_solve6n_pair(M2, e, b2, x2);
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             hg[j] = plo(x2[j]);
             hf[j] = phi(x2[j]);
         }
     } else {
-        chol_solve6(G.M, e, G.f, hg);
-        chol_solve6(F.M, e, F.f, hf);
+        chol_solve6n(G.M, e, G.f, hg);
+        chol_solve6n(F.M, e, F.f, hf);
     }
     hg[6] = G.f[6] * Mth<T>::rcp(G.m7 + e);
     hf[6] = F.f[6] * Mth<T>::rcp(F.m7 + e);
