@@ -431,16 +431,19 @@ MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> co
 template <typename T> struct PointAcc2 {
     Sym3<P2<T>> A;
     V3<P2<T>> b;
-    P2<T> num;
+    V3<P2<T>> nv; // sum of d * gs * (f - f_e terms): dotted with the ego point's velocity once per point -> num
 };
 template <typename T> MRF_HD void acc2_zero(PointAcc2<T>& a) {
     const P2<T> z = psplat(T(0));
     a.A = Sym3<P2<T>>{z, z, z, z, z, z};
     a.b = V3<P2<T>>{z, z, z};
-    a.num = z;
+    a.nv = V3<P2<T>>{z, z, z};
 }
 // cM = 0.02 x multiplicity (d2L/dxdot2 coefficient of the leaf).  IRHO: every leaf of the loop has the same rho, the
 // caller passes irho = 1 / rho (one reciprocal per ego point instead of the combined-reciprocal trick per leaf).
+// The FP32 rollout spends two thirds of its FMA-pipe cycles here (a packed instruction occupies the pipe for two
+// cycles: packing halves the issue slots, not the pipe time), so the algebra is arranged for the fewest operations:
+// 58 packed instructions + 4 MUFU per pair of leaves.
 template <typename T, bool IRHO>
 MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>& cc, const V3<P2<T>>& xo,
                          const V3<P2<T>>& vo, const V3<P2<T>>& co, T vref, T aref, P2<T> rho, P2<T> irho, P2<T> cM, T sigma,
@@ -450,10 +453,11 @@ MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>
     V3<P2<T>> w{pfma(vo.x, nvref, v.x), pfma(vo.y, nvref, v.y), pfma(vo.z, nvref, v.z)};
     P2<T> n2 = pdot(d, d);
     P2<T> in1 = prsqrt(n2);
-    P2<T> gs, ix;
+    P2<T> gs, ix, nrin;
     if (IRHO) {
         gs = pmul(in1, irho);                   // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
         ix = prcp(pfma(n2, gs, m1));            // 1/x, x = n/rho - 1 = n^2/(n rho) - 1
+        nrin = pmul(in1, rho);                  // caller passes rho = -(r_o + r_b) on this path: -rho/n
     } else {
         // one reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) and 1/x
         P2<T> n = pmul(n2, in1);
@@ -462,11 +466,10 @@ MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>
         P2<T> u = prcp(pmul(nr, t));
         gs = pmul(u, t);
         ix = pmul(pmul(u, nr), rho);
+        nrin = pmul(pmul(in1, rho), m1);
     }
-    P2<T> dw = pdot(d, w), da = pdot(d, co), dv = pdot(d, v);
+    P2<T> dw = pdot(d, w), da = pdot(d, co);
     P2<T> wc = pfma(d.z, cc.z, pfma(d.y, cc.y, pfma(d.x, cc.x, pdot(w, w)))); // |w|^2 + d.c
-    P2<T> q = pmul(dw, in1);                                      // component of w along d
-    P2<T> inner = pfma(pmul(q, m1), q, wc);                       // (kappa + g.c)/gs = |w|^2 - q^2 + d.c
     P2<T> ix2 = pmul(ix, ix), ix4 = pmul(ix2, ix2);
     P2<T> Ml = pmul(cM, ix4);                                     // d2L/dxdot2 = 0.02 w / x^4
     P2<T> Mg = pmul(Ml, gs);
@@ -475,10 +478,11 @@ MRF_HD void sphere_leaf2(const V3<P2<T>>& p, const V3<P2<T>>& v, const V3<P2<T>>
     P2<T> hh = pmul(ix4, psplat(T(-0.5)));
     P2<T> fl = pmul(u1, hh);                                      // M h, h = -0.5 xdot^2 / x^4
     P2<T> fd = pmul(u1, pfma(ix, psplat(T(2)), hh));              // f_l - f_e,l (Euler-Lagrange force -2 M xdot^2 / x)
-    P2<T> s1 = pfma(psplat(sigma), inner, pmul(psplat(-aref), da));
-    P2<T> fq = pfma(Mg, s1, fl);
-    P2<T> e1 = pfma(pmul(Mg, psplat(sigma - T(1))), inner, fd);
-    acc.num = pfma(pmul(dv, gs), e1, acc.num);
+    // X = M |grad x| (kappa + g.c) = Mg (|w|^2 + d.c) - Mg (d.w)^2 / n^2, and Mg (d.w)^2 / n^2 = u1 rho / n
+    P2<T> X = pfma(u1, nrin, pmul(Mg, wc));
+    P2<T> fq = pfma(X, psplat(sigma), pfma(pmul(Mg, da), psplat(-aref), fl));
+    P2<T> ge = pmul(gs, pfma(X, psplat(sigma - T(1)), fd));
+    acc.nv.x = pfma(d.x, ge, acc.nv.x); acc.nv.y = pfma(d.y, ge, acc.nv.y); acc.nv.z = pfma(d.z, ge, acc.nv.z);
     V3<P2<T>> Md{pmul(d.x, k), pmul(d.y, k), pmul(d.z, k)};
     acc.A.xx = pfma(Md.x, d.x, acc.A.xx); acc.A.xy = pfma(Md.x, d.y, acc.A.xy); acc.A.xz = pfma(Md.x, d.z, acc.A.xz);
     acc.A.yy = pfma(Md.y, d.y, acc.A.yy); acc.A.yz = pfma(Md.y, d.z, acc.A.yz); acc.A.zz = pfma(Md.z, d.z, acc.A.zz);
@@ -495,13 +499,13 @@ MRF_HD void plane_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> nh, T dn, T rb, T wt, T
     T s = xd > T(0) ? T(0) : (xd < T(0) ? T(1) : T(0.5)); // -0.5 (sign(xdot) - 1)
     T ix = Mth<T>::rcp(x);
     T xd2 = xd * xd;
-    T Ml = T(0.2) * s * ix * ix * wt;
-    T fel = T(-0.2) * s * xd2 * ix * ix * ix * wt;
+    T Ml = ((T(0.2) * wt) * s) * ix * ix;                  // d2L/dxdot2 = 0.2 s / x^2
+    T u = Ml * xd2;                                         // f_e = -u / x
     T h = T(-10) * xd2 * Mth<T>::rcp(T(1) + Mth<T>::exp(T(10) * x));
     T fl = Ml * h;
-    T curv = dot(nh, cc);
-    T fq = fl + Ml * sigma * curv;
-    num += xd * ((fl - fel) + Ml * (sigma - T(1)) * curv);
+    T X = Ml * dot(nh, cc);
+    T fq = fl + sigma * X;
+    num += xd * ((fl + u * ix) + (sigma - T(1)) * X);
     V3<T> Mg = nh * Ml;
     acc.A.xx += Mg.x * nh.x; acc.A.xy += Mg.x * nh.y; acc.A.xz += Mg.x * nh.z;
     acc.A.yy += Mg.y * nh.y; acc.A.yz += Mg.y * nh.z; acc.A.zz += Mg.z * nh.z;
@@ -821,7 +825,8 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 acc.A.yz = pick(om[0].A.yz, om[1].A.yz, om[2].A.yz); acc.A.zz = pick(om[0].A.zz, om[1].A.zz, om[2].A.zz);
                 acc.b.x = pick(om[0].b.x, om[1].b.x, om[2].b.x); acc.b.y = pick(om[0].b.y, om[1].b.y, om[2].b.y);
                 acc.b.z = pick(om[0].b.z, om[1].b.z, om[2].b.z);
-                num += pick(om[0].num, om[1].num, om[2].num);
+                num += dot(v, mk(pick(om[0].nv.x, om[1].nv.x, om[2].nv.x), pick(om[0].nv.y, om[1].nv.y, om[2].nv.y),
+                                 pick(om[0].nv.z, om[1].nv.z, om[2].nv.z)));
             }
             const V3<P2<T>> p2{psplat(p.x), psplat(p.y), psplat(p.z)}, v2{psplat(v.x), psplat(v.y), psplat(v.z)},
                 c2{psplat(cc.x), psplat(cc.y), psplat(cc.z)};
@@ -833,9 +838,10 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                     // FP32: sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2)
                     const P2<T> cw = psplat(T(0.02) * we);
                     if constexpr (Src::kUniformRadius) {
-                        const P2<T> irho = psplat(Mth<T>::rcp(src.ro + rb)); // one rho for every leaf of this ego point
-                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
-                            sphere_leaf2<T, true>(p2, v2, c2, xo, vo, co, src.vref, src.aref, ro, irho, pmul(wo, cw), sigma, acc2);
+                        // one rho for every leaf of this ego point: 1/rho and -rho go in
+                        const P2<T> irho = psplat(Mth<T>::rcp(src.ro + rb)), nrho = psplat(-(src.ro + rb));
+                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T>, P2<T> wo) {
+                            sphere_leaf2<T, true>(p2, v2, c2, xo, vo, co, src.vref, src.aref, nrho, irho, pmul(wo, cw), sigma, acc2);
                         });
                     } else {
                         src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
@@ -863,7 +869,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
             acc.A.yz += plo(acc2.A.yz) + phi(acc2.A.yz); acc.A.zz += plo(acc2.A.zz) + phi(acc2.A.zz);
             acc.b.x += plo(acc2.b.x) + phi(acc2.b.x); acc.b.y += plo(acc2.b.y) + phi(acc2.b.y);
             acc.b.z += plo(acc2.b.z) + phi(acc2.b.z);
-            num += plo(acc2.num) + phi(acc2.num);
+            num += dot(v, mk(plo(acc2.nv.x) + phi(acc2.nv.x), plo(acc2.nv.y) + phi(acc2.nv.y), plo(acc2.nv.z) + phi(acc2.nv.z)));
             stiff_sum += (acc.A.xx + acc.A.yy) + acc.A.zz;
             if (kKeepJ8 && e == kEgo - 1) have_j8 = true;
 #pragma unroll
