@@ -111,6 +111,7 @@ template <> struct Mth<float> {
         *s = (q & 2) ? -ss : ss;
         *c = ((q + 1) & 2) ? -cc : cc;
     }
+    static MRF_HD float fma(float a, float b, float c) { return ::fmaf(a, b, c); } // explicit: never re-associated
     static MRF_HD float abs(float x) { return ::fabsf(x); }
     static MRF_HD float max(float a, float b) { return ::fmaxf(a, b); }
 };
@@ -134,6 +135,7 @@ template <> struct Mth<double> {
         *c = ::cos(x);
 #endif
     }
+    static MRF_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
     static MRF_HD double abs(double x) { return ::fabs(x); }
     static MRF_HD double max(double a, double b) { return ::fmax(a, b); }
 };
@@ -812,8 +814,6 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 passes = 0;
             }
             if (!Src::kFullLinks && passes == 0) continue; // no collision link at this point: no leaves, nothing to pull back
-            PointAcc2<T> acc2;
-            acc2_zero(acc2);
             if (kObstMajor) {
                 // pick this point's accumulators from the pair slots: link3 = slot0.lo, link4 = slot0.hi,
                 // link5 + link6 = slot1.lo + slot1.hi (same point), link7 = slot2.lo, link8 = slot2.hi
@@ -828,28 +828,12 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 num += dot(v, mk(pick(om[0].nv.x, om[1].nv.x, om[2].nv.x), pick(om[0].nv.y, om[1].nv.y, om[2].nv.y),
                                  pick(om[0].nv.z, om[1].nv.z, om[2].nv.z)));
             }
-            const V3<P2<T>> p2{psplat(p.x), psplat(p.y), psplat(p.z)}, v2{psplat(v.x), psplat(v.y), psplat(v.z)},
-                c2{psplat(cc.x), psplat(cc.y), psplat(cc.z)};
+            // scalar leaves first (plane, static spheres; every sphere for FP64) ...
+            constexpr bool kPackedSpheres = sizeof(T) == 4 && !kObstMajor;
+            const T rb0 = rb;
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
-                if (kObstMajor) {
-                    // sphere leaves already accumulated above
-                } else if (sizeof(T) == 4) {
-                    // FP32: sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2)
-                    const P2<T> cw = psplat(T(0.02) * we);
-                    if constexpr (Src::kUniformRadius) {
-                        // one rho for every leaf of this ego point: 1/rho and -rho go in
-                        const P2<T> irho = psplat(Mth<T>::rcp(src.ro + rb)), nrho = psplat(-(src.ro + rb));
-                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T>, P2<T> wo) {
-                            sphere_leaf2<T, true>(p2, v2, c2, xo, vo, co, src.vref, src.aref, nrho, irho, pmul(wo, cw), sigma, acc2);
-                        });
-                    } else {
-                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
-                            sphere_leaf2<T, false>(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)), ro,
-                                                   pmul(wo, cw), sigma, acc2);
-                        });
-                    }
-                } else {
+                if (!kPackedSpheres && !kObstMajor) {
                     // FP64: no packed instructions exist and pairing doubles the live registers -> one leaf at a time
                     src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
                         sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
@@ -864,12 +848,43 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                     });
                 plane_leaf(p, v, cc, nh, dn, rb, we, sigma, acc, num);
             }
-            acc.A.xx += plo(acc2.A.xx) + phi(acc2.A.xx); acc.A.xy += plo(acc2.A.xy) + phi(acc2.A.xy);
-            acc.A.xz += plo(acc2.A.xz) + phi(acc2.A.xz); acc.A.yy += plo(acc2.A.yy) + phi(acc2.A.yy);
-            acc.A.yz += plo(acc2.A.yz) + phi(acc2.A.yz); acc.A.zz += plo(acc2.A.zz) + phi(acc2.A.zz);
-            acc.b.x += plo(acc2.b.x) + phi(acc2.b.x); acc.b.y += plo(acc2.b.y) + phi(acc2.b.y);
-            acc.b.z += plo(acc2.b.z) + phi(acc2.b.z);
-            num += dot(v, mk(plo(acc2.nv.x) + phi(acc2.nv.x), plo(acc2.nv.y) + phi(acc2.nv.y), plo(acc2.nv.z) + phi(acc2.nv.z)));
+            if (kPackedSpheres) {
+                // ... then the FP32 sphere leaves two at a time with packed FP32x2 instructions (sm_100a FFMA2 / FMUL2); the
+                // scalar sums seed the lo halves of the pair accumulators, so folding the pairs is one addition per entry
+                PointAcc2<T> acc2;
+                acc2.A = Sym3<P2<T>>{pmk(acc.A.xx, T(0)), pmk(acc.A.xy, T(0)), pmk(acc.A.xz, T(0)),
+                                     pmk(acc.A.yy, T(0)), pmk(acc.A.yz, T(0)), pmk(acc.A.zz, T(0))};
+                acc2.b = V3<P2<T>>{pmk(acc.b.x, T(0)), pmk(acc.b.y, T(0)), pmk(acc.b.z, T(0))};
+                acc2.nv = V3<P2<T>>{psplat(T(0)), psplat(T(0)), psplat(T(0))};
+                const V3<P2<T>> p2{psplat(p.x), psplat(p.y), psplat(p.z)}, v2{psplat(v.x), psplat(v.y), psplat(v.z)},
+                    c2{psplat(cc.x), psplat(cc.y), psplat(cc.z)};
+                const P2<T> cw = psplat(T(0.02) * we);
+                rb = rb0;
+                for (int pass = 0; pass < passes; ++pass) {
+                    if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
+                    if constexpr (Src::kUniformRadius) {
+                        // one rho for every leaf of this ego point: 1/rho and -rho go in
+                        const P2<T> irho = psplat(Mth<T>::rcp(src.ro + rb)), nrho = psplat(-(src.ro + rb));
+                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T>, P2<T> wo) {
+                            sphere_leaf2<T, true>(p2, v2, c2, xo, vo, co, src.vref, src.aref, nrho, irho, pmul(wo, cw), sigma, acc2);
+                        });
+                    } else {
+                        src.each2([&](const V3<P2<T>>& xo, const V3<P2<T>>& vo, const V3<P2<T>>& co, P2<T> ro, P2<T> wo) {
+                            sphere_leaf2<T, false>(p2, v2, c2, xo, vo, co, src.vref, src.aref, padd(ro, psplat(rb)), ro,
+                                                   pmul(wo, cw), sigma, acc2);
+                        });
+                    }
+                }
+                acc.A.xx = plo(acc2.A.xx) + phi(acc2.A.xx); acc.A.xy = plo(acc2.A.xy) + phi(acc2.A.xy);
+                acc.A.xz = plo(acc2.A.xz) + phi(acc2.A.xz); acc.A.yy = plo(acc2.A.yy) + phi(acc2.A.yy);
+                acc.A.yz = plo(acc2.A.yz) + phi(acc2.A.yz); acc.A.zz = plo(acc2.A.zz) + phi(acc2.A.zz);
+                acc.b.x = plo(acc2.b.x) + phi(acc2.b.x); acc.b.y = plo(acc2.b.y) + phi(acc2.b.y);
+                acc.b.z = plo(acc2.b.z) + phi(acc2.b.z);
+                // explicit multiply-adds: the compiler's choice of which products of a scalar sum to contract differed between
+                // two instantiations of the rollout kernel (host-record / device layouts must stay bitwise identical)
+                num = Mth<T>::fma(v.x, plo(acc2.nv.x) + phi(acc2.nv.x),
+                                  Mth<T>::fma(v.y, plo(acc2.nv.y) + phi(acc2.nv.y), Mth<T>::fma(v.z, plo(acc2.nv.z) + phi(acc2.nv.z), num)));
+            }
             stiff_sum += (acc.A.xx + acc.A.yy) + acc.A.zz;
             if (kKeepJ8 && e == kEgo - 1) have_j8 = true;
 #pragma unroll
