@@ -289,8 +289,10 @@ MRF_HD void chain_forward(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
     ch.z[5] = fr_joint<T, 1>(f, q[5], qd[5]);                        // joint6 (zero offset)
     fr_advance(f, f.a * T(0.088));                                   // joint7 origin (0.088,0,0)
     kin_store(kin, NT, tid, 3, f);                                   // link7
-    (void)fr_joint<T, 1>(f, q[6], qd[6]);
-    fr_advance(f, f.n * T(0.107));                                   // fixed joint8 (0,0,0.107); hand == link8
+    // joint7 turns about the very axis the hand sits on (fixed joint8 (0,0,0.107) along it): hand position, velocity and
+    // d(J qdot)/dq qdot do not depend on q7 / qdot7 (the angular terms cancel identically), so only the roll of the joint
+    // frame is applied -- its axis is -b -- and the joint itself (sincos, angular updates) is skipped
+    fr_advance(f, f.b * T(-0.107));                                  // hand == link8
     kin_store(kin, NT, tid, 4, f);                                   // link8
     if (kAxesInSmem<T>) {
 #pragma unroll
@@ -1095,7 +1097,11 @@ template <typename T, int R> struct SmemSrcUniform {
     template <typename F> MRF_HD void each2(F f) const {
         constexpr int NT = kTile * R;
         const P2<T> ro2 = psplat(ro);
+#ifdef MRF_EACH2_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int j = 0; j < R; ++j) {
             if (j == r) continue;
             const int t = j * kTile + lane;
