@@ -729,6 +729,7 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
         num += qd[i] * (T(0.08) * du);
     }
 
+
     // joint origins: FP64 re-reads them from the point table where a Jacobian column is formed (not held across the
     // leaves); FP32 keeps them in registers
     V3<T> org_[6];
@@ -792,6 +793,42 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                                            sigma, om[ps]);
             });
         }
+        // FP64 with a global-memory source: obstacle-major as well, one scalar leaf per (sphere, ego point), the five task-space
+        // accumulators in registers and the ego points re-read from shared memory -- the list is fetched once instead of
+        // five times and the five leaves of a sphere are independent instruction streams for the FP64 pipe
+#ifdef MRF_NO_OBSTMAJOR_F64
+        constexpr bool kObstMajorD = false;
+#else
+        constexpr bool kObstMajorD = Src::kObstacleMajor && sizeof(T) == 8;
+#endif
+        PointAcc<T> od[kEgo];
+        if (kObstMajorD) {
+            T rbv[6], wl[6];
+#pragma unroll
+            for (int l = 0; l < 6; ++l) {
+                rbv[l] = prm[(P_RB + l) * NT + tid];
+                wl[l] = T((em >> l) & 1);
+            }
+            if (wl[2] > T(0) && wl[3] > T(0) && rbv[2] == rbv[3]) { // link5 == link6: one leaf of weight 2
+                wl[2] = T(2);
+                wl[3] = T(0);
+            }
+#pragma unroll
+            for (int e = 0; e < kEgo; ++e) {
+                od[e].A = Sym3<T>{T(0), T(0), T(0), T(0), T(0), T(0)};
+                od[e].b = mk(T(0), T(0), T(0));
+            }
+            src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
+#pragma unroll
+                for (int e = 0; e < kEgo; ++e) {
+                    const int l = e + (e > 2 ? 1 : 0);
+                    const V3<T> pe = kin_load(kin, NT, tid, e, 0), ve = kin_load(kin, NT, tid, e, 3), ce = kin_load(kin, NT, tid, e, 6);
+                    sphere_leaf(pe, ve, ce, xo, vo, co, src.vref, src.aref, ro + rbv[l], wl[l] * wo, sigma, od[e], num);
+                    if (e == 2 && wl[3] > T(0))
+                        sphere_leaf(pe, ve, ce, xo, vo, co, src.vref, src.aref, ro + rbv[3], wl[3] * wo, sigma, od[e], num);
+                }
+            });
+        }
 #pragma unroll 1
         for (int e = 0; e < kEgo; ++e) {
             const int K = e < 3 ? e + 2 : 6;           // link3: 2, link4: 3, link5/6: 4, link7: 6, link8: 6 joints
@@ -830,12 +867,24 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 num += dot(v, mk(pick(om[0].nv.x, om[1].nv.x, om[2].nv.x), pick(om[0].nv.y, om[1].nv.y, om[2].nv.y),
                                  pick(om[0].nv.z, om[1].nv.z, om[2].nv.z)));
             }
+            if (kObstMajorD) {
+                auto pk = [&](T a0, T a1, T a2, T a3, T a4) { return e == 0 ? a0 : e == 1 ? a1 : e == 2 ? a2 : e == 3 ? a3 : a4; };
+                acc.A.xx = pk(od[0].A.xx, od[1].A.xx, od[2].A.xx, od[3].A.xx, od[4].A.xx);
+                acc.A.xy = pk(od[0].A.xy, od[1].A.xy, od[2].A.xy, od[3].A.xy, od[4].A.xy);
+                acc.A.xz = pk(od[0].A.xz, od[1].A.xz, od[2].A.xz, od[3].A.xz, od[4].A.xz);
+                acc.A.yy = pk(od[0].A.yy, od[1].A.yy, od[2].A.yy, od[3].A.yy, od[4].A.yy);
+                acc.A.yz = pk(od[0].A.yz, od[1].A.yz, od[2].A.yz, od[3].A.yz, od[4].A.yz);
+                acc.A.zz = pk(od[0].A.zz, od[1].A.zz, od[2].A.zz, od[3].A.zz, od[4].A.zz);
+                acc.b.x = pk(od[0].b.x, od[1].b.x, od[2].b.x, od[3].b.x, od[4].b.x);
+                acc.b.y = pk(od[0].b.y, od[1].b.y, od[2].b.y, od[3].b.y, od[4].b.y);
+                acc.b.z = pk(od[0].b.z, od[1].b.z, od[2].b.z, od[3].b.z, od[4].b.z);
+            }
             // scalar leaves first (plane, static spheres; every sphere for FP64) ...
             constexpr bool kPackedSpheres = sizeof(T) == 4 && !kObstMajor;
             const T rb0 = rb;
             for (int pass = 0; pass < passes; ++pass) {
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
-                if (!kPackedSpheres && !kObstMajor) {
+                if (!kPackedSpheres && !kObstMajor && !kObstMajorD) {
                     // FP64: no packed instructions exist and pairing doubles the live registers -> one leaf at a time
                     src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
                         sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
