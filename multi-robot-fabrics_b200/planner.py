@@ -728,6 +728,23 @@ class StateMachine:
     def get_success_rate(self):
         return (int(self._st[1, 0, 0]) - int(self._st[2, 0, 0])) / self.nr_blocks_panda
 
+    # small read-outs of the reference class (state_machine.py:50-67,130-131); host side, the hand position comes from
+    # the same `fk_fun_ee` callable the decision step uses
+    def get_x_ee(self, q_robot):
+        return np.asarray(self.fk_fun_ee(q_robot), dtype=np.float64).reshape(3)
+
+    def get_distance_ee_goal(self, q_robot, goal):
+        return float(np.linalg.norm(self.get_x_ee(q_robot)[:2] - np.asarray(goal, dtype=np.float64).reshape(-1)[:2]))
+
+    def get_distance_ee_goal3(self, q_robot, goal):
+        return float(np.linalg.norm(self.get_x_ee(q_robot) - np.asarray(goal, dtype=np.float64).reshape(3)))
+
+    def get_distance_ee_start(self, q_robot):
+        return float(np.linalg.norm(self.get_x_ee(q_robot) - self.start_goal))
+
+    def get_gripper_status(self):
+        return ("close" if int(self._st[4, 0, 0]) else "open"), "open"   # (panda, second-robot slot: unused for Pandas)
+
     def get_gripper_action_panda(self, q_panda_gripper):
         """The action computed with the last get_state_machine_panda call's gripper state (same q as the reference's
         call order, example_pandas_Jointspace.py:301,447)."""

@@ -122,6 +122,24 @@ def test_action_matches_oracle(fabs, n_rob, S):
     assert np.abs(act32 - ref)[ok].max() < 2e-3
 
 
+def test_action_nonuniform_body_radii(fabs):
+    """Executed action with a different radius on every ego link (link5 != link6: two leaves at one point) -- the
+    obstacle-major accumulation of both precisions must treat the shared point like the oracle does."""
+    B, S = 40, 12
+    rng = np.random.default_rng(21)
+    rec = m.scenarios.generate(B, 2, seed=14, weight_goal_1=20.0)
+    rec[:, :, o2.RB:o2.RB + 6] = [0.08, 0.07, 0.09, 0.06, 0.08, 0.1]
+    obst = random_obstacles(rng, B, 2, S, rec)
+    fab = get_fab(fabs, 2)
+    ref = oracle_actions(rec, obst)
+    ok = np.isfinite(ref).all(axis=(1, 2))
+    assert ok.sum() > 0.8 * B
+    act = fab.action_host(rec, obst, dtype="f64")
+    assert rel_ps(act, ref, ok) < F64_RTOL
+    act32 = fab.action_host(rec, obst, dtype="f32")
+    assert np.abs(act32 - ref)[ok].max() < 2e-3
+
+
 def test_action_acc_mode_and_grasp_planner(fabs):
     """mode 'acc' returns qdd; has_collision_links=0 is the grasp planner (example_pandas_Jointspace.py:160-166)."""
     B = 20
