@@ -221,8 +221,12 @@ class ForwardFabricsPlanner:
         self.goal_struct_robots = goal_struct_robots
         self.nr_subgoals = [3] * self.nr_robots
         self.dtype = dtype
-        if self.fabrics_mode != "vel":
-            raise MrfError("joint-space rollouts are defined for fabrics_mode 'vel' (forward_planner_Jointspace.py:233)")
+        if self.fabrics_mode not in ("vel", "acc"):
+            raise MrfError("fabrics_mode must be 'vel' or 'acc'")
+        # 'acc' reproduces what the reference's loop does, not a double integrator: the acceleration handed to system_step
+        # is reset to zero every step (forward_planner_Jointspace.py:195,202), so q advances with the stored velocity, and
+        # the planner's output -- an acceleration in this mode -- is written into q_dot (:233).  The kernels' recurrence
+        # (q += dt q_dot; q_dot = action) is exactly that with MrfConfig.mode = 0.
         if len(set(self.nr_obsts)) > 1:
             raise MrfError("the CUDA rollout takes the same number of static spheres for every robot")
         self.radius_obsts = getattr(params, "radius_obsts", None)
@@ -237,6 +241,7 @@ class ForwardFabricsPlanner:
                 r_full[i][int(c) - 1] = float(self.r_robots[i][z])
         mounts = [np.asarray(p.mount) for p in planners]
         cfg = default_config(self.nr_robots, dt=self.dt, static_or_dyn=int(params.STATIC_OR_DYN_FABRICS),
+                             mode=1 if self.fabrics_mode == "vel" else 0,
                              mount=mounts, r_robots=r_full, estimate_goal=int(estimate_goal),
                              collision_links=[list(c) for c in self.collision_links_nrs])
         self.fab = Fabrics(config=cfg, device=device)
