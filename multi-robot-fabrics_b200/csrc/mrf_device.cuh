@@ -421,34 +421,45 @@ template <typename T> struct Spec {
 
 // One sphere leaf (collision_geometry "-0.5/x^4 xdot^2", collision_finsler "0.01/x^4 xdot^2",
 // examples/example_pandas_Jointspace.py:88-89) of ego point (p, v, c) against sphere (xo, vo, ao), in the
-// point's task space.  wt = multiplicity of identical leaves.
-template <typename T>
+// point's task space.  wt = multiplicity of identical leaves.  Same arrangement of the algebra as the packed
+// sphere_leaf2 below (the FP64 kernels are bound by the FP64 pipe's issue rate, so operations count there too).
+// IRHO: every leaf of the caller's loop has the same rho and the caller passes irho = 1 / rho.
+template <typename T, bool IRHO = false>
 MRF_HD void sphere_leaf(V3<T> p, V3<T> v, V3<T> cc, V3<T> xo, V3<T> vo, V3<T> co, T vref, T aref, T rho, T wt,
-                        T sigma, PointAcc<T>& acc, T& num) {
+                        T sigma, PointAcc<T>& acc, T& num, T irho = T(0)) {
     // obstacle velocity = vref * vo, obstacle acceleration = aref * co (the scalars are applied to dot products)
     V3<T> d = p - xo;
     V3<T> w = mk(v.x - vref * vo.x, v.y - vref * vo.y, v.z - vref * vo.z);
     T n2 = dot(d, d);
     T in1 = Mth<T>::rsqrt(n2);
-    T n = n2 * in1;
-    // x = n/rho - 1.  One reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) (gradient scale) and 1/x.
-    T t = n - rho;
-    T nr = n * rho;
-    T u = Mth<T>::rcp(nr * t);
-    T gs = u * t;                        // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
-    T ix = (u * nr) * rho;               // 1/x = rho/(n - rho)
-    T dw = dot(d, w), dc = dot(d, cc), da = dot(d, co), dv = dot(d, v), ww = dot(w, w);
-    T inner = (ww - (dw * dw) * (in1 * in1)) + dc;   // (kappa + g.c) / gs
-    T xd = dw * gs;
+    T gs, ix;
+    if (IRHO) {
+        gs = in1 * irho;                                   // 1/(n rho): g = d * gs is the gradient of x w.r.t. the point
+        ix = Mth<T>::rcp(Mth<T>::fma(n2, gs, T(-1)));      // 1/x, x = n/rho - 1 = n^2/(n rho) - 1
+    } else {
+        // x = n/rho - 1.  One reciprocal u = 1/(n rho (n - rho)) gives both 1/(n rho) (gradient scale) and 1/x.
+        T n = n2 * in1;
+        T t = n - rho;
+        T nr = n * rho;
+        T u = Mth<T>::rcp(nr * t);
+        gs = u * t;
+        ix = (u * nr) * rho;                               // 1/x = rho/(n - rho)
+    }
+    T dw = dot(d, w), da = dot(d, co), dv = dot(d, v);
+    T wc = dot_add(d, cc, dot(w, w));                      // |w|^2 + d.c
     T ix2 = ix * ix, ix4 = ix2 * ix2;
-    T hx = (xd * xd) * ix4;
-    T Ml = (T(0.02) * wt) * ix4;         // d2L/dxdot2 (x multiplicity)
-    T fl = Ml * (T(-0.5) * hx);          // M h
-    T fel = (T(-0.04) * wt) * (hx * ix); // Euler-Lagrange force of the leaf energy
+    T Ml = (T(0.02) * wt) * ix4;                           // d2L/dxdot2 (x multiplicity)
     T Mg = Ml * gs;
-    T fq = fl + Mg * (sigma * inner - aref * da);
-    num += (dv * gs) * ((fl - fel) + (Mg * (sigma - T(1))) * inner);
-    V3<T> Md = d * (Mg * gs);
+    T k = Mg * gs;
+    T u1 = k * (dw * dw);                                  // M xdot^2, xdot = (d.w) gs
+    T hh = T(-0.5) * ix4;
+    T fl = u1 * hh;                                        // M h, h = -0.5 xdot^2 / x^4
+    T fd = u1 * Mth<T>::fma(T(2), ix, hh);                 // f_l - f_e,l (Euler-Lagrange force of the leaf energy: -2 M xdot^2 / x)
+    // X = M |grad x| (kappa + g.c) = Mg (|w|^2 + d.c) - Mg (d.w)^2 / n^2, and Mg (d.w)^2 / n^2 = u1 rho / n
+    T X = Mth<T>::fma(-u1, rho * in1, Mg * wc);
+    T fq = Mth<T>::fma(sigma, X, Mth<T>::fma(-aref, Mg * da, fl));
+    num = Mth<T>::fma(dv * gs, Mth<T>::fma(sigma - T(1), X, fd), num);
+    V3<T> Md = d * k;
     acc.A.xx += Md.x * d.x; acc.A.xy += Md.x * d.y; acc.A.xz += Md.x * d.z;
     acc.A.yy += Md.y * d.y; acc.A.yz += Md.y * d.z; acc.A.zz += Md.z * d.z;
     acc.b = acc.b + d * (gs * fq);
@@ -910,9 +921,16 @@ MRF_HD void fabric_action(const DevCfg<T>& cfg, int r, const T* q, const T* qd, 
                 if (pass == 1) rb = prm[(P_RB + rb_first + 1) * NT + tid];
                 if (!kPackedSpheres && !kObstMajor && !kObstMajorD) {
                     // FP64: no packed instructions exist and pairing doubles the live registers -> one leaf at a time
-                    src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
-                        sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
-                    });
+                    if constexpr (Src::kUniformRadius) {
+                        const T rho = src.ro + rb, irho = Mth<T>::rcp(rho); // one rho for every leaf of this ego point
+                        src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T, T wo) {
+                            sphere_leaf<T, true>(p, v, cc, xo, vo, co, src.vref, src.aref, rho, we * wo, sigma, acc, num, irho);
+                        });
+                    } else {
+                        src.each([&](V3<T> xo, V3<T> vo, V3<T> co, T ro, T wo) {
+                            sphere_leaf(p, v, cc, xo, vo, co, src.vref, src.aref, ro + rb, we * wo, sigma, acc, num);
+                        });
+                    }
                 }
                 // static spheres of the rollout planners (x_obst_i, radius_obst_i; forward_planner_Jointspace.py:319-322):
                 // the same leaf with a sphere at rest
