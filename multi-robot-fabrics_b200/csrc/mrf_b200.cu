@@ -1159,6 +1159,14 @@ template <typename K> static int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) MRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return MRF_OK;
 }
+// Kernels that run NEXT TO the rollout kernels on the same SMs (the post step of a sweep: guard select, FP64 re-roll,
+// deadlock heuristic) ask for the same L1 / shared-memory split as the rollouts: an SM changes its carve-out only when it
+// is empty, so a kernel preferring another split has to wait for -- and idles -- whole SMs.
+template <typename K> static void same_carveout(K kernel) {
+#ifndef MRF_NO_CARVEOUT
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
+}
 
 // ---------------------------------- device-pointer entries --------------------------------------
 template <typename T>
@@ -1197,6 +1205,7 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
 #define MRF_LAUNCH_ROLLOUT_K(RR, UU, AA, SS)                                                                         \
     {                                                                                                                \
         rc = set_smem(rollout_kernel<T, RR, UU, AA, SS>, smem);                                                      \
+        same_carveout(rollout_kernel<T, RR, UU, AA, SS>);                                                            \
         if (rc) return rc;                                                                                           \
         rollout_kernel<T, RR, UU, AA, SS><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(                       \
             devcfg<T>(h), rec, N, avg_vel, x_ee, goal_est, qN, qdN, (long long)B, h->d_sync + 2 * sync_slot,        \
@@ -1301,7 +1310,12 @@ static int deadlock_dev(mrf_handle_t h, const T* x_ee, T* goals, T* weights, con
             c.n_robots, c.dl_time_wait, c.dl_time_gate, c.dl_avg_vel_constant, c.dl_dist_constant,
             c.dl_goal_weight_follower, c.dl_goal_weight_leader, c.dl_nr_goal_scale, c.dl_dist_endeff, c.dl_backoff};
     const long long dl_blocks = (B + 255) / 256;
-    deadlock_kernel<T><<<(unsigned)(dl_blocks < 64 ? dl_blocks : 64), 256, 0, (cudaStream_t)stream>>>(
+    same_carveout(deadlock_kernel<T>);
+    // Grid-stride.  As the last kernel of a sweep's post step (result tensor given) it runs next to the rollouts of the
+    // following batches, where every CTA it places takes a slot from them: 16 CTAs instead of 64 cost the sweep 0.5 % less
+    // (measured; fewer still lengthen the chain).  A stand-alone call wants the latency of the wider grid.
+    const long long dl_grid = result != nullptr ? 16 : 64;
+    deadlock_kernel<T><<<(unsigned)(dl_blocks < dl_grid ? dl_blocks : dl_grid), 256, 0, (cudaStream_t)stream>>>(
         d, x_ee, goals, weights, avg_vel, avg_sum, sm_state, time_step, tdo, st_int, st_goal, flag, goal_est, (long long)B,
         ov, result);
     MRF_CUDA(cudaGetLastError());
@@ -1446,6 +1460,7 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
                    {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_rel[0], h->guard_rel[1], h->guard_rel[2]},
                    {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
         const long long sel_blocks = (B + 255) / 256;
+        same_carveout(guard_select_kernel<T>);
         guard_select_kernel<T><<<(unsigned)(sel_blocks < 64 ? sel_blocks : 64), 256, 0, st>>>(
             g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk, sm_state, time_step, h->cfg.dl_time_gate,
             h->cfg.dl_dist_constant, slot_of, counters, list, (long long)B);
