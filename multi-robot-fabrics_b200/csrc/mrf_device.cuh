@@ -182,7 +182,10 @@ template <> struct Mth<double> {
         const double r = (1.0 - t) * rcp(1.0 + t);
         return ::copysign(r, x);
     }
-    static __device__ __forceinline__ void sincos(double x, double* s, double* c) {
+    static __device__ __forceinline__ void sincos(double x0, double* s, double* c) {
+        // joint angles are a few radians; a rollout that has blown up stays finite and bounded (the quadrant counter is the
+        // low word of t: valid below 2^31 quarter turns), NaN passes through the comparisons
+        const double x = x0 > 1.0e9 ? 1.0e9 : (x0 < -1.0e9 ? -1.0e9 : x0);
         const double t = ::fma(x, 0.6366197723675814, 6755399441055744.0);
         const double k = t - 6755399441055744.0;
         const int q = __double2loint(t);
