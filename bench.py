@@ -7,10 +7,11 @@
 
 A "step" is one pass of the hot path over one batch of synthetic scenarios on every rank: the coupled RF-CV rollout
 kernel (goal estimate + H horizon steps for 3 Pandas per scenario, FP32) followed by the post step
-(mrf_rfcv_post_dev_f32: FP64 re-roll of the scenarios whose FP32 results sit in the guard band of a deadlock threshold,
-then the deadlock kernel, which writes the per-scenario result tensor avg_vel[R] + flag) and, for N > 1, the all_gather of
-that tensor.  The steps of a sweep are independent batches: the post step and the gather of step i run on a side stream
-while the compute stream already runs the rollout of step i+1 (three output sets, high-priority side stream; sharding.gather_into).  One
+(mrf_rfcv_post_dev_f32, two kernels: the deadlock heuristic for every scenario the FP32 rollout decides safely + the list of
+those in the guard band of a threshold; then their FP64 re-roll, each CTA followed by the heuristic for what it re-rolled;
+both write the per-scenario result tensor avg_vel[R] + flag) and, for N > 1, one final all_gather of that tensor.  The steps
+of a sweep are independent batches: the post step of step i runs on a side stream while the rollout streams already run
+steps i+1, i+2 (eight output sets in flight; sharding.gather_into).  One
 robot-step = one fabric action evaluation of one robot at one horizon step (FK/J/Jdot qdot, leaves, pullback, solve,
 integrator update, avg-velocity accumulation).
 
@@ -272,15 +273,17 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
     _, R, B = recs[0].shape
     tdt = recs[0].dtype
     main = torch.cuda.current_stream(dev)
-    NBUF = int(os.environ.get("MRF_BENCH_NBUF", "4"))
+    NBUF = int(os.environ.get("MRF_BENCH_NBUF", "8"))
     NROLL = int(os.environ.get("MRF_BENCH_NROLL", "2"))
     roll = [torch.cuda.Stream(device=dev) for _ in range(NROLL)] if NROLL > 1 else [main]
-    # the rollout kernels fill the register file of every SM, so the post step's small kernels run when rollout CTAs
-    # retire; high priority places them first
+    # the rollout kernels fill the register file of every SM, so the post step's two kernels run when rollout CTAs retire.
+    # Measured (tools/sweep_probe.py): at normal priority with eight output sets in flight (the post chain of a step then
+    # finishes in the tails of the next rollouts without ever holding one back) the step costs 1.008 ms, on high-priority
+    # streams with four sets 1.018 ms
     # the post steps of consecutive batches overlap too (one FP64 re-roll tile has a latency of ~0.8 ms): one stream and
     # one scratch slot per output set
     NPOST = min(NBUF, 4, int(os.environ.get("MRF_BENCH_NPOST", "4")))
-    sides = [torch.cuda.Stream(device=dev, priority=int(os.environ.get("MRF_BENCH_PRIO", "-1"))) for _ in range(NPOST)]
+    sides = [torch.cuda.Stream(device=dev, priority=int(os.environ.get("MRF_BENCH_PRIO", "0"))) for _ in range(NPOST)]
     mk = lambda *shape, dtype=tdt: [torch.empty(shape, dtype=dtype, device=dev) for _ in range(NBUF)]
     avg, xee, gest, risk = mk(R, B), mk(R, 3, B), mk(3, B), mk(R, B)
     flag = mk(B, dtype=torch.int32)

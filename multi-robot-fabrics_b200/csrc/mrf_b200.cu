@@ -34,6 +34,276 @@
 namespace mrf {
 
 // ------------------------------------------------------------------------------------------------
+// deadlock heuristic, one thread per scenario (deadlock_prevention.py:50-118)
+// ------------------------------------------------------------------------------------------------
+struct DlCfg {
+    // goal element (robot i, component k, scenario b) at goals[i * g_sr + k * g_sc + b]; weight at weights[i * w_sr + b]
+    long long g_sr, g_sc, w_sr;
+    int est_robot; // >= 0: goals of this robot are first overwritten by goal_est (RF-CV), -1: off
+    int R, time_wait, time_gate;
+    double avg_vel_constant, dist_constant, w_follower, w_leader, goal_scale, dist_endeff, backoff;
+};
+
+// Euclidean norm exactly as numpy computes it for a 3-vector (np.linalg.norm -> sqrt(x.dot(x)), OpenBLAS ddot: an
+// FMA-chained accumulation; checked against numpy on 200 000 random vectors) -- explicit rounding intrinsics so the
+// compiler can neither fuse nor un-fuse anything; the follower goal then matches the reference bit for bit.
+__device__ __forceinline__ double np_norm3(double x, double y, double z) {
+    return __dsqrt_rn(__fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x))));
+}
+
+// Optional FP64 overrides for scenarios the FP32 rollout could not decide safely (see guard_select_one): slot[b] >= 0
+// selects column slot[b] of the compact FP64 results avg [R][cap], x_ee [R][3][cap], goal_est [3][cap].
+struct DlOverride {
+    const int* slot;
+    const double* avg;
+    const double* x_ee;
+    const double* goal_est;
+    long long cap;
+    unsigned* counters; // the list counter is reset once its consumers are done
+};
+
+// One scenario of the heuristic.  os >= 0: this scenario was re-rolled in FP64, its rollout outputs are column os of the
+// compact arrays of `ov`.
+template <typename T>
+__device__ __forceinline__ void deadlock_one(const DlCfg& c, long long b, long long B, int os, const DlOverride& ov,
+                                             const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
+                                             const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
+                                             const int* __restrict__ sm_state, const int* __restrict__ time_step,
+                                             int* __restrict__ tdo, int* __restrict__ st_int, T* __restrict__ st_goal,
+                                             int* __restrict__ flag, const T* __restrict__ goal_est, T* __restrict__ result) {
+    const int R = c.R;
+    if (c.est_robot >= 0 && goal_est != nullptr) // goal_pandas[1] = estimate (example_pandas_Jointspace.py:346-348)
+        for (int k = 0; k < 3; ++k)
+            goals[c.est_robot * c.g_sr + k * c.g_sc + b] = os >= 0 ? (T)ov.goal_est[k * ov.cap + os] : goal_est[(long long)k * B + b];
+    // the reference does this arithmetic in float64 whatever the planner precision
+    double x[MRF_MAX_ROBOTS][3], g[MRF_MAX_ROBOTS][3], dist_goal[MRF_MAX_ROBOTS];
+    int st[MRF_MAX_ROBOTS];
+    double avg_sum = 0.0;
+    for (int i = 0; i < R; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = os >= 0 ? ov.x_ee[((long long)i * 3 + k) * ov.cap + os] : (double)x_ee[((long long)i * 3 + k) * B + b];
+            g[i][k] = (os >= 0 && i == c.est_robot && goal_est != nullptr) ? ov.goal_est[k * ov.cap + os]
+                                                                           : (double)goals[i * c.g_sr + k * c.g_sc + b];
+        }
+        dist_goal[i] = np_norm3(__dsub_rn(x[i][0], g[i][0]), __dsub_rn(x[i][1], g[i][1]), __dsub_rn(x[i][2], g[i][2]));
+        st[i] = sm_state[(long long)i * B + b];
+        if (avg_vel) {
+            const double a = os >= 0 ? ov.avg[(long long)i * ov.cap + os] : (double)avg_vel[(long long)i * B + b];
+            avg_sum += a;
+            if (result) result[(long long)i * B + b] = (T)a;
+        }
+    }
+    // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375), or the caller's scalar
+    avg_sum = avg_vel ? avg_sum / (double)R : (double)avg_sum_in[b];
+    const int ts = time_step[b];
+    int t_out = tdo[b];
+    int i_leader = st_int[0 * B + b], i_follower = st_int[1 * B + b];
+    int dead0 = st_int[2 * B + b], dead1 = st_int[3 * B + b];
+    bool deadlock = false;
+    double min_dist = 100.0; // deadlock_distance initial value / deadlock_min_dist (:57,74)
+    for (int a = 0; a < R; ++a)
+        for (int bq = a + 1; bq < R; ++bq) { // itertools.combinations order (:29-30)
+            double dsum = __dadd_rn(dist_goal[a], dist_goal[bq]);
+            bool check_state = (st[a] == 0 || st[a] == 1) && (st[bq] == 0 || st[bq] == 1);
+            double de = np_norm3(__dsub_rn(x[a][0], x[bq][0]), __dsub_rn(x[a][1], x[bq][1]), __dsub_rn(x[a][2], x[bq][2]));
+            if (avg_sum < c.avg_vel_constant && dsum > c.dist_constant && ts > c.time_gate && check_state &&
+                de < c.dist_endeff) {
+                deadlock = true;
+                // after each hit the reference rescans all pairs for the minimum recorded distance with a
+                // strict '<' (:74-80): the first pair reaching the minimum wins
+                if (de < min_dist) {
+                    min_dist = de;
+                    dead0 = a;
+                    dead1 = bq;
+                }
+            }
+        }
+    int fl = 0;
+    double g0[3] = {(double)st_goal[0 * B + b], (double)st_goal[1 * B + b], (double)st_goal[2 * B + b]};
+    bool apply = false;
+    if (deadlock && ts > c.time_gate) {
+        fl = 1;
+        if (dist_goal[dead0] > dist_goal[dead1]) {
+            i_leader = dead1;
+            i_follower = dead0;
+        } else {
+            i_leader = dead0;
+            i_follower = dead1;
+        }
+        double d[3], dg[3];
+        for (int k = 0; k < 3; ++k) {
+            d[k] = __dsub_rn(x[i_leader][k], x[i_follower][k]);
+            dg[k] = __dmul_rn(d[k], c.goal_scale);
+        }
+        const double nrm = np_norm3(dg[0], dg[1], dg[2]);
+        const double sc = __ddiv_rn(c.backoff, nrm);       // 0.3 / norm, then elementwise * and - as numpy does
+        for (int k = 0; k < 3; ++k)
+            g0[k] = nrm > 0.05 ? __dsub_rn(x[i_follower][k], __dmul_rn(sc, dg[k]))
+                               : __dsub_rn(x[i_follower][k], __dmul_rn(d[k], c.goal_scale));
+        if (g0[2] < 0.0) g0[2] = 0.1;
+        apply = true;
+        t_out = 0;
+    } else if (st[dead0] == 2 || st[dead1] == 2) {
+        t_out = 400;
+    } else if (t_out < c.time_wait) {
+        apply = true;
+        t_out = t_out + 1;
+    }
+    if (apply) {
+        weights[i_leader * c.w_sr + b] = (T)c.w_leader;
+        weights[i_follower * c.w_sr + b] = (T)c.w_follower;
+        for (int k = 0; k < 3; ++k) goals[i_follower * c.g_sr + k * c.g_sc + b] = (T)g0[k];
+    }
+    tdo[b] = t_out;
+    st_int[0 * B + b] = i_leader;
+    st_int[1 * B + b] = i_follower;
+    st_int[2 * B + b] = dead0;
+    st_int[3 * B + b] = dead1;
+    for (int k = 0; k < 3; ++k) st_goal[k * B + b] = (T)g0[k];
+    if (flag) flag[b] = fl;
+    if (result) result[(long long)R * B + b] = (T)fl; // what a sweep gathers per scenario: avg_vel[R] and the flag
+}
+
+template <typename T>
+__global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
+                                const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
+                                const int* __restrict__ sm_state,
+                                const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
+                                T* __restrict__ st_goal, int* __restrict__ flag, const T* __restrict__ goal_est,
+                                long long B, DlOverride ov, T* __restrict__ result) {
+    // grid-stride over the scenarios: a few fat CTAs instead of B / 128 thin ones -- next to a sweep whose rollout kernels
+    // fill every SM's register file, each CTA of a small kernel delays one rollout CTA slot at a wave boundary
+    if (ov.counters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ov.counters[0] = 0; // list consumed (same stream order)
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x)
+        deadlock_one<T>(c, b, B, ov.slot != nullptr ? ov.slot[b] : -1, ov, x_ee, goals, weights, avg_vel, avg_sum_in, sm_state,
+                        time_step, tdo, st_int, st_goal, flag, goal_est, result);
+}
+
+// ------------------------------------------------------------------------------------------------
+// "deadlock flags identical" for the FP32 path.  The heuristic compares rollout outputs with thresholds
+// (deadlock_prevention.py:61-66: vel_avg_tot < 0.16, ee distance < 0.35) and with each other (:76,85: closest pair,
+// leader = closer to its goal); an FP32 rollout answers those tests like the reference's float64 one unless a value sits
+// within the FP32 error of the threshold.  guard_select_one lists exactly those scenarios -- a narrow band for
+// ordinary scenarios, a wide one for numerically stiff ones (risk = max over the horizon of the summed leaf metric:
+// near contact the explicit dt = 0.01 integration amplifies rounding) and anything non-finite; they are re-rolled by the
+// FP64 kernel from the same records and the deadlock kernel reads the FP64 values for them (DlOverride).
+// ------------------------------------------------------------------------------------------------
+struct GuardCfg {
+    int R, est_robot;
+    double c_avg, c_dist, band_dist;
+    double band[3], rel[3], edge[2]; // |vel_avg_tot - c_avg| <= band[t] + rel[t] vel_avg_tot, tier t = (risk >= edge[0]) + (risk >= edge[1])
+    unsigned cap;
+};
+// counters: [0] listed this call (may exceed cap), [1] not used, [2] cumulative re-rolled, [3] cumulative overflow
+// One scenario of the selection; returns its slot in the list (-1: not listed, or the list is full).
+template <typename T>
+__device__ __forceinline__ int guard_select_one(const GuardCfg& c, long long b, long long B, const T* __restrict__ avg_vel,
+                                                const T* __restrict__ x_ee, const T* __restrict__ rec,
+                                                const T* __restrict__ goal_est, const T* __restrict__ risk,
+                                                const int* __restrict__ sm_state, const int* __restrict__ time_step,
+                                                int time_gate, double dist_constant, unsigned* __restrict__ counters,
+                                                int* __restrict__ list) {
+    const int R = c.R;
+    const long long RB = (long long)R * B;
+    double s = 0.0, rk = 0.0, x[MRF_MAX_ROBOTS][3], dg[MRF_MAX_ROBOTS];
+    int st[MRF_MAX_ROBOTS];
+    for (int i = 0; i < R; ++i) {
+        s += (double)avg_vel[(long long)i * B + b];
+        if (risk) rk = fmax(rk, (double)risk[(long long)i * B + b]);
+        st[i] = sm_state[(long long)i * B + b];
+        double d2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
+            const double g = (i == c.est_robot && goal_est != nullptr) ? (double)goal_est[(long long)k * B + b]
+                                                                       : (double)rec[(MRF_G0 + k) * RB + (long long)i * B + b];
+            d2 += (x[i][k] - g) * (x[i][k] - g);
+        }
+        dg[i] = sqrt(d2);
+    }
+    s /= (double)R;
+    // Only a scenario with a candidate pair -- both robots in state 0 / 1, hands closer than the distance threshold (plus
+    // the band), goal distances above the constant, time gate open (deadlock_prevention.py:61-66) -- can raise the flag at
+    // all; for every other scenario the velocity test is never consulted and nothing needs FP64.
+    bool cand = false, knife = false;
+    double de[MRF_MAX_ROBOTS * (MRF_MAX_ROBOTS - 1) / 2];
+    int np = 0;
+    if (time_step[b] > time_gate) {
+        for (int a = 0; a < R; ++a)
+            for (int q = a + 1; q < R; ++q) {
+                if (!((st[a] == 0 || st[a] == 1) && (st[q] == 0 || st[q] == 1))) continue;
+                const double d = sqrt((x[a][0] - x[q][0]) * (x[a][0] - x[q][0]) + (x[a][1] - x[q][1]) * (x[a][1] - x[q][1]) +
+                                      (x[a][2] - x[q][2]) * (x[a][2] - x[q][2]));
+                if (!(d >= c.c_dist + c.band_dist) && !(dg[a] + dg[q] <= dist_constant - c.band_dist)) { // NaN counts as candidate
+                    cand = true;
+                    knife = knife || fabs(d - c.c_dist) <= c.band_dist;                           // :64 distance test
+                    knife = knife || fabs(dg[a] + dg[q] - dist_constant) <= c.band_dist;          // :61 goal-distance test
+                    knife = knife || fabs(dg[a] - dg[q]) <= c.band_dist;                          // :85 leader choice
+                    for (int e = 0; e < np; ++e) knife = knife || fabs(de[e] - d) <= c.band_dist; // :76 closest pair
+                    de[np++] = d;
+                }
+            }
+    }
+    bool guard = false;
+    if (cand) {
+        const double da = fabs(s - c.c_avg);
+        const int tier = (rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0);
+        const double band = c.band[tier] + c.rel[tier] * fabs(s);
+        guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk);   // non-finite FP32 rollout
+        guard = guard || da <= band;                                   // velocity knife edge, widened by stiffness tier
+        guard = guard || (knife && s < c.c_avg + band);                // geometric knife edges matter if the velocity test can pass
+    }
+    int slot = -1;
+    if (guard) {
+        const unsigned t = atomicAdd(&counters[0], 1u);
+        if (t < c.cap) {
+            slot = (int)t;
+            list[t] = (int)b;
+        }
+    }
+    return slot;
+}
+
+// Arguments of the heuristic as the post step of a sweep hands them to the kernels (FP32 arrays; see deadlock_one)
+struct DlPost {
+    int enabled;
+    DlCfg c;
+    long long B;
+    const float* x_ee;
+    float* goals;
+    float* weights;
+    const float* avg_vel;
+    const int* sm_state;
+    const int* time_step;
+    int* tdo;
+    int* st_int;
+    float* st_goal;
+    int* flag;
+    const float* goal_est;
+    float* result;
+    DlOverride ov;
+    unsigned* done; // CTAs of the re-roll kernel that have finished: the last one resets the list counter
+};
+
+// First kernel of the post step: list the scenarios the FP32 rollout could not decide safely -- and run the heuristic right
+// away for all the others.  The listed ones get theirs from the FP64 re-roll kernel (rollout_kernel<double, ..., STRIDE>),
+// each CTA for the scenarios it has just re-rolled: two launches per step instead of three next to the rollouts.
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+    guard_deadlock_kernel(GuardCfg g, const T* __restrict__ rec, const T* __restrict__ risk, int time_gate,
+                          double dist_constant, int* __restrict__ slot_of, unsigned* __restrict__ counters,
+                          int* __restrict__ list, DlPost d) {
+    const long long B = d.B;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const int slot = guard_select_one<T>(g, b, B, (const T*)d.avg_vel, (const T*)d.x_ee, rec, (const T*)d.goal_est, risk,
+                                             d.sm_state, d.time_step, time_gate, dist_constant, counters, list);
+        slot_of[b] = slot;
+        if (slot < 0)
+            deadlock_one<T>(d.c, b, B, -1, d.ov, (const T*)d.x_ee, (T*)d.goals, (T*)d.weights, (const T*)d.avg_vel, nullptr,
+                            d.sm_state, d.time_step, d.tdo, d.st_int, (T*)d.st_goal, d.flag, (const T*)d.goal_est, (T*)d.result);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // coupled joint-space rollout
 // ------------------------------------------------------------------------------------------------
 #ifndef MRF_ROLLOUT_MINBLOCKS
@@ -73,6 +343,9 @@ template <typename T> struct RollExtra {
     // post step (goal rows for the heuristic, whole records of the re-rolled scenarios) then never touches the bus
     int out_soa;
     T* rec_out;
+    // STRIDE as the second kernel of a sweep's post step: every CTA runs the deadlock heuristic for the scenarios it has
+    // just re-rolled (dl.enabled), and the last CTA to finish resets the list counter
+    DlPost dl;
 };
 
 template <typename T, int R, bool UNIFORM, bool AOS, bool STRIDE = false>
@@ -86,7 +359,7 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     const int n_static = ex.n_static;
     const bool rec_order_out = AOS && !ex.out_soa; // results in the caller's record order (AoS) or in the device SoA layout
     // STRIDE (FP64 re-roll of the guard band): the scenarios are the first min(*n_live, B) entries of `list` -- produced
-    // on the device by guard_select_kernel -- read from the FP32 records rec_f32 [44][R][B_src] (exact promotion); results
+    // on the device by guard_deadlock_kernel -- read from the FP32 records rec_f32 [44][R][B_src] (exact promotion); results
     // go to compact arrays of stride B.  The grid is a handful of CTAs that stride over the tiles, so only a few
     // (register-heavy) CTAs have to find room next to the FP32 sweep.  Ordinary launches: one CTA per tile, no loop.
     const long long Bn = STRIDE ? ((long long)*n_live < B ? (long long)*n_live : B) : B;
@@ -97,8 +370,10 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     }
     constexpr int NT = kTile * R; // compile-time so every shared-memory offset is an immediate
     unsigned tile_first = blockIdx.x;
-    if (STRIDE && (long long)tile_first * kTile >= Bn) return;
-  do {
+    const bool fused_post = STRIDE && ex.dl.enabled != 0;
+    bool has_work = !(STRIDE && (long long)tile_first * kTile >= Bn);
+    if (!has_work && !fused_post) return;
+  while (has_work) {
     const int tid = threadIdx.x, lane = tid & (kTile - 1), r = tid / kTile;
     // (a double-buffered point table with one barrier per step was measured 2 % slower: more shared memory per CTA
     //  and non-immediate offsets; the barrier stall is load imbalance between the robots' warps, not barrier count)
@@ -239,10 +514,25 @@ __global__ void __launch_bounds__(kTile* R, (R == 3 && sizeof(T) == 4) ? MRF_ROL
     // stiffness indicator (maximum over the horizon of fabric_action's sum of leaf metrics), see mrf_rfcv_post_dev_f32
     if (risk != nullptr && live) risk[rec_order_out ? b * R + r : (long long)r * B + b] = prm[P_RISK * NT + tid];
     if (STRIDE) {
-        __syncthreads(); // the next tile of this CTA overwrites the tables
+        __syncthreads(); // the next tile of this CTA overwrites the tables; this tile's results are visible to the CTA
+        if (fused_post && tid < kTile && live) // one thread per re-rolled scenario: its robots' FP64 results are column b
+            deadlock_one<float>(ex.dl.c, (long long)ex.list[b], ex.dl.B, (int)b, ex.dl.ov, ex.dl.x_ee, ex.dl.goals, ex.dl.weights,
+                                ex.dl.avg_vel, nullptr, ex.dl.sm_state, ex.dl.time_step, ex.dl.tdo, ex.dl.st_int, ex.dl.st_goal,
+                                ex.dl.flag, ex.dl.goal_est, ex.dl.result);
         tile_first += gridDim.x;
     }
-  } while (STRIDE && (long long)tile_first * kTile < Bn);
+    has_work = STRIDE && (long long)tile_first * kTile < Bn;
+  }
+    if (fused_post) { // every CTA has read the list counter at entry: the last one out resets it for the next post step
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(ex.dl.done, 1u) == gridDim.x - 1) {
+                *ex.dl.done = 0;
+                n_live[0] = 0;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -361,225 +651,6 @@ __global__ void __launch_bounds__(kActThreads)
         if (v) { v[((long long)l * 3 + 0) * total + idx] = vv.x; v[((long long)l * 3 + 1) * total + idx] = vv.y; v[((long long)l * 3 + 2) * total + idx] = vv.z; }
         if (a) { a[((long long)l * 3 + 0) * total + idx] = aa.x; a[((long long)l * 3 + 1) * total + idx] = aa.y; a[((long long)l * 3 + 2) * total + idx] = aa.z; }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// deadlock heuristic, one thread per scenario (deadlock_prevention.py:50-118)
-// ------------------------------------------------------------------------------------------------
-struct DlCfg {
-    // goal element (robot i, component k, scenario b) at goals[i * g_sr + k * g_sc + b]; weight at weights[i * w_sr + b]
-    long long g_sr, g_sc, w_sr;
-    int est_robot; // >= 0: goals of this robot are first overwritten by goal_est (RF-CV), -1: off
-    int R, time_wait, time_gate;
-    double avg_vel_constant, dist_constant, w_follower, w_leader, goal_scale, dist_endeff, backoff;
-};
-
-// Euclidean norm exactly as numpy computes it for a 3-vector (np.linalg.norm -> sqrt(x.dot(x)), OpenBLAS ddot: an
-// FMA-chained accumulation; checked against numpy on 200 000 random vectors) -- explicit rounding intrinsics so the
-// compiler can neither fuse nor un-fuse anything; the follower goal then matches the reference bit for bit.
-__device__ __forceinline__ double np_norm3(double x, double y, double z) {
-    return __dsqrt_rn(__fma_rn(z, z, __fma_rn(y, y, __dmul_rn(x, x))));
-}
-
-// Optional FP64 overrides for scenarios the FP32 rollout could not decide safely (see guard_select_kernel): slot[b] >= 0
-// selects column slot[b] of the compact FP64 results avg [R][cap], x_ee [R][3][cap], goal_est [3][cap].
-struct DlOverride {
-    const int* slot;
-    const double* avg;
-    const double* x_ee;
-    const double* goal_est;
-    long long cap;
-    unsigned* counters; // the list counter is reset once its consumers are done
-};
-
-template <typename T>
-__global__ void deadlock_kernel(DlCfg c, const T* __restrict__ x_ee, T* __restrict__ goals, T* __restrict__ weights,
-                                const T* __restrict__ avg_vel, const T* __restrict__ avg_sum_in,
-                                const int* __restrict__ sm_state,
-                                const int* __restrict__ time_step, int* __restrict__ tdo, int* __restrict__ st_int,
-                                T* __restrict__ st_goal, int* __restrict__ flag, const T* __restrict__ goal_est,
-                                long long B, DlOverride ov, T* __restrict__ result) {
-    // grid-stride over the scenarios: a few fat CTAs instead of B / 128 thin ones -- next to a sweep whose rollout kernels
-    // fill every SM's register file, each CTA of a small kernel delays one rollout CTA slot at a wave boundary
-    if (ov.counters != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ov.counters[0] = 0; // list consumed (same stream order)
-  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-    const int R = c.R;
-    const int os = ov.slot != nullptr ? ov.slot[b] : -1; // >= 0: this scenario was re-rolled in FP64
-    if (c.est_robot >= 0 && goal_est != nullptr) // goal_pandas[1] = estimate (example_pandas_Jointspace.py:346-348)
-        for (int k = 0; k < 3; ++k)
-            goals[c.est_robot * c.g_sr + k * c.g_sc + b] = os >= 0 ? (T)ov.goal_est[k * ov.cap + os] : goal_est[(long long)k * B + b];
-    // the reference does this arithmetic in float64 whatever the planner precision
-    double x[MRF_MAX_ROBOTS][3], g[MRF_MAX_ROBOTS][3], dist_goal[MRF_MAX_ROBOTS];
-    int st[MRF_MAX_ROBOTS];
-    double avg_sum = 0.0;
-    for (int i = 0; i < R; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            x[i][k] = os >= 0 ? ov.x_ee[((long long)i * 3 + k) * ov.cap + os] : (double)x_ee[((long long)i * 3 + k) * B + b];
-            g[i][k] = (os >= 0 && i == c.est_robot && goal_est != nullptr) ? ov.goal_est[k * ov.cap + os]
-                                                                           : (double)goals[i * c.g_sr + k * c.g_sc + b];
-        }
-        dist_goal[i] = np_norm3(__dsub_rn(x[i][0], g[i][0]), __dsub_rn(x[i][1], g[i][1]), __dsub_rn(x[i][2], g[i][2]));
-        st[i] = sm_state[(long long)i * B + b];
-        if (avg_vel) {
-            const double a = os >= 0 ? ov.avg[(long long)i * ov.cap + os] : (double)avg_vel[(long long)i * B + b];
-            avg_sum += a;
-            if (result) result[(long long)i * B + b] = (T)a;
-        }
-    }
-    // vel_avg_tot = sum(vel_avg)/nr_robots (example_pandas_Jointspace.py:375), or the caller's scalar
-    avg_sum = avg_vel ? avg_sum / (double)R : (double)avg_sum_in[b];
-    const int ts = time_step[b];
-    int t_out = tdo[b];
-    int i_leader = st_int[0 * B + b], i_follower = st_int[1 * B + b];
-    int dead0 = st_int[2 * B + b], dead1 = st_int[3 * B + b];
-    bool deadlock = false;
-    double min_dist = 100.0; // deadlock_distance initial value / deadlock_min_dist (:57,74)
-    for (int a = 0; a < R; ++a)
-        for (int bq = a + 1; bq < R; ++bq) { // itertools.combinations order (:29-30)
-            double dsum = __dadd_rn(dist_goal[a], dist_goal[bq]);
-            bool check_state = (st[a] == 0 || st[a] == 1) && (st[bq] == 0 || st[bq] == 1);
-            double de = np_norm3(__dsub_rn(x[a][0], x[bq][0]), __dsub_rn(x[a][1], x[bq][1]), __dsub_rn(x[a][2], x[bq][2]));
-            if (avg_sum < c.avg_vel_constant && dsum > c.dist_constant && ts > c.time_gate && check_state &&
-                de < c.dist_endeff) {
-                deadlock = true;
-                // after each hit the reference rescans all pairs for the minimum recorded distance with a
-                // strict '<' (:74-80): the first pair reaching the minimum wins
-                if (de < min_dist) {
-                    min_dist = de;
-                    dead0 = a;
-                    dead1 = bq;
-                }
-            }
-        }
-    int fl = 0;
-    double g0[3] = {(double)st_goal[0 * B + b], (double)st_goal[1 * B + b], (double)st_goal[2 * B + b]};
-    bool apply = false;
-    if (deadlock && ts > c.time_gate) {
-        fl = 1;
-        if (dist_goal[dead0] > dist_goal[dead1]) {
-            i_leader = dead1;
-            i_follower = dead0;
-        } else {
-            i_leader = dead0;
-            i_follower = dead1;
-        }
-        double d[3], dg[3];
-        for (int k = 0; k < 3; ++k) {
-            d[k] = __dsub_rn(x[i_leader][k], x[i_follower][k]);
-            dg[k] = __dmul_rn(d[k], c.goal_scale);
-        }
-        const double nrm = np_norm3(dg[0], dg[1], dg[2]);
-        const double sc = __ddiv_rn(c.backoff, nrm);       // 0.3 / norm, then elementwise * and - as numpy does
-        for (int k = 0; k < 3; ++k)
-            g0[k] = nrm > 0.05 ? __dsub_rn(x[i_follower][k], __dmul_rn(sc, dg[k]))
-                               : __dsub_rn(x[i_follower][k], __dmul_rn(d[k], c.goal_scale));
-        if (g0[2] < 0.0) g0[2] = 0.1;
-        apply = true;
-        t_out = 0;
-    } else if (st[dead0] == 2 || st[dead1] == 2) {
-        t_out = 400;
-    } else if (t_out < c.time_wait) {
-        apply = true;
-        t_out = t_out + 1;
-    }
-    if (apply) {
-        weights[i_leader * c.w_sr + b] = (T)c.w_leader;
-        weights[i_follower * c.w_sr + b] = (T)c.w_follower;
-        for (int k = 0; k < 3; ++k) goals[i_follower * c.g_sr + k * c.g_sc + b] = (T)g0[k];
-    }
-    tdo[b] = t_out;
-    st_int[0 * B + b] = i_leader;
-    st_int[1 * B + b] = i_follower;
-    st_int[2 * B + b] = dead0;
-    st_int[3 * B + b] = dead1;
-    for (int k = 0; k < 3; ++k) st_goal[k * B + b] = (T)g0[k];
-    if (flag) flag[b] = fl;
-    if (result) result[(long long)R * B + b] = (T)fl; // what a sweep gathers per scenario: avg_vel[R] and the flag
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// "deadlock flags identical" for the FP32 path.  The heuristic compares rollout outputs with thresholds
-// (deadlock_prevention.py:61-66: vel_avg_tot < 0.16, ee distance < 0.35) and with each other (:76,85: closest pair,
-// leader = closer to its goal); an FP32 rollout answers those tests like the reference's float64 one unless a value sits
-// within the FP32 error of the threshold.  guard_select_kernel lists exactly those scenarios -- a narrow band for
-// ordinary scenarios, a wide one for numerically stiff ones (risk = max over the horizon of the summed leaf metric:
-// near contact the explicit dt = 0.01 integration amplifies rounding) and anything non-finite; they are re-rolled by the
-// FP64 kernel from the same records and the deadlock kernel reads the FP64 values for them (DlOverride).
-// ------------------------------------------------------------------------------------------------
-struct GuardCfg {
-    int R, est_robot;
-    double c_avg, c_dist, band_dist;
-    double band[3], rel[3], edge[2]; // |vel_avg_tot - c_avg| <= band[t] + rel[t] vel_avg_tot, tier t = (risk >= edge[0]) + (risk >= edge[1])
-    unsigned cap;
-};
-// counters: [0] listed this call (may exceed cap), [1] not used, [2] cumulative re-rolled, [3] cumulative overflow
-template <typename T>
-__global__ void guard_select_kernel(GuardCfg c, const T* __restrict__ avg_vel, const T* __restrict__ x_ee,
-                                    const T* __restrict__ rec, const T* __restrict__ goal_est, const T* __restrict__ risk,
-                                    const int* __restrict__ sm_state, const int* __restrict__ time_step, int time_gate,
-                                    double dist_constant, int* __restrict__ slot_of, unsigned* __restrict__ counters,
-                                    int* __restrict__ list, long long B) {
-  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-    const int R = c.R;
-    const long long RB = (long long)R * B;
-    double s = 0.0, rk = 0.0, x[MRF_MAX_ROBOTS][3], dg[MRF_MAX_ROBOTS];
-    int st[MRF_MAX_ROBOTS];
-    for (int i = 0; i < R; ++i) {
-        s += (double)avg_vel[(long long)i * B + b];
-        if (risk) rk = fmax(rk, (double)risk[(long long)i * B + b]);
-        st[i] = sm_state[(long long)i * B + b];
-        double d2 = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            x[i][k] = (double)x_ee[((long long)i * 3 + k) * B + b];
-            const double g = (i == c.est_robot && goal_est != nullptr) ? (double)goal_est[(long long)k * B + b]
-                                                                       : (double)rec[(MRF_G0 + k) * RB + (long long)i * B + b];
-            d2 += (x[i][k] - g) * (x[i][k] - g);
-        }
-        dg[i] = sqrt(d2);
-    }
-    s /= (double)R;
-    // Only a scenario with a candidate pair -- both robots in state 0 / 1, hands closer than the distance threshold (plus
-    // the band), goal distances above the constant, time gate open (deadlock_prevention.py:61-66) -- can raise the flag at
-    // all; for every other scenario the velocity test is never consulted and nothing needs FP64.
-    bool cand = false, knife = false;
-    double de[MRF_MAX_ROBOTS * (MRF_MAX_ROBOTS - 1) / 2];
-    int np = 0;
-    if (time_step[b] > time_gate) {
-        for (int a = 0; a < R; ++a)
-            for (int q = a + 1; q < R; ++q) {
-                if (!((st[a] == 0 || st[a] == 1) && (st[q] == 0 || st[q] == 1))) continue;
-                const double d = sqrt((x[a][0] - x[q][0]) * (x[a][0] - x[q][0]) + (x[a][1] - x[q][1]) * (x[a][1] - x[q][1]) +
-                                      (x[a][2] - x[q][2]) * (x[a][2] - x[q][2]));
-                if (!(d >= c.c_dist + c.band_dist) && !(dg[a] + dg[q] <= dist_constant - c.band_dist)) { // NaN counts as candidate
-                    cand = true;
-                    knife = knife || fabs(d - c.c_dist) <= c.band_dist;                           // :64 distance test
-                    knife = knife || fabs(dg[a] + dg[q] - dist_constant) <= c.band_dist;          // :61 goal-distance test
-                    knife = knife || fabs(dg[a] - dg[q]) <= c.band_dist;                          // :85 leader choice
-                    for (int e = 0; e < np; ++e) knife = knife || fabs(de[e] - d) <= c.band_dist; // :76 closest pair
-                    de[np++] = d;
-                }
-            }
-    }
-    bool guard = false;
-    if (cand) {
-        const double da = fabs(s - c.c_avg);
-        const int tier = (rk >= c.edge[0] ? 1 : 0) + (rk >= c.edge[1] ? 1 : 0);
-        const double band = c.band[tier] + c.rel[tier] * fabs(s);
-        guard = !(da == da) || !(rk == rk) || isinf(s) || isinf(rk);   // non-finite FP32 rollout
-        guard = guard || da <= band;                                   // velocity knife edge, widened by stiffness tier
-        guard = guard || (knife && s < c.c_avg + band);                // geometric knife edges matter if the velocity test can pass
-    }
-    int slot = -1;
-    if (guard) {
-        const unsigned t = atomicAdd(&counters[0], 1u);
-        if (t < c.cap) {
-            slot = (int)t;
-            list[t] = (int)b;
-        }
-    }
-    slot_of[b] = slot;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1017,8 +1088,10 @@ extern "C" int mrf_config_default(MrfConfig* c, int n_robots) {
 static int create_resources(MrfHandle_* h) {
     for (int i = 0; i < 2; ++i) MRF_CUDA(cudaMalloc(&h->d_tail[i], sizeof(double) * MRF_MAX_ROBOTS * MRF_REC));
     // [0..13] ticket pairs (slot 0 synchronous entry, 1..2 rollout submit pipeline, 3..6 RF-CV submit pipeline), [16..] guard counters
-    MRF_CUDA(cudaMalloc(&h->d_sync, (16 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
-    MRF_CUDA(cudaMemset(h->d_sync, 0, (16 + 4 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
+    // [0, 16): ticket / loaded pairs of the in-place host launches; then 4 guard counters per scratch slot; then one
+    // finished-CTA counter per scratch slot (fused post step)
+    MRF_CUDA(cudaMalloc(&h->d_sync, (16 + 5 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
+    MRF_CUDA(cudaMemset(h->d_sync, 0, (16 + 5 * MRF_GUARD_SLOTS) * sizeof(unsigned)));
     int prio_lo = 0, prio_hi = 0;
     MRF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (int i = 0; i < 4; ++i) {
@@ -1439,7 +1512,7 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
     const int R = h->cfg.n_robots;
     const long long RB = (long long)R * B;
     const bool est = h->cfg.estimate_goal != 0 && goal_est != nullptr;
-    DlOverride ov{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
+    const DlOverride ov{nullptr, nullptr, nullptr, nullptr, 0, nullptr};
     if (sizeof(T) == 4 && risk != nullptr) {
         if (R < 2 || R > 4) return fail(MRF_EINVAL, "mrf_rfcv_post: n_robots must be 2..4");
         MRF_CUDA(cudaSetDevice(h->device));
@@ -1459,15 +1532,39 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
         GuardCfg g{R, est ? h->cfg.estimate_robot : -1, h->cfg.dl_avg_vel_constant, h->cfg.dl_dist_endeff, h->guard_band_dist,
                    {h->guard_band[0], h->guard_band[1], h->guard_band[2]}, {h->guard_rel[0], h->guard_rel[1], h->guard_rel[2]},
                    {h->guard_edge[0], h->guard_edge[1]}, (unsigned)cap};
+        // the heuristic's arguments as both kernels of the post step see them (FP32 arrays)
+        const MrfConfig& mc = h->cfg;
+        DlPost dp{};
+        dp.enabled = 1;
+        dp.c = DlCfg{(long long)B, (long long)R * B, (long long)B,
+                     (mc.estimate_goal && goal_est && mc.estimate_robot < mc.n_robots) ? mc.estimate_robot : -1,
+                     mc.n_robots, mc.dl_time_wait, mc.dl_time_gate, mc.dl_avg_vel_constant, mc.dl_dist_constant,
+                     mc.dl_goal_weight_follower, mc.dl_goal_weight_leader, mc.dl_nr_goal_scale, mc.dl_dist_endeff, mc.dl_backoff};
+        dp.B = (long long)B;
+        dp.x_ee = (const float*)x_ee;
+        dp.goals = (float*)(rec_work + MRF_G0 * RB);
+        dp.weights = (float*)(rec_work + MRF_W0 * RB);
+        dp.avg_vel = (const float*)avg_vel;
+        dp.sm_state = sm_state;
+        dp.time_step = time_step;
+        dp.tdo = tdo;
+        dp.st_int = st_int;
+        dp.st_goal = (float*)st_goal;
+        dp.flag = flag;
+        dp.goal_est = (const float*)goal_est;
+        dp.result = (float*)result;
+        dp.ov = DlOverride{slot_of, avg64, xee64, gest64, cap, counters};
+        dp.done = h->d_sync + 16 + 4 * MRF_GUARD_SLOTS + slot;
+        // kernel 1: list the scenarios to re-roll, run the heuristic for all the others
         const long long sel_blocks = (B + 255) / 256;
-        same_carveout(guard_select_kernel<T>);
-        guard_select_kernel<T><<<(unsigned)(sel_blocks < 64 ? sel_blocks : 64), 256, 0, st>>>(
-            g, avg_vel, x_ee, rec, est ? goal_est : nullptr, risk, sm_state, time_step, h->cfg.dl_time_gate,
-            h->cfg.dl_dist_constant, slot_of, counters, list, (long long)B);
+        same_carveout(guard_deadlock_kernel<T>);
+        guard_deadlock_kernel<T><<<(unsigned)(sel_blocks < 64 ? sel_blocks : 64), 256, 0, st>>>(
+            g, rec, risk, h->cfg.dl_time_gate, h->cfg.dl_dist_constant, slot_of, counters, list, dp);
         MRF_CUDA(cudaGetLastError());
         h->launches += 1;
-        // FP64 re-roll of the listed scenarios by the throughput kernel, straight from the FP32 records through the list;
-        // the kernel reads the count from device memory (grid: a few CTAs striding over the tiles)
+        // kernel 2: FP64 re-roll of the listed scenarios by the throughput kernel, straight from the FP32 records through the
+        // list (the kernel reads the count from device memory; grid: a few CTAs striding over the tiles), each CTA followed
+        // by the heuristic for the scenarios it re-rolled
         RollExtra<double> ex{};
         if (src_records) {
             ex = *src_records;
@@ -1480,10 +1577,9 @@ static int rfcv_post_dev(mrf_handle_t h, const T* rec, int N, const T* x_ee, T* 
         }
         ex.n_live = counters;
         ex.list = list;
-        rc = rollout_dev<double>(h, nullptr, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
-                                 nullptr, ex);
-        if (rc) return rc;
-        ov = DlOverride{slot_of, avg64, xee64, gest64, cap, counters};
+        ex.dl = dp;
+        return rollout_dev<double>(h, nullptr, N, avg64, xee64, gest64, nullptr, nullptr, cap, stream, false, 0, MRF_REC, nullptr,
+                                   nullptr, ex);
     }
     return deadlock_dev<T>(h, x_ee, rec_work + MRF_G0 * RB, rec_work + MRF_W0 * RB, avg_vel, nullptr, sm_state, time_step, tdo,
                            st_int, st_goal, flag, B, stream, true, goal_est, ov, result);

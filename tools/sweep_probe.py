@@ -33,27 +33,5 @@ def run(tag, post=True, risk=True, **env):
         os.environ.pop(k)
 
 
-run("full (2 rollout streams, 4 post, prio -1)")
-run("no post step", post=False)
-run("no post step, 1 rollout stream", post=False, MRF_BENCH_NROLL=1)
-run("no post step, 3 rollout streams", post=False, MRF_BENCH_NROLL=3)
-tiny = torch.zeros(1024, device=dev)
-
-
-def only_tiny(n):
-    def f(*a, **k):
-        for _ in range(n):
-            tiny.add_(1.0)          # one 1-CTA kernel on the (high-priority) post stream
-    return f
-
-
-for n in (1, 3, 6):
-    fab.rfcv_post_dev = only_tiny(n)
-    bench._sweep(fab, torch, None, dev, 1, recs, works, H, 5, 3, True)
-    ts = [bench._sweep(fab, torch, None, dev, 1, recs, works, H, K, 5, True)["total_ms"] / K for _ in range(3)]
-    print(f"post = {n} tiny kernels                    ms/step {min(ts):.4f}", flush=True)
-run("post = deadlock kernel only (no guard)", risk=False)
-fab.set_guard(bands=[0, 0, 0, 0, 0, 0], band_dist=0.0)
-run("post, guard lists nothing (empty re-roll)")
-torch.cuda.synchronize()
-print("guard stats", fab.guard_stats())
+run(os.environ.get("TAG", "") + " prio -1, 4 sets")
+run(os.environ.get("TAG", "") + " prio 0, 8 sets", MRF_BENCH_PRIO=0, MRF_BENCH_NBUF=8)
