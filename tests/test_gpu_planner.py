@@ -445,6 +445,46 @@ def test_fused_rfcv_step_deadlock_flags_identical(built, R, N, B, seed):
     fab.close()
 
 
+def test_rfcv_post_step_repeats_and_overflows_cleanly(built):
+    """The post step's list counter is reset by the last CTA of the FP64 re-roll kernel: calling the step again gives the
+    same list and the same flags; a list that overflows its capacity re-rolls `cap` scenarios, decides the others from the
+    FP32 values, and leaves the counters clean for the next call."""
+    import torch
+    from multi_robot_fabrics_b200.api import to_soa
+    R, N, B = 3, 20, 8192
+    rec = m.scenarios.generate(B, R, seed=64).astype(np.float32)
+    rec[:, :, 7:14] *= 0.25
+    fab = Fabrics(R, device=0, estimate_goal=1, dl_dist_endeff=1.0)
+    dev = "cuda:0"
+    d_rec = torch.from_numpy(to_soa(rec)).to(dev)
+    t = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    a, x, ge, risk = t(R, B), t(R, 3, B), t(3, B), t(R, B)
+    fab.rollout_dev(d_rec, N, avg_vel=a, x_ee=x, goal_est=ge, risk=risk)
+    sm = torch.zeros((R, B), dtype=torch.int32, device=dev)
+    ts = torch.full((B,), 100, dtype=torch.int32, device=dev)
+
+    def post():
+        work, result = d_rec.clone(), t(R + 1, B)
+        tdo = torch.full((B,), 1000, dtype=torch.int32, device=dev)
+        st_int = torch.tensor([0, 1, 0, 1], dtype=torch.int32, device=dev).repeat_interleave(B).contiguous()
+        flag = fab.rfcv_post_dev(d_rec, N, x, work, ge, a, sm, ts, tdo, st_int, t(3, B).zero_(), risk=risk, result=result)
+        torch.cuda.synchronize()
+        return flag.cpu().numpy(), result.cpu().numpy(), fab.guard_stats()
+
+    f1, r1, (rr1, ov1, listed1) = post()
+    f2, r2, (rr2, ov2, listed2) = post()
+    assert listed1 > 40 and listed2 == listed1 and ov1 == ov2 == 0 and rr2 == 2 * rr1
+    assert np.array_equal(f1, f2) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+    fab.set_guard(cap=32)
+    f3, r3, (rr3, ov3, listed3) = post()
+    assert listed3 == listed1 and ov3 == listed1 - 32 and rr3 == rr2 + 32
+    assert (f3 != f1).sum() <= listed1 - 32          # only scenarios that lost their re-roll may differ
+    fab.set_guard(cap=0)                             # back to the default capacity
+    f4, r4, (rr4, ov4, listed4) = post()
+    assert listed4 == listed1 and ov4 == ov3 and np.array_equal(f4, f1)
+    fab.close()
+
+
 def test_rfcv_host_submit_end_to_end_matches_device_path(built):
     """mrf_rfcv_host_submit_f32 -- the whole RF-CV step from page-locked host records (in-place rollout kernel, FP64 guard
     re-roll reading the listed scenarios from the same host records, deadlock heuristic, result back to host) -- returns
