@@ -1251,9 +1251,8 @@ static int rollout_dev(mrf_handle_t h, const T* rec, int N, T* avg_vel, T* x_ee,
     const T* const stat = ex.stat;
     if (!h || (!rec && !n_live)) return fail(MRF_EINVAL, "mrf_rollout: null argument");
     if (B <= 0 || N <= 0) return fail(MRF_EINVAL, "mrf_rollout: B and N must be positive");
-    if (h->cfg.mode != 1)
-        return fail(MRF_EUNSUPPORTED, "mrf_rollout: the joint-space rollout is defined for mode 'vel' only "
-                                      "(forward_planner_Jointspace.py:197-201,233)");
+    // mode 'acc' (MrfConfig.mode = 0) is the reference's own recurrence for that mode: it integrates a zero acceleration and
+    // stores the planner output in q_dot (forward_planner_Jointspace.py:195,202,233) -- the same loop with action = qdd
     MRF_CUDA(cudaSetDevice(h->device));
     const int R = h->cfg.n_robots, NT = kTile * R;
     if (aos && (qN || qdN)) return fail(MRF_EINVAL, "mrf_rollout: record-order input has no trajectory output");

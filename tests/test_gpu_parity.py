@@ -399,12 +399,10 @@ def test_error_paths_fail_loudly(fabs):
     import ctypes as C
     import torch
     from multi_robot_fabrics_b200 import _lib
-    fab = Fabrics(2, device=0, mode=0)                       # 'acc' planner: joint-space rollouts are undefined
     rec = m.scenarios.generate(4, 2, seed=1)
-    with pytest.raises(_lib.MrfError, match="vel"):
-        fab.rollout_host(rec, 5)
-    fab.close()
     fab = get_fab(fabs, 2)
+    with pytest.raises(_lib.MrfError, match="positive"):
+        fab.rollout_host(rec, 0)                             # horizon must be positive
     L = _lib.lib()
     assert L.mrf_rollout_host_f64(fab.handle.ptr, None, 5, None, None, None, None, None, 4) == -1
     assert b"null" in L.mrf_last_error()

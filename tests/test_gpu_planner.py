@@ -100,15 +100,17 @@ def test_forward_fabrics_planner_acc_mode(built):
     """fabrics_mode 'acc' in the coupled joint-space rollouts: the reference's loop resets the acceleration it integrates to
     zero each step and stores the planner output in q_dot (forward_planner_Jointspace.py:195,202,233) -- the oracle with
     mode = 0 runs that very recurrence."""
-    R, N = 2, 12
-    rec = m.scenarios.generate(4, R, seed=58)
+    R, N, nb = 2, 3, 16
+    rec = m.scenarios.generate(nb, R, seed=58)
+    rec[:, :, 7:14] *= 0.1            # the recurrence of this mode diverges within a few steps: short horizon, slow start
     planners = [P.set_planner_panda(7, 0, 8, LINKS, {}, MOUNT, i)[0] for i in range(R)]
     goals = [P.PandaGoal() for _ in range(R)]
     prm = make_params(R, N)
     prm.fabrics_mode = "acc"
     fp = P.ForwardFabricsPlanner(prm, planners, 100, None, goals)
     ocfg = o2.default_config(R, mode=0)
-    for b in range(4):
+    compared = 0
+    for b in range(nb):
         ia = {"q_robots": [rec[b, i, 0:7] for i in range(R)], "q_dot_robots": [rec[b, i, 7:14] for i in range(R)],
               "x_obsts": [[] * R], "x_goals0": [rec[b, i, 14:17] for i in range(R)],
               "x_goals1": [goals[i]._config.subgoal1.desired_position for i in range(R)],
@@ -127,6 +129,8 @@ def test_forward_fabrics_planner_acc_mode(built):
             assert np.abs(qd_n[f"robot_{i}"][0] - qdN[i].T).max() < 1e-9 * scale
         vel_avg = fp.get_velocity_rollouts(ia)
         assert np.abs(np.array([v[0] for v in vel_avg]) - avg).max() < 1e-9 * max(1.0, np.abs(avg).max())
+        compared += 1
+    assert compared >= 3
 
 
 def test_fabrics_rollouts_cartesian_dropin(built):
