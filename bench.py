@@ -9,7 +9,8 @@ A "step" is one pass of the hot path over one batch of synthetic scenarios on ev
 kernel (goal estimate + H horizon steps for 3 Pandas per scenario, FP32) followed by the post step
 (mrf_rfcv_post_dev_f32, two kernels: the deadlock heuristic for every scenario the FP32 rollout decides safely + the list of
 those in the guard band of a threshold; then their FP64 re-roll, each CTA followed by the heuristic for what it re-rolled;
-both write the per-scenario result tensor avg_vel[R] + flag) and, for N > 1, one final all_gather of that tensor.  The steps
+both write the per-scenario result tensor avg_vel[R] + flag) and, for N > 1, the all_gather of that tensor -- no per-step
+collective: four chunks of consecutive steps, each exchanged on a side stream under the rollouts that follow.  The steps
 of a sweep are independent batches: the post step of step i runs on a side stream while the rollout streams already run
 steps i+1, i+2 (eight output sets in flight; sharding.gather_into).  One
 robot-step = one fabric action evaluation of one robot at one horizon step (FK/J/Jdot qdot, leaves, pullback, solve,
@@ -291,7 +292,16 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
     # all_gather after the last step, inside the timed region ("only a final NCCL gather", north star)
     results = torch.empty((steps, R + 1, B), dtype=tdt, device=dev)
     scratch = torch.empty((R + 1, B), dtype=tdt, device=dev)
-    gathered = torch.empty((world, steps, R + 1, B), dtype=tdt, device=dev) if world > 1 else None
+    # N > 1: the result tensor is exchanged in a few chunks of consecutive steps, each all_gather issued on its own stream as
+    # soon as the post steps of its chunk are enqueued, so that only the last chunk's transfer is not hidden behind the
+    # rollouts that follow (one gather of all K steps after the sweep left 0.35 ms of NVLink time exposed at N = 8)
+    n_chunks = max(1, min(int(os.environ.get("MRF_BENCH_GATHER_CHUNKS", "4")), steps)) if world > 1 else 0
+    csz = -(-steps // n_chunks) if n_chunks else 0
+    if csz > NBUF:              # a chunk's post_done events must all still belong to its own steps when it is issued
+        csz = NBUF
+    bounds = [(c0, min(c0 + csz, steps)) for c0 in range(0, steps, csz)] if n_chunks else []
+    gathered = [torch.empty((world, c1 - c0, R + 1, B), dtype=tdt, device=dev) for c0, c1 in bounds] if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
     # heuristic state per output set (concurrent post steps must not share the in/out state arrays)
     sm_state = [torch.zeros((R, B), dtype=torch.int32, device=dev) for _ in range(NBUF)]
     tstep = torch.full((B,), 100, dtype=torch.int32, device=dev)
@@ -345,12 +355,22 @@ def _sweep(fab, torch, dist, dev, world, recs, works, H, steps, warmup, with_ris
         if s_ is not main:
             s_.wait_event(t0)
     h0 = time.perf_counter()
+    if comm is not None:
+        comm.wait_event(t0)
+    ci = 0
     for i in range(steps):
         step(warmup + i, True)
+        if world > 1 and i + 1 == bounds[ci][1]:         # the chunk's last step is enqueued: exchange its results
+            c0, c1 = bounds[ci]
+            with torch.cuda.stream(comm):
+                for j in range(c0, c1):
+                    comm.wait_event(post_done[(warmup + j) % NBUF])
+                sharding.gather_into(gathered[ci], results[c0:c1])   # the sweep's only exchange (per chunk of steps)
+            ci += 1
     host_ms = (time.perf_counter() - h0) * 1e3
     join()
-    if world > 1:
-        sharding.gather_into(gathered, results)          # the sweep's only exchange
+    if comm is not None:
+        main.wait_stream(comm)
     t1.record(main)
     torch.cuda.synchronize(dev)
     if world > 1:
