@@ -33,5 +33,19 @@ def run(tag, post=True, risk=True, **env):
         os.environ.pop(k)
 
 
-run(os.environ.get("TAG", "") + " prio -1, 4 sets")
-run(os.environ.get("TAG", "") + " prio 0, 8 sets", MRF_BENCH_PRIO=0, MRF_BENCH_NBUF=8)
+tag = os.environ.get("TAG", "")
+run(tag + "post step, normal priority, 8 output sets (bench default)")
+run(tag + "no post step", post=False)
+run(tag + "no post step, 1 rollout stream", post=False, MRF_BENCH_NROLL=1)
+run(tag + "post step, high priority, 4 output sets", MRF_BENCH_PRIO=-1, MRF_BENCH_NBUF=4)
+run(tag + "post step, normal priority, 4 output sets", MRF_BENCH_NBUF=4)
+run(tag + "post = heuristic kernel only (no guard)", risk=False)
+tiny = torch.zeros(1024, device=dev)
+for n in (1, 6):
+    def only_tiny(*a, **k):
+        for _ in range(n):
+            tiny.add_(1.0)          # one 1-CTA kernel on the post stream
+    fab.rfcv_post_dev = only_tiny
+    bench._sweep(fab, torch, None, dev, 1, recs, works, H, 5, 3, True)
+    ts = [bench._sweep(fab, torch, None, dev, 1, recs, works, H, K, 5, True)["total_ms"] / K for _ in range(3)]
+    print(f"{tag}post = {n} empty kernel(s)                ms/step {min(ts):.4f}", flush=True)
